@@ -1,0 +1,398 @@
+// Gather-GEMM convolution on 5th-generation tensor cores (sm_100a).
+//
+//   out[pixel, j] = sum_{tap t} sum_{c < kc} A[n, h+h0+dh[t], w+w0+dw[t], c0[t]+c] * B[j][t*kc + c]
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer: per k-block (one tap x 64 channels) one 4-D box load of the
+//               activation tile {64 ch, TW, TH, 1} (implicit im2col: a spatial box shifted by the
+//               tap offset; out-of-range coordinates are zero-filled by TMA = zero padding) and
+//               one 2-D box load {64 k, BLOCK_N} of packed weights, 128-byte swizzled, into a
+//               STAGES-deep mbarrier ring.
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (pixels) x N=BLOCK_N x K=16,
+//               fp32 accumulators in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue
+//               of tile i overlaps the main loop of tile i+1.
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns), bias / ReLU, per-(image,channel)
+//               sum and sum-of-squares for InstanceNorm (butterfly shuffles -> smem -> one global
+//               atomic per column per tile), vector stores as NHWC / depth-to-space / NCHW fp32.
+#include "tc_common.cuh"
+
+#include <mutex>
+
+namespace fnst {
+
+PFN_tensorMapEncodeTiled tensor_map_encoder() {
+  static PFN_tensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(p);
+  });
+  return fn;
+}
+
+int encode_tensor_map_2b(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+  FNST_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  FNST_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    FNST_CHECK_ARG(strides_bytes[i] % 16 == 0, "TMA stride %d (%llu B) must be a multiple of 16", i, (unsigned long long)strides_bytes[i]);
+    gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FNST_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+struct ConvTcParams {
+  int32_t out_n, out_h, out_w;
+  int32_t tiles_w, tiles_h, tw_log2;
+  int32_t num_m_tiles, num_n_tiles, num_tiles;
+  int32_t num_kblocks, chunks_per_tap;
+  int32_t h0, w0;
+  int32_t epilogue, c_out, n_gemm, relu, out_is_bf16, out_is_f32;
+  uint32_t idesc;
+  void* out;
+  const float* bias;
+  float* stats;
+  int8_t tap_dh[FNST_MAX_TAPS];
+  int8_t tap_dw[FNST_MAX_TAPS];
+  int16_t tap_c0[FNST_MAX_TAPS];
+};
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;                       // 64 two-byte elements = one 128-byte swizzle row
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
+constexpr int TC_THREADS = 192;
+
+template <int BLOCK_N> struct TcCfg {
+  static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int CHUNK = BLOCK_N < 32 ? BLOCK_N : 32;     // epilogue column chunk
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <typename TOut>
+__device__ __forceinline__ void store_chunk(TOut* p, const float (&v)[32], int count) {
+  // count in {16, 32}; p is 32-byte aligned
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    if (i < count) {
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = v[i + k];
+      store8<TOut>(p + i, t);
+    }
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ ConvTcParams p) {
+  using Cfg = TcCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int CHUNK = Cfg::CHUNK;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  __shared__ float s_sum[BLOCK_N], s_sq[BLOCK_N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < BLOCK_N; i += TC_THREADS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int TW = 1 << p.tw_log2, TH = TC_BLOCK_M >> p.tw_log2;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        int m_tile = tile / p.num_n_tiles;
+        const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+        const int th = m_tile % p.tiles_h;
+        const int n = m_tile / p.tiles_h;
+        const int hb = th * TH + p.h0, wb = tw * TW + p.w0;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          const int t = kb / p.chunks_per_tap, ch = kb - t * p.chunks_per_tap;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + TC_A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, wb + p.tap_dw[t], hb + p.tap_dh[t], n);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, n_tile * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = umma_smem_desc(sa, 16, 1024);
+          const uint64_t db = umma_smem_desc(sa + TC_A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5 = 128 threads) =====================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;            // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int th = m_tile % p.tiles_h;
+      const int n = m_tile / p.tiles_h;
+      const int r = q * 32 + lane;
+      const int h = th * TH + (r >> p.tw_log2), w = tw * TW + (r & (TW - 1));
+      const bool valid = h < p.out_h && w < p.out_w;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
+
+#pragma unroll 1
+      for (int cb = 0; cb < BLOCK_N; cb += CHUNK) {
+        uint32_t raw[32];
+        if (CHUNK == 32) tmem_ld_x32(t_row + cb, raw); else tmem_ld_x16(t_row + cb, raw);
+        tmem_ld_wait();
+        if (cb + CHUNK >= BLOCK_N) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        const int col0 = n_tile * BLOCK_N + cb;           // first GEMM column of this chunk
+        if (col0 >= p.n_gemm) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = i < CHUNK ? __uint_as_float(raw[i]) : 0.f;
+
+        if (p.epilogue == FNST_EPI_NCHW_F32) {
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = col0 + j;
+              if (ch < p.c_out) {
+                float y = v[j] + (p.bias ? p.bias[ch] : 0.f);
+                o[(((size_t)n * p.c_out + ch) * p.out_h + h) * p.out_w + w] = y;
+              }
+            }
+          }
+          continue;
+        }
+
+        int ch0 = col0, phase_id = 0;
+        if (p.epilogue == FNST_EPI_D2S) { phase_id = col0 / p.c_out; ch0 = col0 - phase_id * p.c_out; }
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i) v[i] += p.bias[ch0 + i];
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (valid) {
+          size_t pix;
+          if (p.epilogue == FNST_EPI_D2S)
+            pix = ((size_t)n * (2 * p.out_h) + 2 * h + (phase_id >> 1)) * (size_t)(2 * p.out_w) + 2 * w + (phase_id & 1);
+          else
+            pix = ((size_t)n * p.out_h + h) * (size_t)p.out_w + w;
+          const size_t off = pix * p.c_out + ch0;
+          if (p.out_is_f32) store_chunk<float>(reinterpret_cast<float*>(p.out) + off, v, CHUNK);
+          else if (p.out_is_bf16) store_chunk<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, CHUNK);
+          else store_chunk<__half>(reinterpret_cast<__half*>(p.out) + off, v, CHUNK);
+        }
+        if (p.stats) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+          const float cs = warp_column_sums(v, lane);
+          const float cq = warp_column_sums(sq, lane);
+          if (lane < CHUNK) { atomicAdd(&s_sum[cb + lane], cs); atomicAdd(&s_sq[cb + lane], cq); }
+        }
+      }
+
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = et; c < BLOCK_N; c += 128) {
+          const int col = n_tile * BLOCK_N + c;
+          if (col < p.n_gemm) {
+            const int ch = p.epilogue == FNST_EPI_D2S ? col % p.c_out : col;
+            if (ch < p.c_out) {
+              atomicAdd(&p.stats[((size_t)n * p.c_out + ch) * 2 + 0], s_sum[c]);
+              atomicAdd(&p.stats[((size_t)n * p.c_out + ch) * 2 + 1], s_sq[c]);
+            }
+          }
+          s_sum[c] = 0.f; s_sq[c] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+int validate_conv_desc(const fnst_conv_desc* d);
+
+template <int BLOCK_N>
+static int launch_conv_tc(const CUtensorMap& ma, const CUtensorMap& mb, const ConvTcParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N>;
+  auto kern = conv_tc_kernel<BLOCK_N>;
+  FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  return launch_status("conv_tc");
+}
+
+static int device_sm_count(int device) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) return 148;
+  if (!cached[device]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+    cached[device] = v;
+  }
+  return cached[device];
+}
+
+}  // namespace fnst
+
+using namespace fnst;
+
+extern "C" int fnst_device_supports_tc(int device) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
+  if (int r = validate_conv_desc(d)) return r;
+  FNST_CHECK_ARG(d->dtype == FNST_F16 || d->dtype == FNST_BF16, "conv_tc: operands must be fp16 or bf16");
+  FNST_CHECK_ARG(d->kc % TC_BLOCK_K == 0, "conv_tc: kc %d must be a multiple of 64", d->kc);
+  FNST_CHECK_ARG(d->a_stride_w % 8 == 0 && d->a_stride_h % 8 == 0 && d->a_stride_n % 8 == 0, "conv_tc: A strides must be multiples of 8 elements");
+  FNST_CHECK_ARG(d->a_c % 8 == 0, "conv_tc: a_c must be a multiple of 8");
+  if (d->epilogue == FNST_EPI_D2S) FNST_CHECK_ARG(d->c_out % 32 == 0, "conv_tc: d2s needs c_out %% 32 == 0");
+  if (d->epilogue == FNST_EPI_NHWC) FNST_CHECK_ARG(d->c_out == d->n_gemm && (d->n_gemm == 16 || d->n_gemm % 32 == 0), "conv_tc: NHWC epilogue needs c_out == n_gemm, a multiple of 32 (or 16)");
+  if (d->epilogue == FNST_EPI_NCHW_F32) FNST_CHECK_ARG(d->c_out <= 16 && !d->stats && !d->relu, "conv_tc: NCHW epilogue supports c_out <= 16, no stats/relu");
+  FNST_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.out_n = d->out_n; p.out_h = d->out_h; p.out_w = d->out_w;
+  // pixel tile TH x TW = 128: wide tiles for wide images, never wider than needed
+  const int tw_log2 = d->out_w <= 8 ? 3 : 4;
+  p.tw_log2 = tw_log2;
+  const int TW = 1 << tw_log2, TH = TC_BLOCK_M >> tw_log2;
+  p.tiles_w = (d->out_w + TW - 1) / TW;
+  p.tiles_h = (d->out_h + TH - 1) / TH;
+  p.num_m_tiles = p.tiles_w * p.tiles_h * d->out_n;
+  const int num_sms = device_sm_count(device);
+
+  // column tile: largest that keeps the grid reasonably full
+  int block_n;
+  if (d->n_gemm <= 16) block_n = 16;
+  else if (d->n_gemm <= 32) block_n = 32;
+  else if (d->n_gemm <= 64 || d->n_gemm % 128 != 0) block_n = 64;
+  else if (d->n_gemm % 256 == 0 && (int64_t)p.num_m_tiles * (d->n_gemm / 256) >= num_sms) block_n = 256;
+  else if ((int64_t)p.num_m_tiles * (d->n_gemm / 128) >= num_sms) block_n = 128;
+  else block_n = 64;
+  FNST_CHECK_ARG(d->n_gemm % block_n == 0 || d->n_gemm < block_n, "conv_tc: n_gemm %d not tileable", d->n_gemm);
+  p.num_n_tiles = (d->n_gemm + block_n - 1) / block_n;
+  p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+  p.chunks_per_tap = d->kc / TC_BLOCK_K;
+  p.num_kblocks = d->ntaps * p.chunks_per_tap;
+  p.h0 = d->h0; p.w0 = d->w0;
+  p.epilogue = d->epilogue; p.c_out = d->c_out; p.n_gemm = d->n_gemm; p.relu = d->relu;
+  p.out_is_bf16 = d->out_dtype == FNST_BF16; p.out_is_f32 = d->out_dtype == FNST_F32;
+  p.idesc = umma_idesc_f16(d->dtype == FNST_BF16 ? 1 : 0, block_n, 0, 0);
+  p.out = d->out; p.bias = d->bias; p.stats = d->stats;
+  memcpy(p.tap_dh, d->tap_dh, sizeof(p.tap_dh));
+  memcpy(p.tap_dw, d->tap_dw, sizeof(p.tap_dw));
+  memcpy(p.tap_c0, d->tap_c0, sizeof(p.tap_c0));
+
+  CUtensorMap ma, mb;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->a_c, (uint64_t)d->a_w, (uint64_t)d->a_h, (uint64_t)d->a_n};
+    const uint64_t str[3] = {(uint64_t)d->a_stride_w * 2, (uint64_t)d->a_stride_h * 2, (uint64_t)d->a_stride_n * 2};
+    const uint32_t box[4] = {TC_BLOCK_K, (uint32_t)TW, (uint32_t)TH, 1};
+    if (int r = encode_tensor_map_2b(&ma, d->a, 4, dims, str, box)) return r;
+  }
+  {
+    const uint64_t ktot = (uint64_t)d->ntaps * d->kc;
+    const uint64_t dims[2] = {ktot, (uint64_t)d->n_gemm};
+    const uint64_t str[1] = {ktot * 2};
+    const uint32_t box[2] = {TC_BLOCK_K, (uint32_t)block_n};
+    if (int r = encode_tensor_map_2b(&mb, d->b, 2, dims, str, box)) return r;
+  }
+  if (d->stats) FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
+  switch (block_n) {
+    case 16: return launch_conv_tc<16>(ma, mb, p, num_sms, st);
+    case 32: return launch_conv_tc<32>(ma, mb, p, num_sms, st);
+    case 64: return launch_conv_tc<64>(ma, mb, p, num_sms, st);
+    case 128: return launch_conv_tc<128>(ma, mb, p, num_sms, st);
+    default: return launch_conv_tc<256>(ma, mb, p, num_sms, st);
+  }
+}

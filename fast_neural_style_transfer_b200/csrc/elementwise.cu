@@ -1,0 +1,242 @@
+// HBM-bound kernels of the style-transfer path: InstanceNorm apply (+ReLU, dropout scale,
+// residual add, halo write), 2x2 max-pool, squared-error and total-variation reductions,
+// NHWC<->NCHW layout conversion.  All use 16/32-byte vector accesses on the channel dimension.
+#include "common.cuh"
+
+namespace fnst {
+
+// -------------------------------------------------------------------------------------------
+// InstanceNorm apply.  One block per (padded output row, image).  256 threads = CG channel
+// groups of 8 channels x PL pixel lanes; per-channel scale/shift are computed once per thread.
+// -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) inorm_apply_kernel(const T* __restrict__ raw, const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ drop, const T* __restrict__ res, int res_pad,
+                                                          T* __restrict__ out, int H, int W, int C, int relu, float eps,
+                                                          int pad, int pad_mode, int s2d) {
+  const int n = blockIdx.y, hp = blockIdx.x;
+  const int CG = C >> 3, PL = 256 / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  if (pl >= PL) return;
+  const int c0 = cg * 8;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+
+  float a[8], b[8];
+  {
+    const float inv_cnt = 1.f / (float)(H * W);
+    const float* st = stats + ((size_t)n * C + c0) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float mean = st[2 * i] * inv_cnt;
+      const float var = fmaxf(st[2 * i + 1] * inv_cnt - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float ai = gamma[c0 + i] * rstd;
+      float bi = beta[c0 + i] - mean * ai;
+      if (drop) { const float ds = drop[(size_t)n * C + c0 + i]; ai *= ds; bi *= ds; }
+      a[i] = ai; b[i] = bi;
+    }
+  }
+
+  int sh = hp - pad;
+  bool row_zero = false;
+  if (sh < 0 || sh >= H) {
+    if (pad_mode == FNST_PAD_REFLECT) sh = reflect_index(sh, H); else row_zero = true;
+  }
+  const int Hp2 = (Hp + 1) >> 1, Wp2 = (Wp + 1) >> 1;
+  for (int wp = pl; wp < Wp; wp += PL) {
+    int sw = wp - pad;
+    bool zero = row_zero;
+    if (sw < 0 || sw >= W) {
+      if (pad_mode == FNST_PAD_REFLECT) sw = reflect_index(sw, W); else zero = true;
+    }
+    float v[8];
+    if (zero) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    } else {
+      load8<T>(raw + (((size_t)n * H + sh) * W + sw) * C + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(v[i], a[i], b[i]);
+        v[i] = relu ? fmaxf(y, 0.f) : y;
+      }
+      if (res) {
+        float r[8];
+        load8<T>(res + (((size_t)n * (H + 2 * res_pad) + sh + res_pad) * (W + 2 * res_pad) + sw + res_pad) * C + c0, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
+      }
+    }
+    T* dst;
+    if (!s2d) dst = out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0;
+    else dst = out + (((size_t)n * Hp2 + (hp >> 1)) * Wp2 + (wp >> 1)) * (4 * C) + ((hp & 1) * 2 + (wp & 1)) * C + c0;
+    store8<T>(dst, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                       int N, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, CG = C >> 3;
+  const size_t total = (size_t)N * Ho * Wo * CG;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cg = i % CG; size_t r = i / CG;
+    const int wo = r % Wo; r /= Wo;
+    const int ho = r % Ho; const int n = r / Ho;
+    const T* p = in + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + cg * 8;
+    float v0[8], v1[8], v2[8], v3[8];
+    load8<T>(p, v0); load8<T>(p + C, v1); load8<T>(p + (size_t)W * C, v2); load8<T>(p + (size_t)W * C + C, v3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v0[k] = fmaxf(fmaxf(v0[k], v1[k]), fmaxf(v2[k], v3[k]));
+    store8<T>(out + (((size_t)n * Ho + ho) * Wo + wo) * C + cg * 8, v0);
+  }
+}
+
+__device__ __forceinline__ void block_accumulate(float v, double* acc) {
+  __shared__ float s_part[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < (blockDim.x >> 5) ? s_part[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(acc, (double)t);
+  }
+}
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) sse_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t count,
+                                                  int64_t period, double* acc) {
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = to_f32<TA>(a[i]) - to_f32<TB>(b[i % period]);
+    s = fmaf(d, d, s);
+  }
+  block_accumulate(s, acc);
+}
+
+__global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ img, int planes, int H, int W, double* acc) {
+  const int64_t total = (int64_t)planes * H * W;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = i % W; const int y = (i / W) % H;
+    const float v = img[i];
+    if (y + 1 < H) { const float d = img[i + W] - v; s = fmaf(d, d, s); }
+    if (x + 1 < W) { const float d = img[i + 1] - v; s = fmaf(d, d, s); }
+  }
+  block_accumulate(s, acc);
+}
+
+// [HW][C] (T) <-> [C][HW] (fp32) per image, 32x32 smem tiles.
+template <typename T, bool TO_NCHW>
+__global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__ in_, void* __restrict__ out_, int HW, int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  if (TO_NCHW) {
+    const T* in = reinterpret_cast<const T*>(in_) + (size_t)n * HW * C;
+    float* out = reinterpret_cast<float*>(out_) + (size_t)n * HW * C;
+    for (int r = ty; r < 32; r += 8) {
+      const int p = p0 + r, c = c0 + tx;
+      tile[r][tx] = (p < HW && c < C) ? to_f32<T>(in[(size_t)p * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int c = c0 + r, p = p0 + tx;
+      if (p < HW && c < C) out[(size_t)c * HW + p] = tile[tx][r];
+    }
+  } else {
+    const float* in = reinterpret_cast<const float*>(in_) + (size_t)n * HW * C;
+    T* out = reinterpret_cast<T*>(out_) + (size_t)n * HW * C;
+    for (int r = ty; r < 32; r += 8) {
+      const int c = c0 + r, p = p0 + tx;
+      tile[r][tx] = (p < HW && c < C) ? in[(size_t)c * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int p = p0 + r, c = c0 + tx;
+      if (p < HW && c < C) out[(size_t)p * C + c] = from_f32<T>(tile[tx][r]);
+    }
+  }
+}
+
+static int grid_for(int64_t work_items, int threads = 256) {
+  int64_t b = (work_items + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace fnst
+
+using namespace fnst;
+
+extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, const float* beta,
+                                const float* drop, const void* res, int res_pad, void* out,
+                                int n, int h, int w, int c, int dtype, int relu, float eps,
+                                int pad, int pad_mode, int s2d, int device, void* stream) {
+  FNST_CHECK_ARG(raw && stats && gamma && beta && out, "inorm_apply: null pointer");
+  FNST_CHECK_ARG(n > 0 && h > 0 && w > 0, "inorm_apply: empty tensor");
+  FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_apply: unsupported channel count %d", c);
+  FNST_CHECK_ARG(pad >= 0 && (pad == 0 || pad_mode == FNST_PAD_REFLECT || pad_mode == FNST_PAD_ZERO), "inorm_apply: bad pad mode");
+  if (pad_mode == FNST_PAD_REFLECT) FNST_CHECK_ARG(h > pad && w > pad, "inorm_apply: reflect pad %d needs h,w > pad (got %dx%d)", pad, h, w);
+  FNST_CHECK_ARG(!(s2d && res), "inorm_apply: residual with space-to-depth output unsupported");
+  FNST_CUDA(cudaSetDevice(device));
+  dim3 grid(h + 2 * pad, n);
+  FNST_DISPATCH_DTYPE(dtype, T, {
+    inorm_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const T*>(raw), stats, gamma, beta, drop, reinterpret_cast<const T*>(res), res_pad,
+        reinterpret_cast<T*>(out), h, w, c, relu, eps, pad, pad_mode, s2d);
+  });
+  return launch_status("inorm_apply");
+}
+
+extern "C" int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream) {
+  FNST_CHECK_ARG(in && out, "maxpool2: null pointer");
+  FNST_CHECK_ARG(c % 8 == 0 && h >= 2 && w >= 2, "maxpool2: unsupported shape");
+  FNST_CUDA(cudaSetDevice(device));
+  const int64_t items = (int64_t)n * (h / 2) * (w / 2) * (c / 8);
+  FNST_DISPATCH_DTYPE(dtype, T, {
+    maxpool2_kernel<T><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(in),
+                                                                        reinterpret_cast<T*>(out), n, h, w, c);
+  });
+  return launch_status("maxpool2");
+}
+
+extern "C" int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
+                        double* acc, int device, void* stream) {
+  FNST_CHECK_ARG(a && b && acc && count > 0 && b_period > 0, "sse: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  FNST_DISPATCH_DTYPE(dtype_a, TA, {
+    FNST_DISPATCH_DTYPE(dtype_b, TB, {
+      sse_kernel<TA, TB><<<grid_for(count / 4), 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const TA*>(a), reinterpret_cast<const TB*>(b), count, b_period, acc);
+    });
+  });
+  return launch_status("sse");
+}
+
+extern "C" int fnst_tv(const float* img, int planes, int h, int w, double* acc, int device, void* stream) {
+  FNST_CHECK_ARG(img && acc && planes > 0 && h > 0 && w > 0, "tv: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  tv_kernel<<<grid_for((int64_t)planes * h * w / 4), 256, 0, (cudaStream_t)stream>>>(img, planes, h, w, acc);
+  return launch_status("tv");
+}
+
+extern "C" int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w, int c, int dtype, int device, void* stream) {
+  FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0, "nhwc_to_nchw: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
+  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c); });
+  return launch_status("nhwc_to_nchw");
+}
+
+extern "C" int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream) {
+  FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0, "nchw_to_nhwc: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
+  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c); });
+  return launch_status("nchw_to_nhwc");
+}

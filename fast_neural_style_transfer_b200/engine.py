@@ -1,0 +1,289 @@
+"""Forward plans for the style-transfer hot path: weight packing, halo-buffer management and the
+operator sequence of StyleTransferNet (models/model.py:49-65) and VGG-19 features[0:25]
+(models/vgg19_net.py:56-65) expressed in libfnst operators.
+
+Two precisions share the same plan:
+  "fp16"/"bf16"  tcgen05 tensor-core path: 2-byte NHWC activations, fp32 accumulation/statistics
+  "fp32"         CUDA-core path: fp32 NHWC activations (the 1e-4 parity path)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import EPI_NHWC, EPI_D2S, EPI_NCHW_F32, PAD_NONE, PAD_REFLECT, PAD_ZERO
+from .ops import ConvSpec
+
+PRECISIONS = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def act_dtype(precision: str) -> torch.dtype:
+    if precision not in PRECISIONS:
+        raise ValueError(f"unknown precision {precision!r}; expected one of {sorted(PRECISIONS)}")
+    return PRECISIONS[precision]
+
+
+# ---------------------------------------------------------------------------------------------
+# Weight packing: PyTorch parameter layouts -> gather-GEMM B operands [n_gemm, ntaps*kc]
+# ---------------------------------------------------------------------------------------------
+
+def taps_kxk(k: int, origin: int = 0) -> List[Tuple[int, int, int]]:
+    return [(kh + origin, kw + origin, 0) for kh in range(k) for kw in range(k)]
+
+
+def pack_conv(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Conv2d weight (O, C, k, k) -> (O, k*k*C), K index = (kh*k + kw)*C + c."""
+    o, c, k, _ = w.shape
+    return w.permute(0, 2, 3, 1).reshape(o, k * k * c).to(dtype).contiguous()
+
+
+def taps_s2d_3x3(c_in: int) -> List[Tuple[int, int, int]]:
+    """3x3 stride-2 conv on a space-to-depth halo buffer: tap (kh,kw) reads spatial offset
+    (kh>>1, kw>>1) of phase (kh&1, kw&1), i.e. channel window ((kh&1)*2 + (kw&1)) * c_in."""
+    return [(kh >> 1, kw >> 1, ((kh & 1) * 2 + (kw & 1)) * c_in) for kh in range(3) for kw in range(3)]
+
+
+TAPS_2X2 = [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)]
+# ConvTranspose2d(k=3, s=2, p=1, op=1): output row 2i+ph takes input row i+dh with kernel row _KT[ph][dh]
+_KT = {0: {0: 1}, 1: {0: 2, 1: 0}}
+
+
+def pack_conv_transpose(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """ConvTranspose2d weight (Cin, Cout, 3, 3) -> (4*Cout, 4*Cin): row (ph*2+pw)*Cout + o,
+    K index (dh*2+dw)*Cin + c; unused (phase, tap) pairs stay zero (models/model.py:13-19)."""
+    cin, cout = w.shape[0], w.shape[1]
+    b = torch.zeros((2, 2, cout, 2, 2, cin), dtype=w.dtype, device=w.device)
+    for ph in (0, 1):
+        for dh, kh in _KT[ph].items():
+            for pw in (0, 1):
+                for dw, kw in _KT[pw].items():
+                    b[ph, pw, :, dh, dw, :] = w[:, :, kh, kw].t()
+    return b.reshape(4 * cout, 4 * cin).to(dtype).contiguous()
+
+
+def taps_final_pairs() -> List[Tuple[int, int, int]]:
+    return [(kh, 2 * j, 0) for kh in range(9) for j in range(5)]
+
+
+def pack_final_pairs(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """final_conv weight (3, 32, 9, 9) -> (16, 45*64): the activation view pairs two adjacent
+    pixels (64 = 2 x 32 channels) per tap so that every K block is a full 128-byte row; the
+    phantom tap kw = 9 and output rows 3..15 are zero."""
+    o, c, k, _ = w.shape
+    assert (c, k) == (32, 9) and o <= 16
+    b = torch.zeros((16, 9, 5, 2, 32), dtype=w.dtype, device=w.device)
+    for j in range(5):
+        for jj in range(2):
+            kw = 2 * j + jj
+            if kw < 9:
+                b[:o, :, j, jj, :] = w[:, :, :, kw].permute(0, 2, 1)
+    return b.reshape(16, 45 * 64).to(dtype).contiguous()
+
+
+def pack_final_plain(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    o = w.shape[0]
+    b = torch.zeros((16, w.shape[2] * w.shape[3] * w.shape[1]), dtype=w.dtype, device=w.device)
+    b[:o] = w.permute(0, 2, 3, 1).reshape(o, -1)
+    return b.to(dtype).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# StyleTransferNet
+# ---------------------------------------------------------------------------------------------
+
+def _half_up(v: int) -> int:
+    return (v + 1) // 2
+
+
+def _nhwc_strides(t: torch.Tensor) -> Tuple[int, int, int]:
+    n, h, w, c = t.shape
+    return (h * w * c, w * c, c)
+
+
+class StyleNetPlan:
+    """Packed weights + forward for one parameter set.  `params` maps the reference state-dict
+    names (models/model.py:25-47) to CUDA tensors; re-pack (cheap) after every optimizer step."""
+
+    def __init__(self, precision: str = "fp16"):
+        self.precision = precision
+        self.dtype = act_dtype(precision)
+        self.use_tc = precision != "fp32"
+        self.w: Dict[str, torch.Tensor] = {}
+        self.params: Dict[str, torch.Tensor] = {}
+
+    # -- weights ---------------------------------------------------------------------------------
+    def pack(self, params: Dict[str, torch.Tensor]) -> "StyleNetPlan":
+        p = {k: v.detach() for k, v in params.items()}
+        self.params = p
+        dt = self.dtype
+        w = {"conv1": p["conv1.conv.weight"].float().contiguous(),
+             "conv2": pack_conv(p["conv2.conv.weight"], dt)}
+        for i in range(5):
+            w[f"res{i}a"] = pack_conv(p[f"res_blocks.{i}.conv1.conv.weight"], dt)
+            w[f"res{i}b"] = pack_conv(p[f"res_blocks.{i}.conv2.conv.weight"], dt)
+        w["up1"] = pack_conv_transpose(p["up1.upsample_conv.weight"], dt)
+        w["up2"] = pack_conv_transpose(p["up2.upsample_conv.weight"], dt)
+        w["final"] = (pack_final_pairs if self.use_tc else pack_final_plain)(p["final_conv.conv.weight"], dt)
+        self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
+        self.final_bias[:3] = p["final_conv.conv.bias"].float()
+        self.w = w
+        return self
+
+    def _affine(self, name: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.params[name + ".weight"].float().contiguous(), self.params[name + ".bias"].float().contiguous()
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, drop_scales: Optional[Sequence[torch.Tensor]] = None,
+                tape: Optional[dict] = None) -> torch.Tensor:
+        """x: (B,3,H,W) fp32 CUDA.  Returns (B,3,H',W') fp32, H' = 4*ceil(ceil(H/2)/2).
+        Conv biases in front of an InstanceNorm are mathematically cancelled by the mean
+        subtraction and are skipped; final_conv's bias is applied."""
+        assert x.dim() == 4 and x.shape[1] == 3
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        dev, dt, tc = x.device, self.dtype, self.use_tc
+        w = self.w
+        new = lambda *s: torch.empty(s, dtype=dt, device=dev)
+        stats = lambda c: torch.empty((B, c, 2), dtype=torch.float32, device=dev)
+        if H <= 4 or W <= 4:
+            raise RuntimeError("StyleTransferNet needs H, W >= 5 (ReflectionPad2d(4))")
+
+        # conv1: 9x9 stride 2, reflect 4 -> raw1 (B,H1,W1,64)
+        H1, W1 = _half_up(H), _half_up(W)
+        raw1, st1 = new(B, H1, W1, 64), stats(64)
+        ops.conv_first(x, w["conv1"], None, 9, 2, 4, PAD_REFLECT, False, raw1, st1)
+        # norm1 + relu -> space-to-depth halo buffer for the stride-2 conv2
+        Hp, Wp = H1 + 2, W1 + 2
+        Hs, Ws = _half_up(Hp), _half_up(Wp)
+        buf2 = torch.zeros((B, Hs, Ws, 256), dtype=dt, device=dev)
+        g, b = self._affine("norm1")
+        ops.inorm_apply(raw1, st1, g, b, buf2, relu=True, pad=1, pad_mode=PAD_REFLECT, s2d=True)
+        # conv2: 3x3 stride 2 as a 9-tap gather over the s2d buffer
+        H2, W2 = _half_up(H1), _half_up(W1)
+        raw2, st2 = new(B, H2, W2, 256), stats(256)
+        spec = ConvSpec(taps_s2d_3x3(64), 64, w["conv2"], 256, 256)
+        ops.conv_gather(spec, buf2, (B, Hs, Ws, 256), _nhwc_strides(buf2), raw2, (H2, W2), st2, tc)
+        cur = new(B, H2 + 2, W2 + 2, 256)
+        g, b = self._affine("norm2")
+        ops.inorm_apply(raw2, st2, g, b, cur, relu=True, pad=1, pad_mode=PAD_REFLECT)
+        if tape is not None:
+            tape.update(raw1=raw1, st1=st1, buf2=buf2, raw2=raw2, st2=st2, trunk=[cur])
+
+        # residual trunk
+        taps9 = taps_kxk(3)
+        for i in range(5):
+            raw_a, st_a = new(B, H2, W2, 256), stats(256)
+            ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}a"], 256, 256), cur, (B, H2 + 2, W2 + 2, 256),
+                            _nhwc_strides(cur), raw_a, (H2, W2), st_a, tc)
+            mid = new(B, H2 + 2, W2 + 2, 256)
+            g, b = self._affine(f"res_blocks.{i}.in1")
+            drop = None if drop_scales is None else drop_scales[i].float().contiguous()
+            ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop)
+            raw_b, st_b = new(B, H2, W2, 256), stats(256)
+            ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}b"], 256, 256), mid, (B, H2 + 2, W2 + 2, 256),
+                            _nhwc_strides(mid), raw_b, (H2, W2), st_b, tc)
+            last = i == 4
+            nxt = new(B, H2, W2, 256) if last else new(B, H2 + 2, W2 + 2, 256)
+            g, b = self._affine(f"res_blocks.{i}.in2")
+            ops.inorm_apply(raw_b, st_b, g, b, nxt, relu=False, pad=0 if last else 1,
+                            pad_mode=PAD_NONE if last else PAD_REFLECT, res=cur, res_pad=1)
+            if tape is not None:
+                tape.setdefault("blocks", []).append(dict(raw_a=raw_a, st_a=st_a, mid=mid, raw_b=raw_b, st_b=st_b, drop=drop))
+                tape["trunk"].append(nxt)
+            cur = nxt
+
+        # up1: ConvTranspose2d(256->64) = 2x2-tap gather, 256 columns, depth-to-space
+        H3, W3 = 2 * H2, 2 * W2
+        raw3, st3 = new(B, H3, W3, 64), stats(64)
+        ops.conv_gather(ConvSpec(TAPS_2X2, 256, w["up1"], 256, 64, epilogue=EPI_D2S), cur, (B, H2, W2, 256),
+                        _nhwc_strides(cur), raw3, (H2, W2), st3, tc)
+        act3 = new(B, H3, W3, 64)
+        g, b = self._affine("norm3")
+        ops.inorm_apply(raw3, st3, g, b, act3, relu=True)
+        # up2: ConvTranspose2d(64->32)
+        H4, W4 = 2 * H3, 2 * W3
+        raw4, st4 = new(B, H4, W4, 32), stats(32)
+        ops.conv_gather(ConvSpec(TAPS_2X2, 64, w["up2"], 128, 32, epilogue=EPI_D2S), act3, (B, H3, W3, 64),
+                        _nhwc_strides(act3), raw4, (H3, W3), st4, tc)
+        # norm4 + relu -> reflect-4 halo buffer (+ slack so the paired view of the last pixel stays in bounds)
+        Hq, Wq = H4 + 8, W4 + 8
+        flat = torch.empty(B * Hq * Wq * 32 + 64, dtype=dt, device=dev)
+        flat[-64:].zero_()
+        act4 = flat[:B * Hq * Wq * 32].view(B, Hq, Wq, 32)
+        g, b = self._affine("norm4")
+        ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT)
+        # final_conv 9x9 -> NCHW fp32
+        y = torch.empty((B, 3, H4, W4), dtype=torch.float32, device=dev)
+        if tc:
+            spec = ConvSpec(taps_final_pairs(), 64, w["final"], 16, 3, epilogue=EPI_NCHW_F32, bias=self.final_bias)
+            ops.conv_gather(spec, act4, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), y, (H4, W4), None, True)
+        else:
+            spec = ConvSpec(taps_kxk(9), 32, w["final"], 16, 3, epilogue=EPI_NCHW_F32, bias=self.final_bias)
+            ops.conv_gather(spec, act4, (B, Hq, Wq, 32), _nhwc_strides(act4), y, (H4, W4), None, False)
+        if tape is not None:
+            tape.update(raw3=raw3, st3=st3, act3=act3, raw4=raw4, st4=st4, act4=act4, x=x)
+        return y
+
+
+# ---------------------------------------------------------------------------------------------
+# VGG-19 features[0:25]
+# ---------------------------------------------------------------------------------------------
+
+VGG_LAYERS = ("slice1.0", "slice1.2", "slice2.5", "slice2.7", "slice3.10", "slice3.12", "slice3.14",
+              "slice4.16", "slice4.19", "slice4.21", "slice5.23")
+
+
+class VGGPlan:
+    """Frozen VGG-19 feature stack.  forward() returns the five NHWC feature maps
+    [relu1_2, relu2_2, relu3_3, relu4_2, relu4_3] (models/vgg19_net.py:56-65; element 3 is
+    observed post-ReLU because torchvision's ReLUs are in-place)."""
+
+    def __init__(self, precision: str = "fp16"):
+        self.precision = precision
+        self.dtype = act_dtype(precision)
+        self.use_tc = precision != "fp32"
+        self.w: Dict[str, torch.Tensor] = {}
+        self.b: Dict[str, torch.Tensor] = {}
+
+    def pack(self, params: Dict[str, torch.Tensor]) -> "VGGPlan":
+        for name in VGG_LAYERS:
+            wt = params[name + ".weight"].detach()
+            self.b[name] = params[name + ".bias"].detach().float().contiguous()
+            self.w[name] = wt.float().contiguous() if name == "slice1.0" else pack_conv(wt, self.dtype)
+        return self
+
+    def _conv(self, name: str, a: torch.Tensor, tape: Optional[dict]) -> torch.Tensor:
+        B, H, W, C = a.shape
+        cout = self.w[name].shape[0]
+        out = torch.empty((B, H, W, cout), dtype=self.dtype, device=a.device)
+        spec = ConvSpec(taps_kxk(3), C, self.w[name], cout, cout, h0=-1, w0=-1, bias=self.b[name], relu=True)
+        ops.conv_gather(spec, a, (B, H, W, C), _nhwc_strides(a), out, (H, W), None, self.use_tc)
+        if tape is not None:
+            tape[name] = (a, out)
+        return out
+
+    def forward(self, x: torch.Tensor, tape: Optional[dict] = None) -> List[torch.Tensor]:
+        assert x.dim() == 4 and x.shape[1] == 3
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        if H < 8 or W < 8:
+            raise RuntimeError("VGG19 feature stack needs H, W >= 8 (three 2x2 max-pools)")
+        h = torch.empty((B, H, W, 64), dtype=self.dtype, device=x.device)
+        ops.conv_first(x, self.w["slice1.0"], self.b["slice1.0"], 3, 1, 1, PAD_ZERO, True, h, None)
+        if tape is not None:
+            tape["x"] = x
+            tape["slice1.0"] = (x, h)
+        f0 = self._conv("slice1.2", h, tape)
+        h = self._conv("slice2.7", self._conv("slice2.5", ops.maxpool2(f0), tape), tape)
+        f1 = h
+        h = ops.maxpool2(f1)
+        h = self._conv("slice3.14", self._conv("slice3.12", self._conv("slice3.10", h, tape), tape), tape)
+        f2 = h
+        h = self._conv("slice4.16", f2, tape)
+        h = self._conv("slice4.21", self._conv("slice4.19", ops.maxpool2(h), tape), tape)
+        f3 = h
+        f4 = self._conv("slice5.23", f3, tape)
+        return [f0, f1, f2, f3, f4]

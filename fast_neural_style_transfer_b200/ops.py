@@ -1,0 +1,162 @@
+"""Operator wrappers: torch tensors in, libfnst launches on torch's current CUDA stream.
+
+Layouts (see include/fnst.h): activations are NHWC tensors of the path's element type
+(torch.float32 for the CUDA-core fp32 path, torch.float16 / bfloat16 for the tcgen05 path);
+`ConvSpec` carries the tap table and packed weights of one gather-GEMM convolution.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ConvDesc
+
+_DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+# launches issued through this module since import (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def dt(t: torch.dtype) -> int:
+    return _DT[t]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _ctx(t: torch.Tensor) -> Tuple[int, C.c_void_p]:
+    if not t.is_cuda:
+        raise RuntimeError("libfnst operators need CUDA tensors (no CPU fallback)")
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return dev, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+@dataclass
+class ConvSpec:
+    """One gather-GEMM convolution: taps (dh, dw, c0), channels per tap, packed weights [n_gemm, ntaps*kc]."""
+    taps: Sequence[Tuple[int, int, int]]
+    kc: int
+    weight: torch.Tensor
+    n_gemm: int
+    c_out: int
+    h0: int = 0
+    w0: int = 0
+    epilogue: int = _lib.EPI_NHWC
+    bias: Optional[torch.Tensor] = None
+    relu: bool = False
+
+
+def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, int], a_strides: Tuple[int, int, int],
+                out: torch.Tensor, out_hw: Tuple[int, int], stats: Optional[torch.Tensor], use_tc: bool) -> None:
+    """a_dims = (n, h, w, c) logical extents of the activation view; a_strides = (n, h, w) element strides."""
+    d = ConvDesc()
+    n, ah, aw, ac = a_dims
+    d.a = a.data_ptr()
+    d.a_stride_n, d.a_stride_h, d.a_stride_w = a_strides
+    d.a_n, d.a_h, d.a_w, d.a_c = n, ah, aw, ac
+    d.ntaps, d.kc = len(spec.taps), spec.kc
+    d.h0, d.w0 = spec.h0, spec.w0
+    for i, (dh, dw, c0) in enumerate(spec.taps):
+        d.tap_dh[i], d.tap_dw[i], d.tap_c0[i] = dh, dw, c0
+    assert spec.weight.is_contiguous() and spec.weight.shape == (spec.n_gemm, len(spec.taps) * spec.kc), spec.weight.shape
+    assert spec.weight.dtype == a.dtype
+    d.b = spec.weight.data_ptr()
+    d.n_gemm = spec.n_gemm
+    d.out_n, d.out_h, d.out_w = n, out_hw[0], out_hw[1]
+    d.epilogue, d.c_out, d.relu = spec.epilogue, spec.c_out, int(spec.relu)
+    d.dtype = dt(a.dtype)
+    d.out_dtype = dt(out.dtype)
+    d.out = out.data_ptr()
+    d.bias = None if spec.bias is None else spec.bias.data_ptr()
+    d.stats = None if stats is None else stats.data_ptr()
+    dev, st = _ctx(a)
+    fn = lib.fnst_conv_tc if use_tc else lib.fnst_conv_simt
+    check(fn(C.byref(d), dev, st), "conv_tc" if use_tc else "conv_simt")
+    _count(2 if stats is not None else 1)
+
+
+def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, pad: int,
+               pad_mode: int, relu: bool, out: torch.Tensor, stats: Optional[torch.Tensor]) -> None:
+    n, c, h, w = x.shape
+    assert c == 3 and x.dtype == torch.float32 and x.is_contiguous()
+    assert weight.dtype == torch.float32 and weight.is_contiguous()
+    dev, st = _ctx(x)
+    check(lib.fnst_conv_first(_ptr(x), n, h, w, _ptr(weight), _ptr(bias), weight.shape[0], k, stride, pad, pad_mode,
+                              int(relu), _ptr(out), dt(out.dtype), _ptr(stats), dev, st), "conv_first")
+    _count(2 if stats is not None else 1)
+
+
+def inorm_apply(raw: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
+                relu: bool, pad: int = 0, pad_mode: int = _lib.PAD_NONE, s2d: bool = False,
+                drop: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, res_pad: int = 0,
+                eps: float = 1e-5) -> None:
+    n, h, w, c = raw.shape
+    dev, st = _ctx(raw)
+    check(lib.fnst_inorm_apply(_ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(res), res_pad, _ptr(out),
+                               n, h, w, c, dt(raw.dtype), int(relu), eps, pad, pad_mode, int(s2d), dev, st), "inorm_apply")
+    _count()
+
+
+def maxpool2(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+    dev, st = _ctx(x)
+    check(lib.fnst_maxpool2(_ptr(x), _ptr(out), n, h, w, c, dt(x.dtype), dev, st), "maxpool2")
+    _count()
+    return out
+
+
+def gram(feat_nhwc: torch.Tensor, use_tc: bool) -> torch.Tensor:
+    n, h, w, c = feat_nhwc.shape
+    assert feat_nhwc.is_contiguous()
+    out = torch.empty((n, c, c), dtype=torch.float32, device=feat_nhwc.device)
+    dev, st = _ctx(feat_nhwc)
+    check(lib.fnst_gram(_ptr(feat_nhwc), _ptr(out), n, h * w, c, dt(feat_nhwc.dtype), int(use_tc), dev, st), "gram")
+    _count(2)
+    return out
+
+
+def sse(a: torch.Tensor, b: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc (float64 scalar tensor) += sum (a - b)^2 ; b is broadcast with period b.numel()."""
+    assert a.is_contiguous() and b.is_contiguous() and acc.dtype == torch.float64
+    assert a.numel() % b.numel() == 0
+    dev, st = _ctx(a)
+    check(lib.fnst_sse(_ptr(a), _ptr(b), a.numel(), b.numel(), dt(a.dtype), dt(b.dtype), _ptr(acc), dev, st), "sse")
+    _count()
+
+
+def tv(img: torch.Tensor, acc: torch.Tensor) -> None:
+    b, c, h, w = img.shape
+    assert img.dtype == torch.float32 and img.is_contiguous() and acc.dtype == torch.float64
+    dev, st = _ctx(img)
+    check(lib.fnst_tv(_ptr(img), b * c, h, w, _ptr(acc), dev, st), "tv")
+    _count()
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    dev, st = _ctx(x)
+    check(lib.fnst_nhwc_to_nchw(_ptr(x), _ptr(out), n, h, w, c, dt(x.dtype), dev, st), "nhwc_to_nchw")
+    _count()
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+    dev, st = _ctx(x)
+    check(lib.fnst_nchw_to_nhwc(_ptr(x), _ptr(out), n, h, w, c, dt(dtype), dev, st), "nchw_to_nhwc")
+    _count()
+    return out

@@ -1,0 +1,137 @@
+/*
+ * fnst.h -- C ABI of libfnst.so: hand-written sm_100a kernels for the style-transfer hot path.
+ *
+ * The reference (HajarHAMDOUCH01/Fast-neural-style-transfer) is pure Python and has no FFI; its
+ * boundary for this path is a set of Python symbols.  Each entry point
+ * below is the native operator that the drop-in Python symbol binds through ctypes; the
+ * reference construct it replaces is cited as file:line into the reference tree.
+ *
+ * Conventions
+ *   - extern "C", POD arguments only: raw device pointers, ints, one POD descriptor struct.
+ *   - All device memory is caller-owned (torch-allocated); the library never allocates, frees or
+ *     retains device pointers across calls.
+ *   - Every launch is asynchronous on `stream` of CUDA device `device`; no hidden sync.
+ *   - Return 0 on success, <0 for argument/shape/alignment errors, >0 = cudaError_t.
+ *     fnst_last_error() returns a thread-local message.  There is no fallback path: an
+ *     unsupported configuration is an error.
+ *   - Activations are NHWC ("pixel-major") tensors of element type FNST_F32 / FNST_F16 /
+ *     FNST_BF16.  Reflection padding is materialised by the producer as a halo in the
+ *     consumer's buffer, so every convolution is a stride-1 "valid" gather-GEMM:
+ *         out[n,h,w,j] = sum_t sum_{c<kc} A[n, h+h0+dh[t], w+w0+dw[t], c0[t]+c] * B[j][t*kc+c]
+ *     with out-of-range A coordinates reading as zero (TMA out-of-bounds fill).  Stride-2
+ *     convolutions read a space-to-depth halo buffer; transposed convolutions are 2x2-tap
+ *     gather-GEMMs with 4*C_out columns and a depth-to-space epilogue.
+ */
+#ifndef FNST_H_
+#define FNST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNST_MAX_TAPS 96
+
+enum { FNST_F32 = 0, FNST_F16 = 1, FNST_BF16 = 2 };
+
+/* conv epilogues */
+enum {
+  FNST_EPI_NHWC = 0,   /* out[n,h,w,j], j < c_out; optional bias, relu, per-(n,c) sum/sumsq      */
+  FNST_EPI_D2S = 1,    /* j = (ph*2+pw)*c_out + o  ->  out[n,2h+ph,2w+pw,o]; stats indexed by o   */
+  FNST_EPI_NCHW_F32 = 2 /* out[n,j,h,w] fp32 (+bias), j < c_out                                  */
+};
+
+enum { FNST_PAD_NONE = 0, FNST_PAD_REFLECT = 1, FNST_PAD_ZERO = 2 };
+
+/* Descriptor of one gather-GEMM convolution (see formula above).  Strides are in elements. */
+typedef struct fnst_conv_desc {
+  const void* a;                 /* activation view, element type `dtype`                         */
+  int64_t a_stride_w, a_stride_h, a_stride_n;
+  int32_t a_w, a_h, a_n, a_c;    /* logical extents of the view (bounds for zero fill)            */
+  int32_t ntaps, kc;             /* taps and channels per tap (kc % 64 == 0 for tensor cores)     */
+  int32_t h0, w0;
+  int8_t tap_dh[FNST_MAX_TAPS];
+  int8_t tap_dw[FNST_MAX_TAPS];
+  int16_t tap_c0[FNST_MAX_TAPS];
+  const void* b;                 /* packed weights [n_gemm][ntaps*kc], element type `dtype`       */
+  int32_t n_gemm;                /* GEMM columns (multiple of 16)                                 */
+  int32_t out_n, out_h, out_w;   /* output tile space                                             */
+  int32_t epilogue;              /* FNST_EPI_*                                                    */
+  int32_t c_out;                 /* real output channels                                          */
+  int32_t relu;
+  int32_t dtype;                 /* operand element type                                          */
+  int32_t out_dtype;             /* element type of `out` (ignored for NCHW_F32)                  */
+  void* out;
+  const float* bias;             /* [c_out] or NULL                                               */
+  float* stats;                  /* [out_n][c_out][2] (sum, sumsq), zeroed by the call; or NULL   */
+} fnst_conv_desc;
+
+int fnst_version(void);
+const char* fnst_last_error(void);
+/* 1 when the running device can execute the tcgen05/TMA kernels (compute capability 10.x). */
+int fnst_device_supports_tc(int device);
+
+/*
+ * Gather-GEMM convolution on tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads).
+ * Replaces nn.Conv2d behind ReflectionPad2d (models/model.py:68-75), nn.ConvTranspose2d
+ * (models/model.py:13-22) and torchvision VGG conv+ReLU (models/vgg19_net.py:38-51).
+ * dtype must be FNST_F16 or FNST_BF16.
+ */
+int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream);
+
+/* Same operator on CUDA cores with fp32 accumulation (any dtype); the fp32-accurate path. */
+int fnst_conv_simt(const fnst_conv_desc* d, int device, void* stream);
+
+/*
+ * First-layer convolution for 3-channel NCHW fp32 images: reflect/zero padding by index math.
+ * Replaces ConvLayer(3,64,9,stride=2) (models/model.py:28) and VGG conv1_1 (features[0]).
+ * x [n,3,h,w] fp32; w [c_out,3,k,k] fp32 (PyTorch OIHW); out NHWC [n,ho,wo,c_out] of out_dtype.
+ * stats (optional) as above; bias/relu optional.
+ */
+int fnst_conv_first(const float* x, int n, int h, int w, const float* wgt, const float* bias,
+                    int c_out, int k, int stride, int pad, int pad_mode, int relu,
+                    void* out, int out_dtype, float* stats, int device, void* stream);
+
+/*
+ * InstanceNorm2d(affine) apply + ReLU + Dropout2d scale + residual add, writing the consumer's
+ * halo buffer.  Replaces nn.InstanceNorm2d / F.relu / nn.Dropout2d / `x + y`
+ * (models/model.py:51,52,60,61,86-90).
+ *   raw   [n,h,w,c] dtype          conv output
+ *   stats [n,c,2] fp32             per-plane sum / sum of squares from the conv epilogue
+ *   drop  [n,c] fp32 or NULL       Dropout2d scale (0 or 1/0.9)
+ *   res   or NULL                  residual source: NHWC buffer with halo `res_pad`
+ *   out                            [n, h+2*pad, w+2*pad, c]; if s2d: [n, ceil((h+2p)/2), ceil((w+2p)/2), 4c]
+ *                                  with channel = ((hp&1)*2 + (wp&1))*c + ch
+ */
+int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, const float* beta,
+                     const float* drop, const void* res, int res_pad, void* out,
+                     int n, int h, int w, int c, int dtype, int relu, float eps,
+                     int pad, int pad_mode, int s2d, int device, void* stream);
+
+/* MaxPool2d(2,2) on NHWC (torchvision features[4], [9], [18]); h, w are input extents (floor). */
+int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream);
+
+/*
+ * Gram matrix G[n] = F[n]^T F[n] for NHWC features F[n] = [h*w][c]  (losses/losses.py:6-13).
+ * out fp32 [n][c][c].  use_tc: tcgen05 path (dtype F16/BF16, c % 64 == 0), else CUDA cores.
+ */
+int fnst_gram(const void* feat, float* out, int n, int hw, int c, int dtype, int use_tc, int device, void* stream);
+
+/* acc[0] += sum (a-b)^2 over `count` elements (double accumulator)  (losses/losses.py:41,54).
+ * b_period: b is indexed modulo b_period (target Gram broadcast over the batch). */
+int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
+             double* acc, int device, void* stream);
+
+/* acc[0] += sum of squared vertical and horizontal differences of an NCHW fp32 image
+ * (losses/losses.py:62-73; the caller divides by b*c*h*w). */
+int fnst_tv(const float* img, int planes, int h, int w, double* acc, int device, void* stream);
+
+/* NHWC (dtype) -> NCHW fp32 and back (layout plumbing at the module boundary). */
+int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w, int c, int dtype, int device, void* stream);
+int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNST_H_ */

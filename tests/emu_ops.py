@@ -1,0 +1,128 @@
+"""Pure-torch CPU emulation of the libfnst operator semantics documented in include/fnst.h.
+
+TEST INFRASTRUCTURE: lets the CPU test-suite check the host logic of the product (tap tables,
+weight packing, halo / space-to-depth buffers, depth-to-space epilogue, operator order) against
+the oracle without a GPU, by substituting these functions for fast_neural_style_transfer_b200.ops.
+Never imported by the product.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+EPI_NHWC, EPI_D2S, EPI_NCHW_F32 = 0, 1, 2
+PAD_NONE, PAD_REFLECT, PAD_ZERO = 0, 1, 2
+
+
+def _reflect(i: torch.Tensor, n: int) -> torch.Tensor:
+    i = i.abs()
+    return torch.where(i >= n, 2 * (n - 1) - i, i)
+
+
+def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc):
+    n, ah, aw, ac = a_dims
+    sn, sh, sw = a_strides
+    view = a.as_strided((n, ah, aw, ac), (sn, sh, sw, 1), a.storage_offset()).double()
+    oh, ow = out_hw
+    wgt = spec.weight.double()
+    acc = torch.zeros((n, oh, ow, spec.n_gemm), dtype=torch.float64)
+    for t, (dh, dw, c0) in enumerate(spec.taps):
+        hs = torch.arange(oh) + spec.h0 + dh
+        ws = torch.arange(ow) + spec.w0 + dw
+        hm = ((hs >= 0) & (hs < ah)).double().view(1, -1, 1, 1)
+        wm = ((ws >= 0) & (ws < aw)).double().view(1, 1, -1, 1)
+        patch = view[:, hs.clamp(0, ah - 1)][:, :, ws.clamp(0, aw - 1)][..., c0:c0 + spec.kc] * hm * wm
+        acc += patch @ wgt[:, t * spec.kc:(t + 1) * spec.kc].t()
+    c = spec.c_out
+    if spec.epilogue == EPI_D2S:
+        v = acc.view(n, oh, ow, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * oh, 2 * ow, c)
+    else:
+        v = acc[..., :c]
+    if spec.bias is not None:
+        v = v + spec.bias.double()[:c]
+    if spec.relu:
+        v = v.clamp_min(0)
+    if stats is not None:
+        stats[:, :, 0] = v.sum(dim=(1, 2)).float()
+        stats[:, :, 1] = (v * v).sum(dim=(1, 2)).float()
+    if spec.epilogue == EPI_NCHW_F32:
+        out.copy_(v.permute(0, 3, 1, 2).to(out.dtype))
+    else:
+        out.copy_(v.to(out.dtype))
+
+
+def conv_first(x, weight, bias, k, stride, pad, pad_mode, relu, out, stats):
+    xp = F.pad(x.double(), (pad,) * 4, mode="reflect" if pad_mode == PAD_REFLECT else "constant")
+    v = F.conv2d(xp, weight.double(), None if bias is None else bias.double(), stride=stride)
+    if relu:
+        v = v.clamp_min(0)
+    v = v.permute(0, 2, 3, 1)
+    if stats is not None:
+        stats[:, :, 0] = v.sum(dim=(1, 2)).float()
+        stats[:, :, 1] = (v * v).sum(dim=(1, 2)).float()
+    out.copy_(v.to(out.dtype))
+
+
+def inorm_apply(raw, stats, gamma, beta, out, relu, pad=0, pad_mode=PAD_NONE, s2d=False, drop=None, res=None,
+                res_pad=0, eps=1e-5):
+    n, h, w, c = raw.shape
+    cnt = h * w
+    mean = stats[:, :, 0].double() / cnt
+    var = (stats[:, :, 1].double() / cnt - mean * mean).clamp_min(0)
+    a = gamma.double() / torch.sqrt(var + eps)
+    b = beta.double() - mean * a
+    y = raw.double() * a.view(n, 1, 1, c) + b.view(n, 1, 1, c)
+    if relu:
+        y = y.clamp_min(0)
+    if drop is not None:
+        y = y * drop.double().view(n, 1, 1, c)
+    if res is not None:
+        y = y + res.double()[:, res_pad:res_pad + h, res_pad:res_pad + w, :]
+    if pad:
+        if pad_mode == PAD_REFLECT:
+            hi = _reflect(torch.arange(-pad, h + pad), h)
+            wi = _reflect(torch.arange(-pad, w + pad), w)
+            y = y[:, hi][:, :, wi]
+        else:
+            y = F.pad(y, (0, 0, pad, pad, pad, pad))
+    if s2d:
+        hp, wp = y.shape[1], y.shape[2]
+        y = F.pad(y, (0, 0, 0, wp % 2, 0, hp % 2))
+        hs, ws = y.shape[1] // 2, y.shape[2] // 2
+        y = y.view(n, hs, 2, ws, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, hs, ws, 4 * c)
+    out.copy_(y.to(out.dtype))
+
+
+def maxpool2(x):
+    n, h, w, c = x.shape
+    v = x[:, :h // 2 * 2, :w // 2 * 2].reshape(n, h // 2, 2, w // 2, 2, c)
+    return v.amax(dim=(2, 4))
+
+
+def gram(feat_nhwc, use_tc):
+    n, h, w, c = feat_nhwc.shape
+    f = feat_nhwc.reshape(n, h * w, c).double()
+    return (f.transpose(1, 2) @ f).float()
+
+
+def sse(a, b, acc):
+    d = a.double().reshape(-1, b.numel()) - b.double().reshape(1, -1)
+    acc += (d * d).sum()
+
+
+def tv(img, acc):
+    acc += ((img[:, :, 1:] - img[:, :, :-1]).double() ** 2).sum() + ((img[:, :, :, 1:] - img[:, :, :, :-1]).double() ** 2).sum()
+
+
+def nhwc_to_nchw(x):
+    return x.permute(0, 3, 1, 2).float().contiguous()
+
+
+def nchw_to_nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).to(dtype).contiguous()
+
+
+def install(monkeypatch, ops_module):
+    """Substitute every operator of `ops_module` by its emulation."""
+    for name in ("conv_gather", "conv_first", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc"):
+        monkeypatch.setattr(ops_module, name, globals()[name])
