@@ -1,0 +1,160 @@
+"""torch.autograd.Function wrappers that connect the libfnst operators to PyTorch autograd:
+whole-network functions for StyleTransferNet and the VGG-19 feature stack, and the loss
+reductions (Gram, squared error, total variation)."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+def _as_nhwc(feat: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Logical (B,C,H,W) tensor -> contiguous NHWC tensor (zero-copy when the memory already is NHWC)."""
+    v = feat.permute(0, 2, 3, 1)
+    if v.is_contiguous() and (dtype is None or v.dtype == dtype):
+        return v
+    if feat.dtype == torch.float32 and feat.is_contiguous():
+        return ops.nchw_to_nhwc(feat, dtype or torch.float32)
+    return ops.nchw_to_nhwc(feat.float().contiguous(), dtype or torch.float32)
+
+
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: CUDA tensor required (the B200 path has no CPU fallback)")
+
+
+# ---- Gram matrix ----------------------------------------------------------------------------------
+
+class _Gram(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat):
+        f = _as_nhwc(feat.detach())
+        ctx.save_for_backward(f)
+        return ops.gram(f, use_tc=False)
+
+    @staticmethod
+    def backward(ctx, dg):
+        from . import backward
+        (f,) = ctx.saved_tensors
+        return backward.gram_backward(f, dg).permute(0, 3, 1, 2)
+
+
+def gram(feat: torch.Tensor) -> torch.Tensor:
+    _need_cuda(feat, "gram_matrix")
+    if torch.is_grad_enabled() and feat.requires_grad:
+        return _Gram.apply(feat)
+    return ops.gram(_as_nhwc(feat.detach()), use_tc=False)
+
+
+# ---- sum of squared differences ----------------------------------------------------------------------
+
+def _sse_forward(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    acc = torch.zeros((), dtype=torch.float64, device=a.device)
+    ops.sse(a, b, acc)
+    return acc.float()
+
+
+def _match_layout(a: torch.Tensor, b: torch.Tensor):
+    """Bring a (B,C,H,W)-logical pair to identical contiguous memory order; Gram-like (B,C,C)/(C,C) pass through."""
+    if a.dim() == 4:
+        an = _as_nhwc(a)
+        bn = _as_nhwc(b, an.dtype) if b.dim() == 4 else b
+        return an, bn.contiguous()
+    return a.contiguous(), b.contiguous()
+
+
+class _SSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        an, bn = _match_layout(a.detach(), b.detach())
+        ctx.save_for_backward(an, bn)
+        ctx.is_feat = a.dim() == 4
+        return _sse_forward(an, bn)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import backward
+        an, bn = ctx.saved_tensors
+        da = backward.sse_backward(an, bn, g)
+        return (da.permute(0, 3, 1, 2) if ctx.is_feat else da), None
+
+
+def sse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """sum((a - b)^2) with b broadcast over the leading (batch) dimension; differentiable in a."""
+    _need_cuda(a, "mse/sse")
+    if torch.is_grad_enabled() and a.requires_grad:
+        return _SSE.apply(a, b)
+    an, bn = _match_layout(a.detach(), b.detach())
+    return _sse_forward(an, bn)
+
+
+# ---- total variation ---------------------------------------------------------------------------------
+
+class _TV(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img):
+        x = img.detach().float().contiguous()
+        ctx.save_for_backward(x)
+        acc = torch.zeros((), dtype=torch.float64, device=x.device)
+        ops.tv(x, acc)
+        return acc.float()
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import backward
+        (x,) = ctx.saved_tensors
+        return backward.tv_backward(x, g)
+
+
+def tv(img: torch.Tensor) -> torch.Tensor:
+    _need_cuda(img, "total_variation_loss")
+    if torch.is_grad_enabled() and img.requires_grad:
+        return _TV.apply(img)
+    x = img.detach().float().contiguous()
+    acc = torch.zeros((), dtype=torch.float64, device=x.device)
+    ops.tv(x, acc)
+    return acc.float()
+
+
+# ---- whole-network functions -----------------------------------------------------------------------------
+
+class _StyleNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, names, x, drop, *params):
+        tape: dict = {}
+        y = plan.forward(x.detach(), drop, tape)
+        ctx.plan, ctx.names, ctx.tape, ctx.drop = plan, names, tape, drop
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import backward
+        grads = backward.stylenet_backward(ctx.plan, ctx.tape, dy.contiguous())
+        ctx.tape = None
+        return (None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+def stylenet_apply(plan, names: Sequence[str], x: torch.Tensor, drop, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    return _StyleNet.apply(plan, list(names), x, drop, *params)
+
+
+class _VGG(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x):
+        tape: dict = {}
+        feats = plan.forward(x.detach(), tape)
+        ctx.plan, ctx.tape = plan, tape
+        return tuple(feats)
+
+    @staticmethod
+    def backward(ctx, *dfeats):
+        from . import backward
+        dx = backward.vgg_backward(ctx.plan, ctx.tape, dfeats)
+        ctx.tape = None
+        return None, dx
+
+
+def vgg_apply(plan, x: torch.Tensor) -> List[torch.Tensor]:
+    return list(_VGG.apply(plan, x))

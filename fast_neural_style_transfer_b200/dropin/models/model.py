@@ -1,0 +1,114 @@
+"""Drop-in for the reference's models/model.py: same class names, constructor signatures,
+child-module names and 58 state-dict keys (models/model.py:7-90), forward executed by libfnst
+(hand-written sm_100a kernels) instead of ATen/cuDNN.
+
+The nn.Conv2d / nn.ConvTranspose2d / nn.InstanceNorm2d children are parameter containers only
+(identical default initialisation and construction order as the reference, so the same seed gives
+the same weights); their own forward is never called.  There is no CPU or library fallback:
+non-CUDA inputs raise.
+
+Precision: `net.precision` in {"fp16" (default; tcgen05 tensor cores), "bf16", "fp32" (CUDA
+cores, 1e-4 parity path)}, or environment variable FNST_PRECISION.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+if _PKG_PARENT not in sys.path:
+    sys.path.append(_PKG_PARENT)
+
+from fast_neural_style_transfer_b200 import engine            # noqa: E402
+from fast_neural_style_transfer_b200 import autograd_fns      # noqa: E402
+
+
+def _standalone(name):
+    raise RuntimeError(f"{name}.forward is not a separate operator in the B200 path; call StyleTransferNet.forward "
+                       "(conv + InstanceNorm + ReLU are fused across these module boundaries)")
+
+
+class UpsampleConv(nn.Module):
+    def __init__(self, in_ch: int, out_ch: int, kernel: int, scale: int = 2):
+        super().__init__()
+        self.scale = scale
+        self.upsample_conv = nn.ConvTranspose2d(in_ch, out_ch, kernel_size=kernel, stride=scale, padding=kernel // 2,
+                                                output_padding=scale - 1)
+
+    def forward(self, x):
+        _standalone("UpsampleConv")
+
+
+class ConvLayer(nn.Module):
+    def __init__(self, in_ch: int, out_ch: int, kernel: int, stride=1):
+        super().__init__()
+        self.reflection_pad = nn.ReflectionPad2d(kernel // 2)
+        self.conv = nn.Conv2d(in_ch, out_ch, kernel_size=kernel, stride=stride)
+
+    def forward(self, x):
+        _standalone("ConvLayer")
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.conv1 = ConvLayer(channels, channels, kernel=3)
+        self.in1 = nn.InstanceNorm2d(channels, affine=True)
+        self.conv2 = ConvLayer(channels, channels, kernel=3)
+        self.in2 = nn.InstanceNorm2d(channels, affine=True)
+        self.dropout = nn.Dropout2d(0.1)
+
+    def forward(self, x):
+        _standalone("ResidualBlock")
+
+
+class StyleTransferNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = ConvLayer(3, 64, kernel=9, stride=2)
+        self.norm1 = nn.InstanceNorm2d(64, affine=True)
+        self.conv2 = ConvLayer(64, 256, kernel=3, stride=2)
+        self.norm2 = nn.InstanceNorm2d(256, affine=True)
+        self.res_blocks = nn.ModuleList([ResidualBlock(256) for _ in range(5)])
+        self.up1 = UpsampleConv(256, 64, kernel=3, scale=2)
+        self.norm3 = nn.InstanceNorm2d(64, affine=True)
+        self.up2 = UpsampleConv(64, 32, kernel=3, scale=2)
+        self.norm4 = nn.InstanceNorm2d(32, affine=True)
+        self.final_conv = ConvLayer(32, 3, kernel=9, stride=1)
+        self.precision = os.environ.get("FNST_PRECISION", "fp16")
+
+    # plan cache (packed weights) is derived state: never pickled, rebuilt when parameters change
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_plan_cache", None)
+        return state
+
+    def _plan(self) -> "engine.StyleNetPlan":
+        params = dict(self.named_parameters())
+        key = (self.precision, tuple((p.data_ptr(), p._version) for p in params.values()))
+        cache = self.__dict__.get("_plan_cache")
+        if cache is None or cache[0] != key:
+            cache = (key, engine.StyleNetPlan(self.precision).pack(params))
+            self.__dict__["_plan_cache"] = cache
+        return cache[1]
+
+    def _dropout_scales(self, x):
+        """One (B,256) Dropout2d scale per residual block, drawn from torch's RNG in block order with the
+        same call the reference makes per block (models/model.py:84,88; SURVEY 8c stochasticity)."""
+        if not self.training:
+            return None
+        ones = torch.ones((x.shape[0], 256, 1, 1), device=x.device)
+        return [F.dropout2d(ones, blk.dropout.p, True).view(x.shape[0], 256) for blk in self.res_blocks]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
+        plan = self._plan()
+        drop = self._dropout_scales(x)
+        params = list(self.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            names = [n for n, _ in self.named_parameters()]
+            return autograd_fns.stylenet_apply(plan, names, x, drop, params)
+        return plan.forward(x, drop)

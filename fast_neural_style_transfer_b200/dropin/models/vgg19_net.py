@@ -1,0 +1,66 @@
+"""Drop-in for the reference's models/vgg19_net.py: class VGG19 whose forward returns the five
+feature maps [relu1_2, relu2_2, relu3_3, relu4_2, relu4_3] (models/vgg19_net.py:56-65), computed by
+libfnst.  The returned tensors have the reference's logical (B,C,H,W) shape; their memory is the
+path's NHWC activation buffer (a permuted view, no copy) in the path's element type.
+
+Weights: torchvision's vgg19 architecture with random init (there is no network for the pretrained
+file the reference downloads, models/vgg19_net.py:27); set FNST_VGG19_WEIGHTS=/path/vgg19.pth to load a
+torchvision state dict instead.  The reference constructor's undefined `slice5` (:51) is created here.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+if _PKG_PARENT not in sys.path:
+    sys.path.append(_PKG_PARENT)
+
+from fast_neural_style_transfer_b200 import engine            # noqa: E402
+from fast_neural_style_transfer_b200 import autograd_fns      # noqa: E402
+
+_SLICES = (("slice1", 0, 4), ("slice2", 4, 9), ("slice3", 9, 16), ("slice4", 16, 22), ("slice5", 22, 25))
+
+
+class VGG19(nn.Module):
+    def __init__(self):
+        super().__init__()
+        from torchvision.models import vgg19
+        net = vgg19(weights=None)
+        path = os.environ.get("FNST_VGG19_WEIGHTS")
+        if path:
+            net.load_state_dict(torch.load(path, map_location="cpu"))
+        feats = net.features
+        for name, lo, hi in _SLICES:
+            seq = nn.Sequential()
+            for i in range(lo, hi):
+                seq.add_module(str(i), feats[i])
+            setattr(self, name, seq)
+        for p in self.parameters():
+            p.requires_grad = False
+        self.precision = os.environ.get("FNST_PRECISION", "fp16")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_plan_cache", None)
+        return state
+
+    def _plan(self) -> "engine.VGGPlan":
+        params = dict(self.named_parameters())
+        key = (self.precision, tuple((p.data_ptr(), p._version) for p in params.values()))
+        cache = self.__dict__.get("_plan_cache")
+        if cache is None or cache[0] != key:
+            cache = (key, engine.VGGPlan(self.precision).pack(params))
+            self.__dict__["_plan_cache"] = cache
+        return cache[1]
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("VGG19 (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
+        plan = self._plan()
+        if torch.is_grad_enabled() and x.requires_grad:
+            feats = autograd_fns.vgg_apply(plan, x)
+        else:
+            feats = plan.forward(x)
+        return [f.permute(0, 3, 1, 2) for f in feats]

@@ -176,14 +176,14 @@ class StyleNetPlan:
         taps9 = taps_kxk(3)
         for i in range(5):
             raw_a, st_a = new(B, H2, W2, 256), stats(256)
-            ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}a"], 256, 256), cur, (B, H2 + 2, W2 + 2, 256),
+            ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}a"], 256, 256, tag=f"res{i}a"), cur, (B, H2 + 2, W2 + 2, 256),
                             _nhwc_strides(cur), raw_a, (H2, W2), st_a, tc)
             mid = new(B, H2 + 2, W2 + 2, 256)
             g, b = self._affine(f"res_blocks.{i}.in1")
             drop = None if drop_scales is None else drop_scales[i].float().contiguous()
             ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop)
             raw_b, st_b = new(B, H2, W2, 256), stats(256)
-            ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}b"], 256, 256), mid, (B, H2 + 2, W2 + 2, 256),
+            ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}b"], 256, 256, tag=f"res{i}b"), mid, (B, H2 + 2, W2 + 2, 256),
                             _nhwc_strides(mid), raw_b, (H2, W2), st_b, tc)
             last = i == 4
             nxt = new(B, H2, W2, 256) if last else new(B, H2 + 2, W2 + 2, 256)

@@ -21,6 +21,39 @@ _DT = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF
 launch_count = 0
 
 
+class KernelTimer:
+    """CUDA-event pairs around tagged launches on the launching stream (bench.py roofline leg)."""
+
+    def __init__(self, tag_prefix: str):
+        self.prefix = tag_prefix
+        self.pairs = []
+
+    def wants(self, tag: str) -> bool:
+        return bool(tag) and tag.startswith(self.prefix)
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, e0) -> None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.pairs.append((e0, e1))
+
+    def count(self) -> int:
+        return len(self.pairs)
+
+    def mean_ms(self):
+        if not self.pairs:
+            return None
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self.pairs) / len(self.pairs)
+
+
+kernel_timer: Optional[KernelTimer] = None
+
+
 def dt(t: torch.dtype) -> int:
     return _DT[t]
 
@@ -54,6 +87,7 @@ class ConvSpec:
     epilogue: int = _lib.EPI_NHWC
     bias: Optional[torch.Tensor] = None
     relu: bool = False
+    tag: str = ""
 
 
 def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, int], a_strides: Tuple[int, int, int],
@@ -81,7 +115,11 @@ def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, in
     d.stats = None if stats is None else stats.data_ptr()
     dev, st = _ctx(a)
     fn = lib.fnst_conv_tc if use_tc else lib.fnst_conv_simt
+    timed = kernel_timer is not None and kernel_timer.wants(spec.tag)
+    e0 = kernel_timer.start() if timed else None
     check(fn(C.byref(d), dev, st), "conv_tc" if use_tc else "conv_simt")
+    if timed:
+        kernel_timer.stop(e0)
     _count(2 if stats is not None else 1)
 
 

@@ -1,0 +1,76 @@
+"""The drop-in modules keep the reference's Python surface: class names, child names,
+58 state-dict keys / shapes, default initialisation, picklability.  CPU only (no compute calls)."""
+import io
+import os
+import pickle
+import sys
+
+import pytest
+import torch
+
+from oracle import stylenet_oracle as O
+
+DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast_neural_style_transfer_b200", "dropin")
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    sys.path.insert(0, DROPIN)
+    for m in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "losses" or k.startswith("losses.")]:
+        del sys.modules[m]
+    import models.model as mm
+    import models.vgg19_net as mv
+    import losses.losses as ll
+    yield mm, mv, ll
+    sys.path.remove(DROPIN)
+    for m in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "losses" or k.startswith("losses.") or k == "config"]:
+        del sys.modules[m]
+
+
+def test_state_dict_contract(dropin):
+    mm, _, _ = dropin
+    net = mm.StyleTransferNet()
+    ref = O.make_net_params(seed=0)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref.keys())           # same names, same order (models/model.py:25-47)
+    for k in ref:
+        assert sd[k].shape == ref[k].shape, k
+    net.load_state_dict(ref)                             # strict
+    assert sum(p.numel() for p in net.parameters()) == 6_243_843
+    assert [n for n, _ in net.named_children()] == ["conv1", "norm1", "conv2", "norm2", "res_blocks", "up1", "norm3", "up2", "norm4", "final_conv"]
+    assert isinstance(net.res_blocks[0].dropout, torch.nn.Dropout2d) and net.res_blocks[0].dropout.p == 0.1
+
+
+def test_default_init_matches_torch_modules(dropin):
+    """Same construction order + same torch default init => same weights as the reference under one seed."""
+    mm, _, _ = dropin
+    torch.manual_seed(0)
+    net = mm.StyleTransferNet()
+    torch.manual_seed(0)
+    c1 = torch.nn.Conv2d(3, 64, 9, stride=2)             # first module the reference constructs (models/model.py:28)
+    assert torch.equal(net.conv1.conv.weight, c1.weight) and torch.equal(net.conv1.conv.bias, c1.bias)
+    assert torch.equal(net.norm1.weight, torch.ones(64))
+
+
+def test_pickle_and_cpu_guard(dropin):
+    mm, _, ll = dropin
+    net = mm.StyleTransferNet()
+    buf = io.BytesIO()
+    torch.save(net, buf)                                 # whole-module pickle, train.py:297
+    buf.seek(0)
+    net2 = torch.load(buf, weights_only=False)
+    assert torch.equal(net2.final_conv.conv.weight, net.final_conv.conv.weight)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 3, 32, 32))                   # no CPU fallback
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ll.total_variation_loss(torch.zeros(1, 3, 8, 8))
+
+
+def test_vgg_contract(dropin):
+    _, mv, _ = dropin
+    vgg = mv.VGG19()
+    ref = O.make_vgg_params(seed=1)
+    assert sorted(vgg.state_dict().keys()) == sorted(ref.keys())
+    vgg.load_state_dict(ref)
+    assert all(not p.requires_grad for p in vgg.parameters())
+    assert hasattr(vgg, "slice5")

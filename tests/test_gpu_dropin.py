@@ -1,0 +1,99 @@
+"""GPU parity of the drop-in Python surface (models.model / models.vgg19_net / losses.losses) vs the oracle."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import stylenet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast_neural_style_transfer_b200", "dropin")
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    sys.path.insert(0, DROPIN)
+    for m in [k for k in sys.modules if k.split(".")[0] in ("models", "losses", "config")]:
+        del sys.modules[m]
+    import models.model as mm
+    import models.vgg19_net as mv
+    import losses.losses as ll
+    yield mm, mv, ll
+    sys.path.remove(DROPIN)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
+def test_inference_like_reference_script(dropin, precision, tol):
+    """inference.py:33-48: build, load_state_dict, eval, no_grad, forward."""
+    mm, _, _ = dropin
+    p = O.make_net_params(seed=0)
+    net = mm.StyleTransferNet().to(DEV)
+    net.load_state_dict(p)
+    net.precision = precision
+    net.eval()
+    x = O.make_image(1, 256, 256, seed=1234)
+    with torch.no_grad():
+        y = net(x.to(DEV))
+        ref = O.stylenet_forward(p, x)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert rel_l2(y, ref) < tol
+    if precision == "fp16":
+        assert float((O.to_pixels(y.cpu()) - O.to_pixels(ref)).abs().max()) <= 1.0
+
+
+def test_train_mode_dropout_uses_torch_rng(dropin):
+    mm, _, _ = dropin
+    p = O.make_net_params(seed=0)
+    net = mm.StyleTransferNet().to(DEV)
+    net.load_state_dict(p)
+    net.precision = "fp32"
+    net.train()
+    x = O.make_image(2, 48, 48, seed=3).to(DEV)
+    with torch.no_grad():
+        torch.manual_seed(11); y1 = net(x)
+        torch.manual_seed(11)
+        ones = torch.ones((2, 256, 1, 1), device=DEV)
+        drop = [torch.nn.functional.dropout2d(ones, 0.1, True).view(2, 256).cpu() for _ in range(5)]
+        ref = O.stylenet_forward(p, x.cpu(), drop)
+        torch.manual_seed(12); y2 = net(x)
+    assert rel_l2(y1, ref) < 1e-4
+    assert not torch.equal(y1, y2)
+    net.eval()
+    with torch.no_grad():
+        assert rel_l2(net(x), O.stylenet_forward(p, x.cpu())) < 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
+def test_vgg_and_losses_forward(dropin, precision, tol):
+    _, mv, ll = dropin
+    vp = O.make_vgg_params(seed=1)
+    vgg = mv.VGG19().to(DEV)
+    vgg.load_state_dict(vp)
+    vgg.precision = precision
+    vgg.eval()
+    x = O.make_image(2, 64, 64, seed=77, normalized=True)
+    y = O.make_image(2, 64, 64, seed=79, normalized=True)
+    sty = O.make_image(1, 64, 64, seed=78, normalized=True)
+    with torch.no_grad():
+        feats, other = vgg(x.to(DEV)), vgg(y.to(DEV))
+        targets = [ll.gram_matrix(f).squeeze(0) for f in vgg(sty.to(DEV))]        # train.py:25-37
+        rf, ro = O.vgg_forward(vp, x), O.vgg_forward(vp, y)
+        rt = O.style_targets(vp, sty)
+        assert [tuple(f.shape) for f in feats] == [tuple(f.shape) for f in rf]
+        for i in range(5):
+            assert rel_l2(targets[i], rt[i]) < tol, i
+        s, c, tv = ll.style_loss(other, targets), ll.content_loss(other, feats), ll.total_variation_loss(x.to(DEV))
+        assert s.dim() == 0 and s.dtype == torch.float32
+        assert abs(float(s) / float(O.style_loss(ro, rt)) - 1) < tol
+        assert abs(float(c) / float(O.content_loss(ro, rf)) - 1) < tol
+        assert abs(float(tv) / float(O.total_variation_loss(x)) - 1) < 1e-5
+        # plain NCHW fp32 tensors (not produced by the drop-in VGG) are accepted as well
+        g = ll.gram_matrix(rf[1].to(DEV))
+        assert rel_l2(g, O.gram_matrix(rf[1])) < 1e-5
