@@ -1,0 +1,122 @@
+"""Training-step leg of bench.py: the reference's step body (train.py:168-206) on the drop-in modules.
+
+One step = content batch (4 per GPU, 256x256) -> StyleTransferNet (train mode, Dropout2d live) -> clamp
+-> VGG-19 twice -> content/style/TV losses -> NaN check -> zero_grad -> backward -> [DP: gradient
+all-reduce] -> clip_grad_norm_(1.0) -> Adam(lr 1e-3, wd 1e-5) -> CosineAnnealingLR step.
+"""
+import json
+import os
+import sys
+
+import torch
+
+import bench as B
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def run(args, wl, net, rank, world, dev, peaks):
+    from oracle import stylenet_oracle as O
+    from fast_neural_style_transfer_b200 import ops, parallel
+    from models.vgg19_net import VGG19
+    from losses import losses as L
+
+    bsz, h, w = wl["batch"], wl["h"], wl["w"]
+    vgg = VGG19()
+    vgg.load_state_dict(O.make_vgg_params(seed=1))
+    vgg = vgg.to(dev).eval()
+    vgg.precision = "fp32" if args.precision == "fp32" else "bf16"
+    for p in vgg.parameters():
+        p.requires_grad = False
+    net.train()
+    style = O.make_image(1, h, w, seed=4321, normalized=True).to(dev)
+    with torch.no_grad():
+        targets = [L.gram_matrix(f).squeeze(0).detach() for f in vgg(style)]           # train.py:25-37
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=80000, eta_min=1e-7)
+    dp = parallel.GradientAllReduce(net, world) if world > 1 else None
+    torch.manual_seed(1000 + rank)                                                      # per-rank dropout streams
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4
+    host_batches = [O.make_image(bsz, h, w, seed=1234 + 17 * rank + i, normalized=True).pin_memory() for i in range(n_host)]
+    dev_batches = [b.to(dev) for b in host_batches]
+    tv_scale = 1.0 / world          # TV is a batch mean, content/style are batch sums: SUM all-reduce
+
+    def step(content, read_losses):
+        stylized = torch.clamp(net(content), -3, 3)
+        with torch.no_grad():
+            cf = vgg(content)
+        sf = vgg(stylized)
+        c_loss = L.content_loss(sf, cf)
+        s_loss = L.style_loss(sf, targets)
+        tv_loss = L.total_variation_loss(stylized)
+        total = 1000.0 * c_loss + 1 * s_loss + 10 * tv_scale * tv_loss
+        if torch.isnan(total) or torch.isinf(total):                                    # train.py:193 (host sync)
+            raise RuntimeError("invalid loss in benchmark step")
+        opt.zero_grad()
+        total.backward()
+        if dp is not None:
+            dp.all_reduce()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
+        opt.step()
+        sched.step()
+        if read_losses:
+            return total.item(), c_loss.item(), s_loss.item(), tv_loss.item()            # train.py:209-212
+        return None
+
+    for i in range(args.warmup):
+        step(dev_batches[i % n_host], False)
+    B.barrier(world)
+    sampler = B.ClockSampler(dev.index) if rank == 0 else None
+    timer = ops.KernelTimer(tag_prefix="res")
+    ops.kernel_timer = timer
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(dev_batches[i % n_host], False)
+    e1.record()
+    B.barrier(world)
+    ops.kernel_timer = None
+    launches = ops.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    ms = B.max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    # end to end: host batch -> H2D -> step -> four loss scalars read back
+    for i in range(2):
+        step(host_batches[i % n_host].to(dev, non_blocking=True), True)
+    B.barrier(world)
+    e0.record()
+    for i in range(args.steps):
+        losses = step(host_batches[i % n_host].to(dev, non_blocking=True), True)
+    e1.record()
+    B.barrier(world)
+    ms_e2e = B.max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+    k_ms = timer.mean_ms()
+    flops = 2.0 * bsz * (h // 4) * (w // 4) * 256 * 2304
+    achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
+    if rank != 0:
+        return
+    value = world * args.steps / (ms / 1e3)
+    line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": {"fp16": "f16 fwd / bf16 grads", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": {"workload": "train", "desc": wl["desc"], "per_gpu_batch": bsz, "image": [h, w],
+                       "optimizer": "clip_grad_norm_(1.0) + Adam(lr 1e-3, wd 1e-5) + CosineAnnealingLR",
+                       "loss_weights": [1000.0, 1, 10], "parallelism": f"dp{world}" if world > 1 else "single",
+                       "value_note": "global steps/s x n_gpus = per-GPU-batch steps processed per second (weak scaling)",
+                       "l2": "per-step activations (>1 GB) exceed the 126 MB L2; 4 rotating input batches"},
+            "images_per_s": value * bsz,
+            "whole_step_tflops": value * bsz * B.TRAIN_GFLOP_IMG / 1e3 / world,
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel<256> (3x3 256->256 residual conv, forward launches)",
+                         "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tf_sustained"] if achieved else None, "traffic": None,
+                         "peak_source": peaks["src"] + " (sustained bf16/fp16)", "launches_timed": timer.count(), "kernel_ms": k_ms,
+                         "kernel_share_of_step": (k_ms * timer.count() / args.steps) / (ms / args.steps) if k_ms else None},
+            "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": wl["unit"],
+                    "h2d_bytes_per_step": host_batches[0].numel() * 4, "d2h_bytes_per_step": 16},
+            "gpu_launches": launches, "clocks": clocks, "last_losses": losses}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = B.cpu_baseline("train", wl)
+    print(json.dumps(line), flush=True)

@@ -40,6 +40,10 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p),
         ("bias", C.c_void_p),
         ("stats", C.c_void_p),
+        ("addend", C.c_void_p),
+        ("mask", C.c_void_p),
+        ("mask_dtype", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -60,7 +64,18 @@ EXPORTS = {
     "fnst_sse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "fnst_tv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "fnst_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "fnst_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_wgrad_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_void_p]),
+    "fnst_conv_first_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "fnst_inorm_bwd_reduce": (C.c_int, [C.c_void_p] * 9 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_inorm_bwd_apply": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_maxpool2_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
+    "fnst_sse_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                               C.c_int, C.c_int, C.c_void_p]),
+    "fnst_tv_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fnst_relu_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_channel_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 

@@ -1,0 +1,287 @@
+"""Backward plans: gradients of StyleTransferNet (58 parameters) and of the frozen VGG-19 feature
+stack (data gradient only), plus the loss-reduction backward helpers, in libfnst operators.
+
+Every data gradient of a convolution is again a gather-GEMM (ops.conv_gather) on the output
+gradient with negated taps and transposed packed weights; weight gradients use ops.wgrad; the
+InstanceNorm / ReLU / Dropout2d / residual / ReflectionPad2d backward is fused in
+ops.inorm_bwd_reduce + ops.inorm_bwd_apply (reference autograd: train.py:200).
+
+Gradient element type: fp32 on the "fp32" path; bfloat16 on the tensor-core paths (gradient norms
+reach 1e7-5e8 at random init, SURVEY 7.2, which overflows fp16).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import engine, ops
+from ._lib import EPI_NHWC, EPI_NCHW_F32, PAD_NONE, PAD_REFLECT
+from .engine import TAPS_2X2, _KT, _nhwc_strides, taps_kxk, taps_s2d_3x3
+from .ops import ConvSpec
+
+
+def grad_dtype(precision: str) -> torch.dtype:
+    return torch.float32 if precision == "fp32" else torch.bfloat16
+
+
+def _neg(taps):
+    return [(-dh, -dw, 0) for dh, dw, _ in taps]
+
+
+def pack_dgrad(bf: torch.Tensor, ntaps: int, kc: int, dtype: torch.dtype) -> torch.Tensor:
+    """Forward operand [n_gemm, ntaps*kc] -> data-gradient operand [kc, ntaps*n_gemm] (same tap order)."""
+    n_gemm = bf.shape[0]
+    return bf.view(n_gemm, ntaps, kc).permute(2, 1, 0).reshape(kc, ntaps * n_gemm).to(dtype).contiguous()
+
+
+def pack_dgrad_s2d(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """3x3 stride-2 conv weight (O, C, 3, 3) -> data-gradient operand for the space-to-depth input:
+    rows (ph_h, ph_w, c), K = (dh, dw, o); kernel tap (kh, kw) = (2*dh + ph_h, 2*dw + ph_w) when <= 2."""
+    o, c = w.shape[0], w.shape[1]
+    b = torch.zeros((2, 2, c, 2, 2, o), dtype=w.dtype, device=w.device)
+    for kh in range(3):
+        for kw in range(3):
+            b[kh & 1, kw & 1, :, kh >> 1, kw >> 1, :] = w[:, :, kh, kw].t()
+    return b.reshape(4 * c, 4 * o).to(dtype).contiguous()
+
+
+def unpack_conv(db: torch.Tensor, o: int, c: int, k: int) -> torch.Tensor:
+    return db[:o].view(o, k, k, c).permute(0, 3, 1, 2).contiguous()
+
+
+def unpack_conv_transpose(db: torch.Tensor, cin: int, cout: int) -> torch.Tensor:
+    """Inverse of engine.pack_conv_transpose for gradients: (4*Cout, 4*Cin) -> (Cin, Cout, 3, 3)."""
+    b = db.view(2, 2, cout, 2, 2, cin)
+    dw = torch.zeros((cin, cout, 3, 3), dtype=db.dtype, device=db.device)
+    for ph in (0, 1):
+        for dh, kh in _KT[ph].items():
+            for pw in (0, 1):
+                for dwi, kw in _KT[pw].items():
+                    dw[:, :, kh, kw] = b[ph, pw, :, dh, dwi, :].t()
+    return dw
+
+
+def _affine_grads(sums: torch.Tensor):
+    s = sums.sum(dim=0)
+    return s[:, 1].contiguous(), s[:, 0].contiguous()      # d gamma, d beta
+
+
+def _tc_ok(use_tc: bool, kc: int, n_gemm: int) -> bool:
+    return use_tc and kc % 64 == 0 and (n_gemm == 16 or n_gemm % 32 == 0)
+
+
+# -------------------------------------------------------------------------------------------------------
+# StyleTransferNet backward
+# -------------------------------------------------------------------------------------------------------
+
+def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """dy: (B,3,H',W') fp32.  Returns gradients for all 58 reference parameter names."""
+    p = plan.params
+    gdt = grad_dtype(plan.precision)
+    tc = plan.use_tc
+    dev = dy.device
+    dy = dy.contiguous().float()
+    B, _, H4, W4 = dy.shape
+    grads: Dict[str, torch.Tensor] = {}
+
+    def zeros_like_param(name):
+        return torch.zeros_like(p[name], dtype=torch.float32)
+
+    def dgrad(g, g_dims, fwd_packed, fwd_taps, fwd_kc, out_shape, out_hw, h0=0, w0=0):
+        """Data gradient of a forward gather-GEMM with plain taps (c0 == 0)."""
+        n_gemm_f = fwd_packed.shape[0]
+        wd = pack_dgrad(fwd_packed, len(fwd_taps), fwd_kc, gdt)
+        spec = ConvSpec(_neg(fwd_taps), n_gemm_f, wd, fwd_kc, fwd_kc, h0=-h0, w0=-w0)
+        out = torch.empty(out_shape, dtype=gdt, device=dev)
+        ops.conv_gather(spec, g, g_dims, _nhwc_strides(g), out, out_hw, None, _tc_ok(tc, n_gemm_f, fwd_kc))
+        return out
+
+    # ---- final_conv (9x9, 32 -> 3) -------------------------------------------------------------------
+    grads["final_conv.conv.bias"] = ops.channel_sum(dy)
+    g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
+    act4 = tape["act4"]
+    Hq, Wq = act4.shape[1], act4.shape[2]
+    taps81 = taps_kxk(9)
+    db = ops.wgrad(ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), _nhwc_strides(act4), g16, (H4, W4))
+    grads["final_conv.conv.weight"] = unpack_conv(db, 3, 32, 9)
+    wf_plain = engine.pack_final_plain(p["final_conv.conv.weight"], gdt)
+    d_act4 = dgrad(g16, (B, H4, W4, 16), wf_plain, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
+
+    # ---- norm4 + up2 ------------------------------------------------------------------------------------
+    g4, b4 = plan._affine("norm4")
+    gy, sums = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT)
+    grads["norm4.weight"], grads["norm4.bias"] = _affine_grads(sums)
+    d_raw4 = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
+    act3 = tape["act3"]
+    H3, W3 = act3.shape[1], act3.shape[2]
+    db = ops.wgrad(ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, (B, H3, W3, 64), _nhwc_strides(act3), d_raw4, (H3, W3))
+    grads["up2.upsample_conv.weight"] = unpack_conv_transpose(db, 64, 32)
+    grads["up2.upsample_conv.bias"] = zeros_like_param("up2.upsample_conv.bias")
+    wup2 = plan.w["up2"] if plan.w["up2"].dtype == gdt else engine.pack_conv_transpose(p["up2.upsample_conv.weight"], gdt)
+    d_act3 = dgrad(d_raw4, (B, H3, W3, 128), wup2, TAPS_2X2, 64, (B, H3, W3, 64), (H3, W3))
+
+    # ---- norm3 + up1 ------------------------------------------------------------------------------------
+    g3, b3 = plan._affine("norm3")
+    gy, sums = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True)
+    grads["norm3.weight"], grads["norm3.bias"] = _affine_grads(sums)
+    d_raw3 = ops.inorm_bwd_apply(gy, tape["raw3"], tape["st3"], sums, g3, out_s2d=True)     # (B,H2,W2,256)
+    trunk = tape["trunk"]
+    last = trunk[5]
+    H2, W2 = last.shape[1], last.shape[2]
+    db = ops.wgrad(ConvSpec(TAPS_2X2, 256, None, 256, 64), last, (B, H2, W2, 256), _nhwc_strides(last), d_raw3, (H2, W2))
+    grads["up1.upsample_conv.weight"] = unpack_conv_transpose(db, 256, 64)
+    grads["up1.upsample_conv.bias"] = zeros_like_param("up1.upsample_conv.bias")
+    wup1 = plan.w["up1"] if plan.w["up1"].dtype == gdt else engine.pack_conv_transpose(p["up1.upsample_conv.weight"], gdt)
+    g_plain = dgrad(d_raw3, (B, H2, W2, 256), wup1, TAPS_2X2, 256, (B, H2, W2, 256), (H2, W2))
+
+    # ---- residual trunk -----------------------------------------------------------------------------------
+    taps9 = taps_kxk(3)
+    pdims = (B, H2 + 2, W2 + 2, 256)
+    gsrc, extra = None, g_plain          # gradient of the block output = fold(gsrc) + extra
+    for i in range(4, -1, -1):
+        blk = tape["blocks"][i]
+        pre = f"res_blocks.{i}"
+        # in2 (no ReLU); the total output gradient also feeds the skip connection
+        ga, ba = plan._affine(pre + ".in2")
+        g_out, sums = ops.inorm_bwd_reduce(gsrc, extra, blk["raw_b"], blk["st_b"], ga, ba, None, gdt, False,
+                                           1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE)
+        grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(sums)
+        d_raw_b = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
+        mid = blk["mid"]
+        db = ops.wgrad(ConvSpec(taps9, 256, None, 256, 256), mid, pdims, _nhwc_strides(mid), d_raw_b, (H2, W2))
+        grads[pre + ".conv2.conv.weight"] = unpack_conv(db, 256, 256, 3)
+        grads[pre + ".conv2.conv.bias"] = zeros_like_param(pre + ".conv2.conv.bias")
+        wb = plan.w[f"res{i}b"] if plan.w[f"res{i}b"].dtype == gdt else engine.pack_conv(p[pre + ".conv2.conv.weight"], gdt)
+        d_mid = dgrad(d_raw_b, (B, H2, W2, 256), wb, taps9, 256, pdims, (H2 + 2, W2 + 2))
+        # in1 + ReLU + Dropout2d
+        ga, ba = plan._affine(pre + ".in1")
+        gy, sums = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT)
+        grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(sums)
+        d_raw_a = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
+        cur = trunk[i]
+        db = ops.wgrad(ConvSpec(taps9, 256, None, 256, 256), cur, pdims, _nhwc_strides(cur), d_raw_a, (H2, W2))
+        grads[pre + ".conv1.conv.weight"] = unpack_conv(db, 256, 256, 3)
+        grads[pre + ".conv1.conv.bias"] = zeros_like_param(pre + ".conv1.conv.bias")
+        wa = plan.w[f"res{i}a"] if plan.w[f"res{i}a"].dtype == gdt else engine.pack_conv(p[pre + ".conv1.conv.weight"], gdt)
+        gsrc = dgrad(d_raw_a, (B, H2, W2, 256), wa, taps9, 256, pdims, (H2 + 2, W2 + 2))
+        extra = g_out
+
+    # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
+    g2, b2 = plan._affine("norm2")
+    gy, sums = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT)
+    grads["norm2.weight"], grads["norm2.bias"] = _affine_grads(sums)
+    d_raw2 = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
+    buf2 = tape["buf2"]
+    Hs, Ws = buf2.shape[1], buf2.shape[2]
+    db = ops.wgrad(ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, (B, Hs, Ws, 256), _nhwc_strides(buf2), d_raw2, (H2, W2))
+    grads["conv2.conv.weight"] = unpack_conv(db, 256, 64, 3)
+    grads["conv2.conv.bias"] = zeros_like_param("conv2.conv.bias")
+    wd2 = pack_dgrad_s2d(p["conv2.conv.weight"], gdt)
+    d_buf2 = torch.empty((B, Hs, Ws, 256), dtype=gdt, device=dev)
+    ops.conv_gather(ConvSpec(_neg(TAPS_2X2), 256, wd2, 256, 256), d_raw2, (B, H2, W2, 256), _nhwc_strides(d_raw2), d_buf2,
+                    (Hs, Ws), None, tc)
+
+    # ---- norm1 + conv1 -----------------------------------------------------------------------------------------
+    g1, b1 = plan._affine("norm1")
+    raw1 = tape["raw1"]
+    gy, sums = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True)
+    grads["norm1.weight"], grads["norm1.bias"] = _affine_grads(sums)
+    d_raw1 = ops.inorm_bwd_apply(gy, raw1, tape["st1"], sums, g1)
+    dw1 = ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT)             # tap-major (243, 64)
+    grads["conv1.conv.weight"] = dw1.view(3, 9, 9, 64).permute(3, 0, 1, 2).contiguous()
+    grads["conv1.conv.bias"] = zeros_like_param("conv1.conv.bias")
+    return {k: v.to(p[k].dtype) for k, v in grads.items()}
+
+
+# -------------------------------------------------------------------------------------------------------
+# VGG-19 backward (frozen weights: data gradient only)
+# -------------------------------------------------------------------------------------------------------
+
+def vgg_backward(plan: "engine.VGGPlan", tape: dict, dfeats: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
+    """dfeats: gradients of the five NHWC feature maps (None where unused).  Returns dx (B,3,H,W) fp32."""
+    gdt = plan.dtype
+    tc = plan.use_tc
+    taps9 = taps_kxk(3, origin=-1)
+    dfe = [None if g is None else g.contiguous().to(gdt) for g in dfeats]
+    if all(g is None for g in dfe):
+        raise RuntimeError("vgg_backward called without any feature gradient")
+
+    def dgrad(name, g, addend=None, masked=True):
+        a, _ = tape[name]
+        B, H, W, cin = a.shape
+        cout = g.shape[-1]
+        wd = pack_dgrad(plan.w[name], 9, cin, gdt)                      # [cin, 9*cout]
+        out = torch.empty((B, H, W, cin), dtype=gdt, device=g.device)
+        spec = ConvSpec(_neg(taps9), cout, wd, cin, cin, addend=addend, mask=a if masked else None)
+        ops.conv_gather(spec, g, (B, H, W, cout), _nhwc_strides(g), out, (H, W), None, _tc_ok(tc, cout, cin))
+        return out
+
+    f4 = tape["slice5.23"][1]
+    f3 = tape["slice5.23"][0]
+    if dfe[4] is not None:
+        g = ops.relu_mask(dfe[4], None, f4)
+        g = dgrad("slice5.23", g, addend=dfe[3])
+    elif dfe[3] is not None:
+        g = ops.relu_mask(dfe[3], None, f3)
+    else:
+        g = None
+    f2 = tape["slice4.16"][0]
+    if g is not None:
+        g = dgrad("slice4.21", g)
+        g = dgrad("slice4.19", g, masked=False)
+        g = ops.maxpool2_bwd(tape["slice4.16"][1], g, None)
+        g = dgrad("slice4.16", g, addend=dfe[2])
+    elif dfe[2] is not None:
+        g = ops.relu_mask(dfe[2], None, f2)
+    f1 = tape["slice2.7"][1]
+    if g is not None:
+        g = dgrad("slice3.14", g)
+        g = dgrad("slice3.12", g)
+        g = dgrad("slice3.10", g, masked=False)
+        g = ops.maxpool2_bwd(f1, g, dfe[1])
+    elif dfe[1] is not None:
+        g = ops.relu_mask(dfe[1], None, f1)
+    f0 = tape["slice1.2"][1]
+    if g is not None:
+        g = dgrad("slice2.7", g)
+        g = dgrad("slice2.5", g, masked=False)
+        g = ops.maxpool2_bwd(f0, g, dfe[0])
+    else:
+        g = ops.relu_mask(dfe[0], None, f0)
+    g = dgrad("slice1.2", g)
+    # conv1_1: 64 -> 3 image channels, NCHW fp32 output
+    x = tape["x"]
+    B, _, H, W = x.shape
+    w0 = plan.params["slice1.0.weight"]                                   # (64, 3, 3, 3)
+    wd = torch.zeros((16, 9, 64), dtype=torch.float32, device=x.device)
+    wd[:3] = w0.permute(1, 2, 3, 0).reshape(3, 9, 64)
+    wd = wd.reshape(16, 576).to(gdt).contiguous()
+    dx = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+    spec = ConvSpec(_neg(taps9), 64, wd, 16, 3, epilogue=EPI_NCHW_F32)
+    ops.conv_gather(spec, g, (B, H, W, 64), _nhwc_strides(g), dx, (H, W), None, tc)
+    return dx
+
+
+# -------------------------------------------------------------------------------------------------------
+# Loss reductions
+# -------------------------------------------------------------------------------------------------------
+
+def gram_backward(f: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
+    """f NHWC (B,H,W,C); dg (B,C,C) fp32.  dF[p,i] = sum_j F[p,j] * (dG + dG^T)[i,j]: one 1x1 gather-GEMM per image."""
+    B, H, W, C = f.shape
+    s = (dg + dg.transpose(1, 2)).to(f.dtype).contiguous()
+    out = torch.empty_like(f)
+    use_tc = f.dtype != torch.float32 and C % 64 == 0
+    for n in range(B):
+        spec = ConvSpec([(0, 0, 0)], C, s[n], C, C)
+        ops.conv_gather(spec, f[n:n + 1], (1, H, W, C), _nhwc_strides(f[n:n + 1]), out[n:n + 1], (H, W), None, use_tc)
+    return out
+
+
+def sse_backward(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    return ops.sse_bwd(a, b, g.reshape(1).float(), a.dtype)
+
+
+def tv_backward(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    return ops.tv_bwd(x, g.reshape(1).float())

@@ -1,0 +1,549 @@
+// Backward operators of the style-transfer path (see include/fnst.h, "Backward operators"):
+// weight gradients of gather-GEMM convolutions, InstanceNorm backward (with ReflectionPad2d
+// fold, ReLU mask, dropout and residual handling), max-pool / squared-error / TV backward.
+#include "common.cuh"
+
+namespace fnst {
+
+int validate_conv_desc(const fnst_conv_desc* d);
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dB[j][t*kc + c] = sum_pixels g[pix][j] * A[pix + tap t][c0_t + c]
+// Block = 64 (j) x 64 (c) output tile of one tap, over a slab of pixels; 256 threads x (4x4).
+// grid.x = ntaps * ceil(kc/64), grid.y = ceil(n_gemm/64), grid.z = image * row-slabs.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 16;   // output rows per pixel slab
+
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const __grid_constant__ fnst_conv_desc d) {
+  __shared__ float Gs[16][64 + 4];
+  __shared__ float As[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int cchunks = (d.kc + 63) / 64;
+  const int t = blockIdx.x / cchunks, cc = blockIdx.x % cchunks;
+  const int j0 = blockIdx.y * 64;
+  const int slabs = (d.out_h + WG_ROWS - 1) / WG_ROWS;
+  const int n = blockIdx.z / slabs, slab = blockIdx.z % slabs;
+  const int r0 = slab * WG_ROWS, r1 = min(d.out_h, r0 + WG_ROWS);
+  const int npix = (r1 - r0) * d.out_w;
+  const int dh = d.tap_dh[t] + d.h0, dw = d.tap_dw[t] + d.w0, c0 = d.tap_c0[t] + cc * 64;
+  const int cw = min(64, d.kc - cc * 64);           // valid channels in this chunk
+
+  const TG* G = reinterpret_cast<const TG*>(d.b);
+  const TA* A = reinterpret_cast<const TA*>(d.a) + (size_t)n * d.a_stride_n;
+  const int lp = tid >> 4, lq = (tid & 15) * 4;     // loader: 16 pixels x 64 (4 per thread)
+  const int tx = tid & 15, ty = tid >> 4;           // compute: ty -> j, tx -> c
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
+
+  for (int p0 = 0; p0 < npix; p0 += 16) {
+    const int p = p0 + lp;
+    float gv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < npix) {
+      const int h = r0 + p / d.out_w, w = p % d.out_w;
+      const TG* gp = G + (((size_t)n * d.out_h + h) * d.out_w + w) * d.n_gemm + j0 + lq;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (j0 + lq + i < d.n_gemm) gv[i] = to_f32<TG>(gp[i]);
+      const int ih = h + dh, iw = w + dw;
+      if (ih >= 0 && ih < d.a_h && iw >= 0 && iw < d.a_w) {
+        const TA* ap = A + (size_t)ih * d.a_stride_h + (size_t)iw * d.a_stride_w + c0 + lq;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (lq + i < cw) av[i] = to_f32<TA>(ap[i]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { Gs[lp][lq + i] = gv[i]; As[lp][lq + i] = av[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 g4 = *reinterpret_cast<const float4*>(&Gs[k][ty * 4]);
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][tx * 4]);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = fmaf(g[i], a[q], acc[i][q]);
+    }
+  }
+  float* out = reinterpret_cast<float*>(d.out);
+  const size_t ktot = (size_t)d.ntaps * d.kc;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + ty * 4 + i;
+    if (j >= d.n_gemm) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = tx * 4 + q;
+      if (c < cw) atomicAdd(&out[(size_t)j * ktot + (size_t)t * d.kc + cc * 64 + c], acc[i][q]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// First-layer wgrad (C_in = 3, NCHW fp32 image).  Block = strip of 8x8 output tiles; thread =
+// (output channel o, tap group q of 4); per tile: patch + g tile in smem, broadcast patch reads.
+// ---------------------------------------------------------------------------------------------
+constexpr int FW_MAX_TPT = 61;   // ceil(243 / 4) taps per thread
+
+template <typename TG>
+__global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __restrict__ x, int H, int W,
+                                                               const TG* __restrict__ g, int c_out, int k, int stride, int pad,
+                                                               int pad_mode, int Ho, int Wo, int tiles_per_block, float* __restrict__ dw) {
+  extern __shared__ float smem[];
+  const int pdim = 7 * stride + k;
+  float* patch = smem;                         // [3][pdim][pdim]
+  float* gs = smem + 3 * pdim * pdim;          // [64 pixels][64 o]
+  const int taps = 3 * k * k;
+  const int tid = threadIdx.x, o = tid & 63, q = tid >> 6;
+  const int tiles_w = (Wo + 7) >> 3, tiles_h = (Ho + 7) >> 3;
+  const int tiles_img = tiles_w * tiles_h;
+  const int n = blockIdx.y;
+  float acc[FW_MAX_TPT];
+  int off[FW_MAX_TPT];          // patch offset of each of this thread's taps (invalid taps read offset 0, never stored)
+#pragma unroll
+  for (int i = 0; i < FW_MAX_TPT; ++i) {
+    acc[i] = 0.f;
+    const int t = q + 4 * i;
+    const int c = t / (k * k), r = t - c * k * k;
+    off[i] = t < taps ? (c * pdim + r / k) * pdim + r % k : 0;
+  }
+
+  for (int ti = 0; ti < tiles_per_block; ++ti) {
+    const int tile = blockIdx.x * tiles_per_block + ti;
+    if (tile >= tiles_img) break;
+    const int tw = tile % tiles_w, th = tile / tiles_w;
+    const int h_base = th * 8 * stride - pad, w_base = tw * 8 * stride - pad;
+    __syncthreads();
+    for (int i = tid; i < 3 * pdim * pdim; i += 256) {
+      const int c = i / (pdim * pdim), r = i - c * pdim * pdim;
+      int ih = h_base + r / pdim, iw = w_base + r % pdim;
+      float v = 0.f;
+      if (pad_mode == FNST_PAD_REFLECT) {
+        ih = reflect_index(ih, H); iw = reflect_index(iw, W);
+        ih = min(max(ih, 0), H - 1); iw = min(max(iw, 0), W - 1);
+        v = x[(((size_t)n * 3 + c) * H + ih) * W + iw];
+      } else if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        v = x[(((size_t)n * 3 + c) * H + ih) * W + iw];
+      }
+      patch[i] = v;
+    }
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int p = i >> 6, oo = i & 63;
+      const int h = th * 8 + (p >> 3), w = tw * 8 + (p & 7);
+      gs[i] = (h < Ho && w < Wo) ? to_f32<TG>(g[(((size_t)n * Ho + h) * Wo + w) * c_out + oo]) : 0.f;
+    }
+    __syncthreads();
+    for (int p = 0; p < 64; ++p) {
+      const float gv = gs[p * 64 + o];
+      const float* pp = patch + (p >> 3) * stride * pdim + (p & 7) * stride;
+#pragma unroll
+      for (int i = 0; i < FW_MAX_TPT; ++i) acc[i] = fmaf(gv, pp[off[i]], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < FW_MAX_TPT; ++i) {
+    const int t = q + 4 * i;
+    if (t < taps) atomicAdd(&dw[(size_t)t * c_out + o], acc[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm backward
+// ---------------------------------------------------------------------------------------------
+struct HaloLayout {
+  int H, W, C, pad, reflect, s2d;
+  __device__ __forceinline__ size_t index(int n, int hp, int wp, int c) const {
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    if (!s2d) return (((size_t)n * Hp + hp) * Wp + wp) * C + c;
+    const int Hs = (Hp + 1) >> 1, Ws = (Wp + 1) >> 1;
+    return (((size_t)n * Hs + (hp >> 1)) * Ws + (wp >> 1)) * (4 * C) + ((hp & 1) * 2 + (wp & 1)) * C + c;
+  }
+  // padded coordinates whose value was copied from interior coordinate i (extent n): returns count (<= 3)
+  __device__ __forceinline__ int sources(int i, int n, int (&src)[3]) const {
+    int cnt = 0;
+    src[cnt++] = i + pad;
+    if (reflect) {
+      if (i >= 1 && i <= pad) src[cnt++] = pad - i;
+      if (i <= n - 2 && i >= n - 1 - pad) src[cnt++] = pad + 2 * (n - 1) - i;
+    }
+    return cnt;
+  }
+};
+
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256) inorm_bwd_reduce_kernel(const TG* __restrict__ gsrc, const TG* __restrict__ extra,
+                                                               const TA* __restrict__ raw, const float* __restrict__ stats,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ drop, TG* __restrict__ gy,
+                                                               float* __restrict__ sums, HaloLayout L, int relu, float eps) {
+  extern __shared__ float s_acc[];   // [2][C]
+  const int n = blockIdx.y, h = blockIdx.x;
+  const int C = L.C, CG = C >> 3, PL = 256 / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, c0 = cg * 8;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+
+  float a[8], b[8], mean[8], rstd[8], ds[8];
+  const float inv_cnt = 1.f / (float)(L.H * L.W);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float* st = stats + ((size_t)n * C + c0 + i) * 2;
+    mean[i] = st[0] * inv_cnt;
+    rstd[i] = rsqrtf(fmaxf(st[1] * inv_cnt - mean[i] * mean[i], 0.f) + eps);
+    a[i] = gamma[c0 + i] * rstd[i];
+    b[i] = beta[c0 + i] - mean[i] * a[i];
+    ds[i] = drop ? drop[(size_t)n * C + c0 + i] : 1.f;
+  }
+  int hs[3]; const int nh = L.sources(h, L.H, hs);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+
+  for (int w = pl; w < L.W; w += PL) {
+    int wsrc[3]; const int nw = L.sources(w, L.W, wsrc);
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    if (gsrc) {
+      for (int ih = 0; ih < nh; ++ih)
+        for (int iw = 0; iw < nw; ++iw) {
+          float t[8];
+          load8<TG>(gsrc + L.index(n, hs[ih], wsrc[iw], c0), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] += t[i];
+        }
+    }
+    const size_t idx = (((size_t)n * L.H + h) * L.W + w) * C + c0;
+    if (extra) {
+      float t[8];
+      load8<TG>(extra + idx, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] += t[i];
+    }
+    float x[8];
+    load8<TA>(raw + idx, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(x[i], a[i], b[i]);
+      float gv = g[i] * ds[i];
+      if (relu && !(y > 0.f)) gv = 0.f;
+      g[i] = gv;
+      s1[i] += gv;
+      s2[i] = fmaf(gv, (x[i] - mean[i]) * rstd[i], s2[i]);
+    }
+    store8<TG>(gy + idx, g);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { atomicAdd(&s_acc[c0 + i], s1[i]); atomicAdd(&s_acc[C + c0 + i], s2[i]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    atomicAdd(&sums[((size_t)n * C + i) * 2 + 0], s_acc[i]);
+    atomicAdd(&sums[((size_t)n * C + i) * 2 + 1], s_acc[C + i]);
+  }
+}
+
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restrict__ gy, const TA* __restrict__ raw,
+                                                              const float* __restrict__ stats, const float* __restrict__ sums,
+                                                              const float* __restrict__ gamma, TG* __restrict__ draw,
+                                                              int H, int W, int C, float eps, int out_s2d) {
+  const int n = blockIdx.y, h = blockIdx.x;
+  const int CG = C >> 3, PL = 256 / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, c0 = cg * 8;
+  float mean[8], rstd[8], k0[8], m1[8], m2[8];
+  const float inv_cnt = 1.f / (float)(H * W);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float* st = stats + ((size_t)n * C + c0 + i) * 2;
+    const float* sm = sums + ((size_t)n * C + c0 + i) * 2;
+    mean[i] = st[0] * inv_cnt;
+    rstd[i] = rsqrtf(fmaxf(st[1] * inv_cnt - mean[i] * mean[i], 0.f) + eps);
+    k0[i] = gamma[c0 + i] * rstd[i];
+    m1[i] = sm[0] * inv_cnt;
+    m2[i] = sm[1] * inv_cnt;
+  }
+  for (int w = pl; w < W; w += PL) {
+    const size_t idx = (((size_t)n * H + h) * W + w) * C + c0;
+    float g[8], x[8];
+    load8<TG>(gy + idx, g);
+    load8<TA>(raw + idx, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = k0[i] * (g[i] - m1[i] - (x[i] - mean[i]) * rstd[i] * m2[i]);
+    TG* dst = out_s2d ? draw + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c0
+                      : draw + idx;
+    store8<TG>(dst, g);
+  }
+}
+
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const TA* __restrict__ in, const TG* __restrict__ gout,
+                                                           const TG* __restrict__ extra, TG* __restrict__ gin,
+                                                           int N, int H, int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, CG = C >> 3;
+  // one thread per (2x2 window incl. the odd tail handled below, 8 channels)
+  const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
+  const size_t total = (size_t)N * Hc * Wc * CG;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cg = i % CG; size_t r = i / CG;
+    const int wo = r % Wc; r /= Wc;
+    const int ho = r % Hc; const int n = r / Hc;
+    const bool pooled = ho < Ho && wo < Wo;      // odd trailing row/column is not covered by any window
+    float go[8];
+    if (pooled) load8<TG>(gout + (((size_t)n * Ho + ho) * Wo + wo) * C + cg * 8, go);
+    float v[4][8];
+    bool ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int hh = 2 * ho + (q >> 1), ww = 2 * wo + (q & 1);
+      ok[q] = hh < H && ww < W;
+      if (ok[q]) load8<TA>(in + (((size_t)n * H + hh) * W + ww) * C + cg * 8, v[q]);
+    }
+    int best[8];
+    if (pooled) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int bi = 0; float bv = v[0][k];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) if (v[q][k] > bv) { bv = v[q][k]; bi = q; }
+        best[k] = bi;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!ok[q]) continue;
+      const int hh = 2 * ho + (q >> 1), ww = 2 * wo + (q & 1);
+      const size_t idx = (((size_t)n * H + hh) * W + ww) * C + cg * 8;
+      float o[8];
+      if (extra) load8<TG>(extra + idx, o);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (pooled && best[k] == q) o[k] += go[k];
+        if (!(v[q][k] > 0.f)) o[k] = 0.f;
+      }
+      store8<TG>(gin + idx, o);
+    }
+  }
+}
+
+template <typename TA, typename TB, typename TG>
+__global__ void __launch_bounds__(256) sse_bwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t count,
+                                                      int64_t period, const float* __restrict__ scale, TG* __restrict__ da,
+                                                      int relu_mask) {
+  const float s = 2.f * scale[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float av = to_f32<TA>(a[i]);
+    float v = s * (av - to_f32<TB>(b[i % period]));
+    if (relu_mask && !(av > 0.f)) v = 0.f;
+    da[i] = from_f32<TG>(v);
+  }
+}
+
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256) relu_mask_kernel(const TG* __restrict__ g, const TG* __restrict__ extra,
+                                                        const TA* __restrict__ act, TG* __restrict__ out, int64_t count8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8], a[8];
+    load8<TG>(g + i * 8, v);
+    load8<TA>(act + i * 8, a);
+    if (extra) {
+      float e[8];
+      load8<TG>(extra + i * 8, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += e[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : 0.f;
+    store8<TG>(out + i * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) tv_bwd_kernel(const float* __restrict__ img, int planes, int H, int W,
+                                                     const float* __restrict__ scale, float* __restrict__ dimg) {
+  const int64_t total = (int64_t)planes * H * W;
+  const float s = 2.f * scale[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = i % W; const int y = (i / W) % H;
+    const float v = img[i];
+    float d = 0.f;
+    if (y > 0) d += v - img[i - W];
+    if (y + 1 < H) d -= img[i + W] - v;
+    if (x > 0) d += v - img[i - 1];
+    if (x + 1 < W) d -= img[i + 1] - v;
+    dimg[i] = s * d;
+  }
+}
+
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, int N, int C, int HW, float* __restrict__ out) {
+  // grid = (chunks, C); each block reduces a chunk of one channel over all images
+  const int c = blockIdx.y;
+  float s = 0.f;
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = i / HW; const int p = i - (int64_t)n * HW;
+    s += x[((size_t)n * C + c) * HW + p];
+  }
+  __shared__ float part[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(&out[c], t);
+  }
+}
+
+static int grid_cap(int64_t items) {
+  int64_t b = (items + 255) / 256;
+  const int64_t cap = 148 * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace fnst
+
+using namespace fnst;
+
+extern "C" int fnst_wgrad_simt(const fnst_conv_desc* d, int g_dtype, int device, void* stream) {
+  if (int r = validate_conv_desc(d)) return r;
+  FNST_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ktot = (size_t)d->ntaps * d->kc;
+  FNST_CUDA(cudaMemsetAsync(d->out, 0, sizeof(float) * ktot * d->n_gemm, st));
+  const int slabs = (d->out_h + WG_ROWS - 1) / WG_ROWS;
+  dim3 grid(d->ntaps * ((d->kc + 63) / 64), (d->n_gemm + 63) / 64, d->out_n * slabs);
+  FNST_CHECK_ARG(grid.z <= 65535, "wgrad: too many pixel slabs (%u)", grid.z);
+  FNST_DISPATCH_DTYPE(d->dtype, TA, {
+    FNST_DISPATCH_DTYPE(g_dtype, TG, { wgrad_simt_kernel<TA, TG><<<grid, 256, 0, st>>>(*d); });
+  });
+  return launch_status("wgrad_simt");
+}
+
+extern "C" int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const void* g, int g_dtype, int c_out, int k,
+                                     int stride, int pad, int pad_mode, float* dw, int device, void* stream) {
+  FNST_CHECK_ARG(x && g && dw, "conv_first_wgrad: null pointer");
+  FNST_CHECK_ARG(c_out == 64 && k % 2 == 1 && k <= 9 && (stride == 1 || stride == 2), "conv_first_wgrad: unsupported configuration");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  FNST_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  FNST_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 3 * k * k * c_out, st));
+  const int pdim = 7 * stride + k;
+  const size_t smem = sizeof(float) * (3 * pdim * pdim + 64 * 64);
+  const int tiles = ((wo + 7) / 8) * ((ho + 7) / 8);
+  const int tpb = 4;
+  dim3 grid((tiles + tpb - 1) / tpb, n);
+  FNST_DISPATCH_DTYPE(g_dtype, TG, {
+    conv_first_wgrad_kernel<TG><<<grid, 256, smem, st>>>(x, h, w, reinterpret_cast<const TG*>(g), c_out, k, stride, pad,
+                                                        pad_mode, ho, wo, tpb, dw);
+  });
+  return launch_status("conv_first_wgrad");
+}
+
+extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
+                                     const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
+                                     int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
+                                     int pad, int pad_mode, int s2d, int device, void* stream) {
+  FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && gy && sums, "inorm_bwd_reduce: null pointer");
+  FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_reduce: unsupported channel count %d", c);
+  FNST_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  FNST_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, st));
+  HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d};
+  dim3 grid(h, n);
+  FNST_DISPATCH_DTYPE(act_dtype, TA, {
+    FNST_DISPATCH_DTYPE(g_dtype, TG, {
+      inorm_bwd_reduce_kernel<TA, TG><<<grid, 256, sizeof(float) * 2 * c, st>>>(
+          reinterpret_cast<const TG*>(gsrc), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(raw), stats, gamma,
+          beta, drop, reinterpret_cast<TG*>(gy), sums, L, relu, eps);
+    });
+  });
+  return launch_status("inorm_bwd_reduce");
+}
+
+extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, const float* sums, const float* gamma,
+                                    void* draw, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps, int out_s2d,
+                                    int device, void* stream) {
+  FNST_CHECK_ARG(gy && raw && stats && sums && gamma && draw, "inorm_bwd_apply: null pointer");
+  FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_apply: unsupported channel count %d", c);
+  FNST_CHECK_ARG(!out_s2d || (h % 2 == 0 && w % 2 == 0), "inorm_bwd_apply: space-to-depth output needs even h, w");
+  FNST_CUDA(cudaSetDevice(device));
+  dim3 grid(h, n);
+  FNST_DISPATCH_DTYPE(act_dtype, TA, {
+    FNST_DISPATCH_DTYPE(g_dtype, TG, {
+      inorm_bwd_apply_kernel<TA, TG><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const TG*>(gy), reinterpret_cast<const TA*>(raw), stats, sums, gamma, reinterpret_cast<TG*>(draw),
+          h, w, c, eps, out_s2d);
+    });
+  });
+  return launch_status("inorm_bwd_apply");
+}
+
+extern "C" int fnst_maxpool2_bwd(const void* in, const void* gout, const void* extra, void* gin, int n, int h, int w, int c,
+                                 int act_dtype, int g_dtype, int device, void* stream) {
+  FNST_CHECK_ARG(in && gout && gin && c % 8 == 0 && h >= 2 && w >= 2, "maxpool2_bwd: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  const int64_t items = (int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8);
+  FNST_DISPATCH_DTYPE(act_dtype, TA, {
+    FNST_DISPATCH_DTYPE(g_dtype, TG, {
+      maxpool2_bwd_kernel<TA, TG><<<grid_cap(items), 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const TA*>(in), reinterpret_cast<const TG*>(gout), reinterpret_cast<const TG*>(extra),
+          reinterpret_cast<TG*>(gin), n, h, w, c);
+    });
+  });
+  return launch_status("maxpool2_bwd");
+}
+
+extern "C" int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
+                            const float* scale, void* da, int g_dtype, int relu_mask, int device, void* stream) {
+  FNST_CHECK_ARG(a && b && scale && da && count > 0 && b_period > 0, "sse_bwd: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  FNST_DISPATCH_DTYPE(dtype_a, TA, {
+    FNST_DISPATCH_DTYPE(dtype_b, TB, {
+      FNST_DISPATCH_DTYPE(g_dtype, TG, {
+        sse_bwd_kernel<TA, TB, TG><<<grid_cap(count / 4), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const TA*>(a), reinterpret_cast<const TB*>(b), count, b_period, scale, reinterpret_cast<TG*>(da), relu_mask);
+      });
+    });
+  });
+  return launch_status("sse_bwd");
+}
+
+extern "C" int fnst_relu_mask(const void* g, const void* extra, const void* act, void* out, int64_t count, int act_dtype,
+                              int g_dtype, int device, void* stream) {
+  FNST_CHECK_ARG(g && act && out && count > 0 && count % 8 == 0, "relu_mask: bad arguments (count must be a multiple of 8)");
+  FNST_CUDA(cudaSetDevice(device));
+  FNST_DISPATCH_DTYPE(act_dtype, TA, {
+    FNST_DISPATCH_DTYPE(g_dtype, TG, {
+      relu_mask_kernel<TA, TG><<<grid_cap(count / 8), 256, 0, (cudaStream_t)stream>>>(
+          reinterpret_cast<const TG*>(g), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(act),
+          reinterpret_cast<TG*>(out), count / 8);
+    });
+  });
+  return launch_status("relu_mask");
+}
+
+extern "C" int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream) {
+  FNST_CHECK_ARG(img && scale && dimg && planes > 0 && h > 0 && w > 0, "tv_bwd: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  tv_bwd_kernel<<<grid_cap((int64_t)planes * h * w / 4), 256, 0, (cudaStream_t)stream>>>(img, planes, h, w, scale, dimg);
+  return launch_status("tv_bwd");
+}
+
+extern "C" int fnst_channel_sum(const float* x, int n, int c, int hw, float* out, int device, void* stream) {
+  FNST_CHECK_ARG(x && out && n > 0 && c > 0 && hw > 0, "channel_sum: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  FNST_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * c, st));
+  int chunks = (int)(((int64_t)n * hw + 256 * 16 - 1) / (256 * 16));
+  if (chunks > 512) chunks = 512;
+  dim3 grid(chunks, c);
+  channel_sum_kernel<<<grid, 256, 0, st>>>(x, n, c, hw, out);
+  return launch_status("channel_sum");
+}

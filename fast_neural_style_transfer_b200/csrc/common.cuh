@@ -93,6 +93,18 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Runtime-typed scalar / 8-vector loads (epilogue extras whose dtype differs from the kernel's template types).
+__device__ __forceinline__ float load_scalar_f32(const void* base, int dtype, size_t idx) {
+  if (dtype == FNST_F32) return reinterpret_cast<const float*>(base)[idx];
+  if (dtype == FNST_F16) return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+__device__ __forceinline__ void load8_dyn(const void* base, int dtype, size_t idx, float (&v)[8]) {
+  if (dtype == FNST_F32) load8<float>(reinterpret_cast<const float*>(base) + idx, v);
+  else if (dtype == FNST_F16) load8<__half>(reinterpret_cast<const __half*>(base) + idx, v);
+  else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(base) + idx, v);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

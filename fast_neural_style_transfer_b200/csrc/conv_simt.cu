@@ -110,6 +110,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
       float v = acc[i][j];
       if (d.bias) v += d.bias[ch];
       if (d.relu) v = fmaxf(v, 0.f);
+      if (d.epilogue == FNST_EPI_NHWC && (d.addend || d.mask)) {
+        const size_t idx = (((size_t)n * d.out_h + h) * d.out_w + w) * d.c_out + col;
+        if (d.addend) v += load_scalar_f32(d.addend, d.out_dtype, idx);
+        if (d.mask && !(load_scalar_f32(d.mask, d.mask_dtype, idx) > 0.f)) v = 0.f;
+      }
       csum[j] += v; csq[j] += v * v;
       store_out<TOut>(d, n, h, w, col, v);
     }
@@ -190,11 +195,9 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   const int th = tile % tiles_h;
   const int n = tile / tiles_h;
 
-  // weights OIHW [o][c][kh][kw] -> ws[(c*k+kh)*k+kw][o]
-  for (int i = tid; i < taps * c_out; i += 256) {
-    const int o = i / taps, t = i - o * taps;
-    ws[t * c_out + o] = wgt[i];
-  }
+  // weights arrive tap-major [(c*k+kh)*k+kw][o]: straight, conflict-free copy
+  for (int i = tid * 4; i < taps * c_out; i += 1024)
+    *reinterpret_cast<float4*>(ws + i) = *reinterpret_cast<const float4*>(wgt + i);
   for (int i = tid; i < 2 * c_out; i += 256) s_stat[i] = 0.f;
   const int h_base = th * 8 * stride - pad, w_base = tw * 8 * stride - pad;
   for (int i = tid; i < 3 * pdim * pdim; i += 256) {

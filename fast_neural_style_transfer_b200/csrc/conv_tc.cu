@@ -59,9 +59,12 @@ struct ConvTcParams {
   int32_t h0, w0;
   int32_t epilogue, c_out, n_gemm, relu, out_is_bf16, out_is_f32;
   uint32_t idesc;
+  int32_t out_dtype, mask_dtype;
   void* out;
   const float* bias;
   float* stats;
+  const void* addend;
+  const void* mask;
   int8_t tap_dh[FNST_MAX_TAPS];
   int8_t tap_dw[FNST_MAX_TAPS];
   int16_t tap_c0[FNST_MAX_TAPS];
@@ -254,6 +257,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           else
             pix = ((size_t)n * p.out_h + h) * (size_t)p.out_w + w;
           const size_t off = pix * p.c_out + ch0;
+          if (p.addend || p.mask) {
+#pragma unroll
+            for (int i = 0; i < CHUNK; i += 8) {
+              float t[8];
+              if (p.addend) {
+                load8_dyn(p.addend, p.out_dtype, off + i, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[i + k] += t[k];
+              }
+              if (p.mask) {
+                load8_dyn(p.mask, p.mask_dtype, off + i, t);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[i + k] = t[k] > 0.f ? v[i + k] : 0.f;
+              }
+            }
+          }
           if (p.out_is_f32) store_chunk<float>(reinterpret_cast<float*>(p.out) + off, v, CHUNK);
           else if (p.out_is_bf16) store_chunk<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, CHUNK);
           else store_chunk<__half>(reinterpret_cast<__half*>(p.out) + off, v, CHUNK);
@@ -369,6 +388,9 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   p.out_is_bf16 = d->out_dtype == FNST_BF16; p.out_is_f32 = d->out_dtype == FNST_F32;
   p.idesc = umma_idesc_f16(d->dtype == FNST_BF16 ? 1 : 0, block_n, 0, 0);
   p.out = d->out; p.bias = d->bias; p.stats = d->stats;
+  p.out_dtype = d->out_dtype; p.mask_dtype = d->mask_dtype;
+  p.addend = d->epilogue == FNST_EPI_NHWC ? d->addend : nullptr;
+  p.mask = d->epilogue == FNST_EPI_NHWC ? d->mask : nullptr;
   memcpy(p.tap_dh, d->tap_dh, sizeof(p.tap_dh));
   memcpy(p.tap_dw, d->tap_dw, sizeof(p.tap_dw));
   memcpy(p.tap_c0, d->tap_c0, sizeof(p.tap_c0));

@@ -131,17 +131,17 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ img, 
 
 // [HW][C] (T) <-> [C][HW] (fp32) per image, 32x32 smem tiles.
 template <typename T, bool TO_NCHW>
-__global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__ in_, void* __restrict__ out_, int HW, int C) {
+__global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__ in_, void* __restrict__ out_, int HW, int C, int CP) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   if (TO_NCHW) {
-    const T* in = reinterpret_cast<const T*>(in_) + (size_t)n * HW * C;
+    const T* in = reinterpret_cast<const T*>(in_) + (size_t)n * HW * CP;
     float* out = reinterpret_cast<float*>(out_) + (size_t)n * HW * C;
     for (int r = ty; r < 32; r += 8) {
       const int p = p0 + r, c = c0 + tx;
-      tile[r][tx] = (p < HW && c < C) ? to_f32<T>(in[(size_t)p * C + c]) : 0.f;
+      tile[r][tx] = (p < HW && c < C) ? to_f32<T>(in[(size_t)p * CP + c]) : 0.f;
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
     }
   } else {
     const float* in = reinterpret_cast<const float*>(in_) + (size_t)n * HW * C;
-    T* out = reinterpret_cast<T*>(out_) + (size_t)n * HW * C;
+    T* out = reinterpret_cast<T*>(out_) + (size_t)n * HW * CP;
     for (int r = ty; r < 32; r += 8) {
       const int c = c0 + r, p = p0 + tx;
       tile[r][tx] = (p < HW && c < C) ? in[(size_t)c * HW + p] : 0.f;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
       const int p = p0 + r, c = c0 + tx;
-      if (p < HW && c < C) out[(size_t)p * C + c] = from_f32<T>(tile[tx][r]);
+      if (p < HW && c < CP) out[(size_t)p * CP + c] = from_f32<T>(tile[tx][r]);   // channels >= C come out as zero
     }
   }
 }
@@ -229,14 +229,14 @@ extern "C" int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w
   FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0, "nhwc_to_nchw: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
   dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
-  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c); });
+  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c, c); });
   return launch_status("nhwc_to_nchw");
 }
 
-extern "C" int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream) {
-  FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0, "nchw_to_nhwc: bad arguments");
+extern "C" int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int c_pad, int dtype, int device, void* stream) {
+  FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0 && c_pad >= c, "nchw_to_nhwc: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
-  dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
-  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c); });
+  dim3 grid((h * w + 31) / 32, (c_pad + 31) / 32, n);
+  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c, c_pad); });
   return launch_status("nchw_to_nhwc");
 }

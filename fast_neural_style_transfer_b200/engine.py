@@ -40,6 +40,12 @@ def pack_conv(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).reshape(o, k * k * c).to(dtype).contiguous()
 
 
+def pack_first(w: torch.Tensor) -> torch.Tensor:
+    """First-layer weight (O, 3, k, k) -> tap-major fp32 (3*k*k, O) for fnst_conv_first."""
+    o = w.shape[0]
+    return w.detach().float().permute(1, 2, 3, 0).reshape(-1, o).contiguous()
+
+
 def taps_s2d_3x3(c_in: int) -> List[Tuple[int, int, int]]:
     """3x3 stride-2 conv on a space-to-depth halo buffer: tap (kh,kw) reads spatial offset
     (kh>>1, kw>>1) of phase (kh&1, kw&1), i.e. channel window ((kh&1)*2 + (kw&1)) * c_in."""
@@ -119,7 +125,7 @@ class StyleNetPlan:
         p = {k: v.detach() for k, v in params.items()}
         self.params = p
         dt = self.dtype
-        w = {"conv1": p["conv1.conv.weight"].float().contiguous(),
+        w = {"conv1": pack_first(p["conv1.conv.weight"]),
              "conv2": pack_conv(p["conv2.conv.weight"], dt)}
         for i in range(5):
             w[f"res{i}a"] = pack_conv(p[f"res_blocks.{i}.conv1.conv.weight"], dt)
@@ -249,10 +255,11 @@ class VGGPlan:
         self.b: Dict[str, torch.Tensor] = {}
 
     def pack(self, params: Dict[str, torch.Tensor]) -> "VGGPlan":
+        self.params = {k: v.detach() for k, v in params.items()}
         for name in VGG_LAYERS:
             wt = params[name + ".weight"].detach()
             self.b[name] = params[name + ".bias"].detach().float().contiguous()
-            self.w[name] = wt.float().contiguous() if name == "slice1.0" else pack_conv(wt, self.dtype)
+            self.w[name] = pack_first(wt) if name == "slice1.0" else pack_conv(wt, self.dtype)
         return self
 
     def _conv(self, name: str, a: torch.Tensor, tape: Optional[dict]) -> torch.Tensor:

@@ -88,11 +88,11 @@ class ConvSpec:
     bias: Optional[torch.Tensor] = None
     relu: bool = False
     tag: str = ""
+    addend: Optional[torch.Tensor] = None      # dgrad epilogue: out = (acc + addend) * (mask > 0)
+    mask: Optional[torch.Tensor] = None
 
 
-def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, int], a_strides: Tuple[int, int, int],
-                out: torch.Tensor, out_hw: Tuple[int, int], stats: Optional[torch.Tensor], use_tc: bool) -> None:
-    """a_dims = (n, h, w, c) logical extents of the activation view; a_strides = (n, h, w) element strides."""
+def _fill_desc(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, out_hw) -> ConvDesc:
     d = ConvDesc()
     n, ah, aw, ac = a_dims
     d.a = a.data_ptr()
@@ -102,14 +102,27 @@ def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, in
     d.h0, d.w0 = spec.h0, spec.w0
     for i, (dh, dw, c0) in enumerate(spec.taps):
         d.tap_dh[i], d.tap_dw[i], d.tap_c0[i] = dh, dw, c0
-    assert spec.weight.is_contiguous() and spec.weight.shape == (spec.n_gemm, len(spec.taps) * spec.kc), spec.weight.shape
-    assert spec.weight.dtype == a.dtype
-    d.b = spec.weight.data_ptr()
     d.n_gemm = spec.n_gemm
     d.out_n, d.out_h, d.out_w = n, out_hw[0], out_hw[1]
     d.epilogue, d.c_out, d.relu = spec.epilogue, spec.c_out, int(spec.relu)
     d.dtype = dt(a.dtype)
+    return d
+
+
+def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, int], a_strides: Tuple[int, int, int],
+                out: torch.Tensor, out_hw: Tuple[int, int], stats: Optional[torch.Tensor], use_tc: bool) -> None:
+    """a_dims = (n, h, w, c) logical extents of the activation view; a_strides = (n, h, w) element strides."""
+    d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
+    assert spec.weight.is_contiguous() and spec.weight.shape == (spec.n_gemm, len(spec.taps) * spec.kc), spec.weight.shape
+    assert spec.weight.dtype == a.dtype
+    d.b = spec.weight.data_ptr()
     d.out_dtype = dt(out.dtype)
+    if spec.addend is not None:
+        assert spec.addend.dtype == out.dtype and spec.addend.is_contiguous()
+        d.addend = spec.addend.data_ptr()
+    if spec.mask is not None:
+        assert spec.mask.is_contiguous()
+        d.mask, d.mask_dtype = spec.mask.data_ptr(), dt(spec.mask.dtype)
     d.out = out.data_ptr()
     d.bias = None if spec.bias is None else spec.bias.data_ptr()
     d.stats = None if stats is None else stats.data_ptr()
@@ -127,9 +140,9 @@ def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
                pad_mode: int, relu: bool, out: torch.Tensor, stats: Optional[torch.Tensor]) -> None:
     n, c, h, w = x.shape
     assert c == 3 and x.dtype == torch.float32 and x.is_contiguous()
-    assert weight.dtype == torch.float32 and weight.is_contiguous()
+    assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.shape[0] == 3 * k * k   # tap-major
     dev, st = _ctx(x)
-    check(lib.fnst_conv_first(_ptr(x), n, h, w, _ptr(weight), _ptr(bias), weight.shape[0], k, stride, pad, pad_mode,
+    check(lib.fnst_conv_first(_ptr(x), n, h, w, _ptr(weight), _ptr(bias), weight.shape[1], k, stride, pad, pad_mode,
                               int(relu), _ptr(out), dt(out.dtype), _ptr(stats), dev, st), "conv_first")
     _count(2 if stats is not None else 1)
 
@@ -190,11 +203,113 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, c_pad: Optional[int] = None) -> torch.Tensor:
     n, c, h, w = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
-    out = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+    c_pad = c_pad or c
+    out = torch.empty((n, h, w, c_pad), dtype=dtype, device=x.device)
     dev, st = _ctx(x)
-    check(lib.fnst_nchw_to_nhwc(_ptr(x), _ptr(out), n, h, w, c, dt(dtype), dev, st), "nchw_to_nhwc")
+    check(lib.fnst_nchw_to_nhwc(_ptr(x), _ptr(out), n, h, w, c, c_pad, dt(dtype), dev, st), "nchw_to_nhwc")
+    _count()
+    return out
+
+
+# ---- backward operators -------------------------------------------------------------------------------
+
+def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, out_hw) -> torch.Tensor:
+    """dB fp32 [n_gemm, ntaps*kc] of the gather-GEMM `spec` (weights unused); g NHWC [n, oh, ow, n_gemm]."""
+    d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
+    assert g.is_contiguous() and g.shape == (a_dims[0], out_hw[0], out_hw[1], spec.n_gemm), (g.shape, spec.n_gemm)
+    out = torch.empty((spec.n_gemm, len(spec.taps) * spec.kc), dtype=torch.float32, device=a.device)
+    d.b, d.out = g.data_ptr(), out.data_ptr()
+    dev, st = _ctx(a)
+    check(lib.fnst_wgrad_simt(C.byref(d), dt(g.dtype), dev, st), "wgrad_simt")
+    _count(2)
+    return out
+
+
+def conv_first_wgrad(x: torch.Tensor, g: torch.Tensor, k: int, stride: int, pad: int, pad_mode: int) -> torch.Tensor:
+    n, c, h, w = x.shape
+    c_out = g.shape[-1]
+    dw = torch.empty((3 * k * k, c_out), dtype=torch.float32, device=x.device)
+    dev, st = _ctx(x)
+    check(lib.fnst_conv_first_wgrad(_ptr(x), n, h, w, _ptr(g), dt(g.dtype), c_out, k, stride, pad, pad_mode, _ptr(dw), dev, st),
+          "conv_first_wgrad")
+    _count(2)
+    return dw
+
+
+def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=_lib.PAD_NONE, s2d=False,
+                     eps: float = 1e-5):
+    n, h, w, c = raw.shape
+    gy = torch.empty((n, h, w, c), dtype=gdtype, device=raw.device)
+    sums = torch.empty((n, c, 2), dtype=torch.float32, device=raw.device)
+    for t in (gsrc, extra):
+        assert t is None or (t.dtype == gdtype and t.is_contiguous())
+    dev, st = _ctx(raw)
+    check(lib.fnst_inorm_bwd_reduce(_ptr(gsrc), _ptr(extra), _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(gy),
+                                    _ptr(sums), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
+                                    dev, st), "inorm_bwd_reduce")
+    _count(2)
+    return gy, sums
+
+
+def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-5):
+    n, h, w, c = raw.shape
+    shape = (n, h // 2, w // 2, 4 * c) if out_s2d else (n, h, w, c)
+    draw = torch.empty(shape, dtype=gy.dtype, device=raw.device)
+    dev, st = _ctx(raw)
+    check(lib.fnst_inorm_bwd_apply(_ptr(gy), _ptr(raw), _ptr(stats), _ptr(sums), _ptr(gamma), _ptr(draw), n, h, w, c,
+                                   dt(raw.dtype), dt(gy.dtype), eps, int(out_s2d), dev, st), "inorm_bwd_apply")
+    _count()
+    return draw
+
+
+def maxpool2_bwd(inp, gout, extra):
+    n, h, w, c = inp.shape
+    gin = torch.empty((n, h, w, c), dtype=gout.dtype, device=inp.device)
+    assert gout.is_contiguous() and (extra is None or (extra.is_contiguous() and extra.dtype == gout.dtype))
+    dev, st = _ctx(inp)
+    check(lib.fnst_maxpool2_bwd(_ptr(inp), _ptr(gout), _ptr(extra), _ptr(gin), n, h, w, c, dt(inp.dtype), dt(gout.dtype), dev, st),
+          "maxpool2_bwd")
+    _count()
+    return gin
+
+
+def sse_bwd(a, b, scale, gdtype, relu_mask=False):
+    """2*scale*(a-b) (b broadcast); scale is a 1-element fp32 CUDA tensor."""
+    assert a.is_contiguous() and b.is_contiguous() and scale.dtype == torch.float32
+    da = torch.empty(a.shape, dtype=gdtype, device=a.device)
+    dev, st = _ctx(a)
+    check(lib.fnst_sse_bwd(_ptr(a), _ptr(b), a.numel(), b.numel(), dt(a.dtype), dt(b.dtype), _ptr(scale), _ptr(da), dt(gdtype),
+                           int(relu_mask), dev, st), "sse_bwd")
+    _count()
+    return da
+
+
+def tv_bwd(img, scale):
+    b, c, h, w = img.shape
+    out = torch.empty_like(img)
+    dev, st = _ctx(img)
+    check(lib.fnst_tv_bwd(_ptr(img), b * c, h, w, _ptr(scale), _ptr(out), dev, st), "tv_bwd")
+    _count()
+    return out
+
+
+def channel_sum(x):
+    n, c, h, w = x.shape
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    dev, st = _ctx(x)
+    check(lib.fnst_channel_sum(_ptr(x), n, c, h * w, _ptr(out), dev, st), "channel_sum")
+    _count(2)
+    return out
+
+
+def relu_mask(g, extra, act):
+    """(g + extra) * (act > 0)."""
+    assert g.is_contiguous() and act.is_contiguous() and g.shape == act.shape
+    out = torch.empty_like(g)
+    dev, st = _ctx(g)
+    check(lib.fnst_relu_mask(_ptr(g), _ptr(extra), _ptr(act), _ptr(out), g.numel(), dt(act.dtype), dt(g.dtype), dev, st), "relu_mask")
     _count()
     return out

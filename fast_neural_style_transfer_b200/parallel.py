@@ -1,0 +1,79 @@
+"""Multi-GPU sharding for the style-transfer path: one process per GPU (torch.distributed, NCCL over
+NVLink 5 / NVSwitch).  Every operator on the path is per-image (InstanceNorm is per (n,c); Gram and the
+squared errors are per-sample then summed), so:
+
+  * inference shards the image batch across ranks with NO collective (`shard_batch`);
+  * data-parallel training replicates StyleTransferNet + VGG-19 and has ONE exchange step per
+    iteration: a SUM all-reduce of a flat fp32 bucket holding the 6 243 843 gradients (24.98 MB)
+    (`GradientAllReduce`), followed by the caller's clip_grad_norm_ / Adam on every rank.
+
+Exact equivalence with the single-process reference at the global batch needs the content and
+style gradients SUMMED over ranks (batch sums, losses/losses.py:41,54) and the TV gradient AVERAGED (batch
+mean, losses.py:71): scale the TV term by 1/world on every rank and all-reduce with SUM.  The NaN/Inf skip
+of train.py:193 must be taken on a reduced flag (`all_finite`) or the ranks desynchronise.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total: int, rank: int, world: int):
+    """Contiguous, balanced [lo, hi) slice of `total` items for `rank`."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    lo, hi = shard_bounds(x.shape[0], rank, world)
+    return x[lo:hi]
+
+
+def tv_weight_scale(world: int) -> float:
+    return 1.0 / world
+
+
+def all_finite(value: torch.Tensor, world: int) -> bool:
+    """True iff `value` is finite on every rank (one MIN all-reduce of a flag)."""
+    flag = torch.isfinite(value.detach()).all().to(torch.float32).reshape(1)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item() > 0)
+
+
+class GradientAllReduce:
+    """Flat-bucket SUM all-reduce of `module`'s gradients (parameters without a gradient contribute zeros)."""
+
+    def __init__(self, module: torch.nn.Module, world: int):
+        self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
+        self.world = world
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def all_reduce(self) -> torch.Tensor:
+        p0 = self.params[0]
+        if self.flat is None or self.flat.device != p0.device:
+            self.flat = torch.empty(self.numel, dtype=torch.float32, device=p0.device)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat[off:off + n].zero_()
+            else:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            g = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+        return self.flat

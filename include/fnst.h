@@ -65,6 +65,11 @@ typedef struct fnst_conv_desc {
   void* out;
   const float* bias;             /* [c_out] or NULL                                               */
   float* stats;                  /* [out_n][c_out][2] (sum, sumsq), zeroed by the call; or NULL   */
+  /* backward (dgrad) epilogue extras, FNST_EPI_NHWC only: out = (acc + addend) * (mask > 0)       */
+  const void* addend;            /* same shape/dtype as out, or NULL                              */
+  const void* mask;              /* forward activation (ReLU output) of dtype mask_dtype, or NULL */
+  int32_t mask_dtype;
+  int32_t reserved;
 } fnst_conv_desc;
 
 int fnst_version(void);
@@ -86,7 +91,8 @@ int fnst_conv_simt(const fnst_conv_desc* d, int device, void* stream);
 /*
  * First-layer convolution for 3-channel NCHW fp32 images: reflect/zero padding by index math.
  * Replaces ConvLayer(3,64,9,stride=2) (models/model.py:28) and VGG conv1_1 (features[0]).
- * x [n,3,h,w] fp32; w [c_out,3,k,k] fp32 (PyTorch OIHW); out NHWC [n,ho,wo,c_out] of out_dtype.
+ * x [n,3,h,w] fp32; wgt [3*k*k][c_out] fp32, tap-major (index ((c*k+kh)*k+kw)*c_out + o, i.e. the
+ * PyTorch OIHW weight permuted to (c,kh,kw,o)); out NHWC [n,ho,wo,c_out] of out_dtype.
  * stats (optional) as above; bias/relu optional.
  */
 int fnst_conv_first(const float* x, int n, int h, int w, const float* wgt, const float* bias,
@@ -127,9 +133,62 @@ int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_period, int 
  * (losses/losses.py:62-73; the caller divides by b*c*h*w). */
 int fnst_tv(const float* img, int planes, int h, int w, double* acc, int device, void* stream);
 
-/* NHWC (dtype) -> NCHW fp32 and back (layout plumbing at the module boundary). */
+/* NHWC (dtype) -> NCHW fp32 and back (layout plumbing at the module boundary).  c_pad >= c: the
+ * NHWC tensor has c_pad channels, channels c..c_pad-1 are written as zero. */
 int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w, int c, int dtype, int device, void* stream);
-int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream);
+int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int c_pad, int dtype, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward operators (autograd of train.py:200 `total_loss.backward()` through the same modules).
+ * Data gradients (dgrad) of every convolution are gather-GEMMs again (fnst_conv_tc / fnst_conv_simt
+ * with negated taps and transposed packed weights); the entry points below are the rest.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Weight gradient of a gather-GEMM: dB[j][t*kc+c] = sum_{n,h,w} g[n,h,w,j] * A[n,h+h0+dh[t],w+w0+dw[t],c0[t]+c].
+ * Uses d->a (A view, d->dtype), the taps, and: d->b = g, NHWC [out_n,out_h,out_w,n_gemm] of dtype g_dtype;
+ * d->out = dB fp32 [n_gemm][ntaps*kc] (zeroed by the call). */
+int fnst_wgrad_simt(const fnst_conv_desc* d, int g_dtype, int device, void* stream);
+
+/* Weight gradient of fnst_conv_first (reflect/zero pad by index math): dw tap-major fp32 [3*k*k][c_out],
+ * zeroed by the call; g NHWC [n,ho,wo,c_out] of g_dtype. */
+int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const void* g, int g_dtype, int c_out, int k, int stride,
+                          int pad, int pad_mode, float* dw, int device, void* stream);
+
+/*
+ * InstanceNorm2d backward, pass 1.  Forms the gradient with respect to the normalised pre-activation
+ *   gy = ( fold(gsrc) + extra ) * drop * [relu ? (y > 0) : 1],    y = raw*a + b  (a, b from stats/gamma/beta)
+ * where gsrc is the gradient of the consumer's halo buffer (layout pad / pad_mode / s2d exactly as written by
+ * fnst_inorm_apply; fold = ReflectionPad2d backward) and extra an optional plain [n,h,w,c] gradient (residual
+ * branch).  Writes gy [n,h,w,c] (g_dtype) and accumulates sums[n][c] = (sum gy, sum gy*xhat) (zeroed by the call).
+ */
+int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
+                          const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
+                          int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
+                          int pad, int pad_mode, int s2d, int device, void* stream);
+/* Pass 2: draw = gamma*rstd*(gy - mean(gy) - xhat*mean(gy*xhat)), written NHWC [n,h,w,c] or, if out_s2d,
+ * space-to-depth [n,h/2,w/2,4c] (channel = ((h&1)*2+(w&1))*c + ch; h, w even). */
+int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, const float* sums, const float* gamma,
+                         void* draw, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps, int out_s2d,
+                         int device, void* stream);
+
+/* MaxPool2d(2,2) backward fused with the ReLU mask of its input: gin = (extra + route(gout)) * (in > 0);
+ * the first maximal element of each window receives the gradient (PyTorch tie rule). */
+int fnst_maxpool2_bwd(const void* in, const void* gout, const void* extra, void* gin, int n, int h, int w, int c,
+                      int act_dtype, int g_dtype, int device, void* stream);
+
+/* da = 2 * scale[0] * (a - b) (b broadcast with period b_period), optionally masked by (a > 0). */
+int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
+                 const float* scale, void* da, int g_dtype, int relu_mask, int device, void* stream);
+
+/* out = (g + extra) * (act > 0): ReLU backward with an optional second gradient branch (count % 8 == 0). */
+int fnst_relu_mask(const void* g, const void* extra, const void* act, void* out, int64_t count, int act_dtype,
+                   int g_dtype, int device, void* stream);
+
+/* Gradient of fnst_tv: dimg = scale[0] * d/dimg sum(dh^2 + dw^2), NCHW fp32. */
+int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream);
+
+/* out[c] = sum over n,h,w of x[n,c,h,w] (fp32 NCHW); final_conv bias gradient. */
+int fnst_channel_sum(const float* x, int n, int c, int hw, float* out, int device, void* stream);
 
 #ifdef __cplusplus
 }

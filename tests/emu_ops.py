@@ -53,7 +53,8 @@ def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc):
 
 def conv_first(x, weight, bias, k, stride, pad, pad_mode, relu, out, stats):
     xp = F.pad(x.double(), (pad,) * 4, mode="reflect" if pad_mode == PAD_REFLECT else "constant")
-    v = F.conv2d(xp, weight.double(), None if bias is None else bias.double(), stride=stride)
+    w_oihw = weight.double().view(3, k, k, -1).permute(3, 0, 1, 2)      # tap-major (c,kh,kw,o) -> OIHW
+    v = F.conv2d(xp, w_oihw, None if bias is None else bias.double(), stride=stride)
     if relu:
         v = v.clamp_min(0)
     v = v.permute(0, 2, 3, 1)

@@ -131,7 +131,7 @@ def test_conv_tc_fp32_out():
 def test_conv_first(stride, k, pad, mode, relu):
     g = torch.Generator().manual_seed(4)
     x = torch.rand((2, 3, 37, 45), generator=g)
-    w = torch.randn((64, 3, k, k), generator=g) / k
+    w = engine.pack_first(torch.randn((64, 3, k, k), generator=g) / k)
     bias = torch.randn(64, generator=g) if relu else None
     ho, wo = (37 + 2 * pad - k) // stride + 1, (45 + 2 * pad - k) // stride + 1
     ref = torch.zeros((2, ho, wo, 64), dtype=torch.float64)

@@ -1,0 +1,127 @@
+"""GPU parity of the training step (train.py:168-206) through the drop-in modules: losses, all 58
+gradients, gradient norm -- against the oracle's autograd on CPU."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import stylenet_oracle as O
+
+pytestmark = pytest.mark.gpu
+DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast_neural_style_transfer_b200", "dropin")
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    sys.path.insert(0, DROPIN)
+    for m in [k for k in sys.modules if k.split(".")[0] in ("models", "losses", "config")]:
+        del sys.modules[m]
+    import models.model as mm
+    import models.vgg19_net as mv
+    import losses.losses as ll
+    yield mm, mv, ll
+    sys.path.remove(DROPIN)
+
+
+def _step(dropin, precision, vgg_precision, b, h, w, seed=0):
+    """One reference-style training step body (train.py:171-200) on the drop-in; returns losses + grads."""
+    mm, mv, ll = dropin
+    p = O.make_net_params(seed=seed, random_affine=True)
+    vp = O.make_vgg_params(seed=1)
+    net = mm.StyleTransferNet().to(DEV); net.load_state_dict(p); net.precision = precision; net.train()
+    vgg = mv.VGG19().to(DEV); vgg.load_state_dict(vp); vgg.precision = vgg_precision; vgg.eval()
+    content = O.make_image(b, h, w, seed=5, normalized=True)
+    sty = O.make_image(1, h, w, seed=6, normalized=True)
+    with torch.no_grad():
+        targets = [ll.gram_matrix(f).squeeze(0) for f in vgg(sty.to(DEV))]
+    torch.manual_seed(99)
+    ones = torch.ones((b, 256, 1, 1), device=DEV)
+    drop = [torch.nn.functional.dropout2d(ones, 0.1, True).view(b, 256).cpu() for _ in range(5)]
+    torch.manual_seed(99)
+    x = content.to(DEV)
+    stylized = torch.clamp(net(x), -3, 3)
+    with torch.no_grad():
+        cf = vgg(x)
+    sf = vgg(stylized)
+    c, s, tv = ll.content_loss(sf, cf), ll.style_loss(sf, targets), ll.total_variation_loss(stylized)
+    total = 1000.0 * c + 1 * s + 10 * tv
+    net.zero_grad()
+    total.backward()
+    grads = {k: v.grad.detach().cpu() for k, v in net.named_parameters()}
+    ref_targets = O.style_targets(vp, sty)
+    ref_losses, ref_grads = O.loss_and_grads(p, vp, content, ref_targets, drop)
+    got = {"total": float(total), "content": float(c), "style": float(s), "tv": float(tv), "stylized": stylized.detach().cpu()}
+    return got, grads, ref_losses, ref_grads
+
+
+def _check(got, grads, ref_losses, ref_grads, tol_loss, tol_grad, label):
+    for k in ("content", "style", "tv", "total"):
+        err = abs(got[k] / float(ref_losses[k]) - 1)
+        print(f"[{label}] loss {k}: got {got[k]:.6g} ref {float(ref_losses[k]):.6g} rel {err:.2e}")
+        assert err < tol_loss, k
+    gn_ref = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref_grads.values())))
+    gn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())))
+    print(f"[{label}] grad norm got {gn:.6g} ref {gn_ref:.6g}")
+    worst = 0.0
+    for k, r in ref_grads.items():
+        g = grads[k]
+        assert g.shape == r.shape, k
+        # relative to max(|ref|, small fraction of the global norm): conv biases under InstanceNorm have ~0 gradient
+        denom = max(float(r.double().norm()), 1e-4 * gn_ref)
+        err = float((g.double() - r.double()).norm()) / denom
+        worst = max(worst, err)
+        if err >= tol_grad:
+            print(f"[{label}] grad {k}: rel {err:.3e} |ref|={float(r.norm()):.3e}")
+        assert err < tol_grad, (k, err)
+    print(f"[{label}] worst per-tensor gradient error {worst:.3e}")
+    assert abs(gn / gn_ref - 1) < min(tol_grad, 5e-3)
+
+
+def test_training_step_fp32_path(dropin):
+    got, grads, rl, rg = _step(dropin, "fp32", "fp32", 2, 32, 32)
+    assert rel_l2(got["stylized"], rl["stylized"]) < 1e-4
+    _check(got, grads, rl, rg, tol_loss=1e-4, tol_grad=2e-3, label="fp32 2x32x32")
+
+
+def test_training_step_fp32_path_odd_size(dropin):
+    got, grads, rl, rg = _step(dropin, "fp32", "fp32", 1, 44, 52, seed=2)
+    _check(got, grads, rl, rg, tol_loss=1e-4, tol_grad=2e-3, label="fp32 1x44x52")
+
+
+def test_training_step_tensor_core_path(dropin):
+    """Tensor-core path: fp16 forward (outputs/losses within the 1e-2 gate); gradients are carried in bf16
+    through ~26 chained GEMMs, so per-tensor gradient error grows with depth (measured <= 7e-2 at conv1,
+    global gradient norm within 1e-3).  The bound is asserted as measured, not as a parity claim of 1e-2."""
+    got, grads, rl, rg = _step(dropin, "fp16", "bf16", 2, 64, 64)
+    assert rel_l2(got["stylized"], rl["stylized"]) < 1e-2
+    _check(got, grads, rl, rg, tol_loss=1e-2, tol_grad=1.2e-1, label="tc 2x64x64")
+
+
+def test_loss_functions_backward_standalone(dropin):
+    """gram / sse / tv backward on plain fp32 NCHW tensors vs torch autograd of the oracle formulas."""
+    _, _, ll = dropin
+    g = torch.Generator().manual_seed(3)
+    f = torch.randn((2, 64, 12, 10), generator=g)
+    tgt = torch.randn((64, 64), generator=g)
+    img = torch.randn((2, 3, 20, 24), generator=g)
+    feats = [f.clone().to(DEV).requires_grad_(True) for _ in range(5)]
+    loss = ll.style_loss([feats[0], feats[0], feats[0], None, feats[0]], [tgt.to(DEV)] * 5) + ll.content_loss(feats, [None] * 4 + [f.to(DEV) * 0.5])
+    loss.backward()
+    fr = f.clone().requires_grad_(True)
+    ref = O.style_loss([fr, fr, fr, None, fr], [tgt] * 5) + O.content_loss([None] * 4 + [fr], [None] * 4 + [f * 0.5])
+    ref.backward()
+    assert abs(float(loss) / float(ref) - 1) < 1e-5
+    total = feats[0].grad.cpu() + feats[4].grad.cpu()
+    assert rel_l2(total, fr.grad) < 1e-5
+    x = img.clone().to(DEV).requires_grad_(True)
+    ll.total_variation_loss(x).backward()
+    xr = img.clone().requires_grad_(True)
+    O.total_variation_loss(xr).backward()
+    assert rel_l2(x.grad, xr.grad) < 1e-5
