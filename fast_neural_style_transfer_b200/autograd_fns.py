@@ -20,6 +20,11 @@ def _as_nhwc(feat: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.T
     return ops.nchw_to_nhwc(feat.float().contiguous(), dtype or torch.float32)
 
 
+def _gram_tc_ok(f: torch.Tensor) -> bool:
+    n, h, w, c = f.shape
+    return f.dtype != torch.float32 and c % 64 == 0 and (h * w) % 8 == 0
+
+
 def _need_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{what}: CUDA tensor required (the B200 path has no CPU fallback)")
@@ -32,7 +37,7 @@ class _Gram(torch.autograd.Function):
     def forward(ctx, feat):
         f = _as_nhwc(feat.detach())
         ctx.save_for_backward(f)
-        return ops.gram(f, use_tc=False)
+        return ops.gram(f, use_tc=_gram_tc_ok(f))
 
     @staticmethod
     def backward(ctx, dg):
@@ -45,7 +50,8 @@ def gram(feat: torch.Tensor) -> torch.Tensor:
     _need_cuda(feat, "gram_matrix")
     if torch.is_grad_enabled() and feat.requires_grad:
         return _Gram.apply(feat)
-    return ops.gram(_as_nhwc(feat.detach()), use_tc=False)
+    f = _as_nhwc(feat.detach())
+    return ops.gram(f, use_tc=_gram_tc_ok(f))
 
 
 # ---- sum of squared differences ----------------------------------------------------------------------

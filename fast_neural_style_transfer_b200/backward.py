@@ -71,6 +71,14 @@ def _tc_ok(use_tc: bool, kc: int, n_gemm: int) -> bool:
     return use_tc and kc % 64 == 0 and (n_gemm == 16 or n_gemm % 32 == 0)
 
 
+def _wgrad(tc: bool, spec: ConvSpec, a, a_dims, g, out_hw) -> torch.Tensor:
+    """Weight gradient of `spec`; tensor cores whenever the channel window is a multiple of 64."""
+    use_tc = tc and spec.kc % 64 == 0
+    if use_tc and a.dtype != g.dtype:
+        a = ops.cast(a, g.dtype)         # kind::f16 MMAs need both operands in one 16-bit format
+    return ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc)
+
+
 # -------------------------------------------------------------------------------------------------------
 # StyleTransferNet backward
 # -------------------------------------------------------------------------------------------------------
@@ -103,7 +111,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     act4 = tape["act4"]
     Hq, Wq = act4.shape[1], act4.shape[2]
     taps81 = taps_kxk(9)
-    db = ops.wgrad(ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), _nhwc_strides(act4), g16, (H4, W4))
+    db = _wgrad(tc, ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), g16, (H4, W4))
     grads["final_conv.conv.weight"] = unpack_conv(db, 3, 32, 9)
     wf_plain = engine.pack_final_plain(p["final_conv.conv.weight"], gdt)
     d_act4 = dgrad(g16, (B, H4, W4, 16), wf_plain, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
@@ -115,7 +123,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     d_raw4 = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
     act3 = tape["act3"]
     H3, W3 = act3.shape[1], act3.shape[2]
-    db = ops.wgrad(ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, (B, H3, W3, 64), _nhwc_strides(act3), d_raw4, (H3, W3))
+    db = _wgrad(tc, ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, (B, H3, W3, 64), d_raw4, (H3, W3))
     grads["up2.upsample_conv.weight"] = unpack_conv_transpose(db, 64, 32)
     grads["up2.upsample_conv.bias"] = zeros_like_param("up2.upsample_conv.bias")
     wup2 = plan.w["up2"] if plan.w["up2"].dtype == gdt else engine.pack_conv_transpose(p["up2.upsample_conv.weight"], gdt)
@@ -129,7 +137,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     trunk = tape["trunk"]
     last = trunk[5]
     H2, W2 = last.shape[1], last.shape[2]
-    db = ops.wgrad(ConvSpec(TAPS_2X2, 256, None, 256, 64), last, (B, H2, W2, 256), _nhwc_strides(last), d_raw3, (H2, W2))
+    db = _wgrad(tc, ConvSpec(TAPS_2X2, 256, None, 256, 64), last, (B, H2, W2, 256), d_raw3, (H2, W2))
     grads["up1.upsample_conv.weight"] = unpack_conv_transpose(db, 256, 64)
     grads["up1.upsample_conv.bias"] = zeros_like_param("up1.upsample_conv.bias")
     wup1 = plan.w["up1"] if plan.w["up1"].dtype == gdt else engine.pack_conv_transpose(p["up1.upsample_conv.weight"], gdt)
@@ -149,7 +157,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(sums)
         d_raw_b = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
         mid = blk["mid"]
-        db = ops.wgrad(ConvSpec(taps9, 256, None, 256, 256), mid, pdims, _nhwc_strides(mid), d_raw_b, (H2, W2))
+        db = _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2))
         grads[pre + ".conv2.conv.weight"] = unpack_conv(db, 256, 256, 3)
         grads[pre + ".conv2.conv.bias"] = zeros_like_param(pre + ".conv2.conv.bias")
         wb = plan.w[f"res{i}b"] if plan.w[f"res{i}b"].dtype == gdt else engine.pack_conv(p[pre + ".conv2.conv.weight"], gdt)
@@ -160,7 +168,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(sums)
         d_raw_a = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
         cur = trunk[i]
-        db = ops.wgrad(ConvSpec(taps9, 256, None, 256, 256), cur, pdims, _nhwc_strides(cur), d_raw_a, (H2, W2))
+        db = _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2))
         grads[pre + ".conv1.conv.weight"] = unpack_conv(db, 256, 256, 3)
         grads[pre + ".conv1.conv.bias"] = zeros_like_param(pre + ".conv1.conv.bias")
         wa = plan.w[f"res{i}a"] if plan.w[f"res{i}a"].dtype == gdt else engine.pack_conv(p[pre + ".conv1.conv.weight"], gdt)
@@ -174,7 +182,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     d_raw2 = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
     buf2 = tape["buf2"]
     Hs, Ws = buf2.shape[1], buf2.shape[2]
-    db = ops.wgrad(ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, (B, Hs, Ws, 256), _nhwc_strides(buf2), d_raw2, (H2, W2))
+    db = _wgrad(tc, ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, (B, Hs, Ws, 256), d_raw2, (H2, W2))
     grads["conv2.conv.weight"] = unpack_conv(db, 256, 64, 3)
     grads["conv2.conv.bias"] = zeros_like_param("conv2.conv.bias")
     wd2 = pack_dgrad_s2d(p["conv2.conv.weight"], gdt)

@@ -163,6 +163,15 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
   }
 }
 
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t count8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8<TI>(in + i * 8, v);
+    store8<TO>(out + i * 8, v);
+  }
+}
+
 static int grid_for(int64_t work_items, int threads = 256) {
   int64_t b = (work_items + threads - 1) / threads;
   const int64_t cap = 148 * 16;
@@ -239,4 +248,16 @@ extern "C" int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w
   dim3 grid((h * w + 31) / 32, (c_pad + 31) / 32, n);
   FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c, c_pad); });
   return launch_status("nchw_to_nhwc");
+}
+
+extern "C" int fnst_cast(const void* in, void* out, int64_t count, int in_dtype, int out_dtype, int device, void* stream) {
+  FNST_CHECK_ARG(in && out && count > 0 && count % 8 == 0, "cast: bad arguments (count must be a multiple of 8)");
+  FNST_CUDA(cudaSetDevice(device));
+  FNST_DISPATCH_DTYPE(in_dtype, TI, {
+    FNST_DISPATCH_DTYPE(out_dtype, TO, {
+      cast_kernel<TI, TO><<<grid_for(count / 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const TI*>(in),
+                                                                                  reinterpret_cast<TO*>(out), count / 8);
+    });
+  });
+  return launch_status("cast");
 }

@@ -216,14 +216,19 @@ def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, c_pad: Optional[int] = Non
 
 # ---- backward operators -------------------------------------------------------------------------------
 
-def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, out_hw) -> torch.Tensor:
+def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, out_hw, use_tc: bool = False) -> torch.Tensor:
     """dB fp32 [n_gemm, ntaps*kc] of the gather-GEMM `spec` (weights unused); g NHWC [n, oh, ow, n_gemm]."""
     d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
     assert g.is_contiguous() and g.shape == (a_dims[0], out_hw[0], out_hw[1], spec.n_gemm), (g.shape, spec.n_gemm)
     out = torch.empty((spec.n_gemm, len(spec.taps) * spec.kc), dtype=torch.float32, device=a.device)
     d.b, d.out = g.data_ptr(), out.data_ptr()
     dev, st = _ctx(a)
-    check(lib.fnst_wgrad_simt(C.byref(d), dt(g.dtype), dev, st), "wgrad_simt")
+    fn = lib.fnst_wgrad_tc if use_tc else lib.fnst_wgrad_simt
+    timed = kernel_timer is not None and kernel_timer.wants(spec.tag)
+    e0 = kernel_timer.start() if timed else None
+    check(fn(C.byref(d), dt(g.dtype), dev, st), "wgrad_tc" if use_tc else "wgrad_simt")
+    if timed:
+        kernel_timer.stop(e0)
     _count(2)
     return out
 
@@ -311,5 +316,14 @@ def relu_mask(g, extra, act):
     out = torch.empty_like(g)
     dev, st = _ctx(g)
     check(lib.fnst_relu_mask(_ptr(g), _ptr(extra), _ptr(act), _ptr(out), g.numel(), dt(act.dtype), dt(g.dtype), dev, st), "relu_mask")
+    _count()
+    return out
+
+
+def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    assert x.is_contiguous()
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    dev, st = _ctx(x)
+    check(lib.fnst_cast(_ptr(x), _ptr(out), x.numel(), dt(x.dtype), dt(dtype), dev, st), "cast")
     _count()
     return out

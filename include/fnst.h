@@ -148,6 +148,9 @@ int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, in
  * Uses d->a (A view, d->dtype), the taps, and: d->b = g, NHWC [out_n,out_h,out_w,n_gemm] of dtype g_dtype;
  * d->out = dB fp32 [n_gemm][ntaps*kc] (zeroed by the call). */
 int fnst_wgrad_simt(const fnst_conv_desc* d, int g_dtype, int device, void* stream);
+/* Same on tensor cores (tcgen05, MN-major operands, split over pixels with fp32 L2 atomics):
+ * operand dtypes fp16/bf16 (they may differ), kc % 64 == 0. */
+int fnst_wgrad_tc(const fnst_conv_desc* d, int g_dtype, int device, void* stream);
 
 /* Weight gradient of fnst_conv_first (reflect/zero pad by index math): dw tap-major fp32 [3*k*k][c_out],
  * zeroed by the call; g NHWC [n,ho,wo,c_out] of g_dtype. */
@@ -186,6 +189,10 @@ int fnst_relu_mask(const void* g, const void* extra, const void* act, void* out,
 
 /* Gradient of fnst_tv: dimg = scale[0] * d/dimg sum(dh^2 + dw^2), NCHW fp32. */
 int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream);
+
+/* Element-type conversion of a contiguous tensor (count % 8 == 0).  tcgen05 kind::f16 needs both operands in the
+ * same 16-bit format, so saved fp16 activations are converted to the bf16 gradient format for fnst_wgrad_tc. */
+int fnst_cast(const void* in, void* out, int64_t count, int in_dtype, int out_dtype, int device, void* stream);
 
 /* out[c] = sum over n,h,w of x[n,c,h,w] (fp32 NCHW); final_conv bias gradient. */
 int fnst_channel_sum(const float* x, int n, int c, int hw, float* out, int device, void* stream);

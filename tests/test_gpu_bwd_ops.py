@@ -77,6 +77,13 @@ def test_wgrad_and_dgrad(kind, gdtype):
     db = ops.wgrad(ConvSpec(taps, kc, None, n_gemm, n_gemm), a.to(DEV), a_dims, engine._nhwc_strides(a), gout.to(DEV), ohw)
     tol = 1e-5 if gdtype == torch.float32 else 2e-3
     assert rel_l2(db, w64.grad) < tol
+    if gdtype != torch.float32 and kc % 64 == 0:      # tensor-core wgrad: fp16 activations x bf16 gradients, fp32 accumulate
+        a_b = ops.cast(a.to(DEV), gdtype)                 # same 16-bit format on both operands (mixed formats are illegal)
+        db_tc = ops.wgrad(ConvSpec(taps, kc, None, n_gemm, n_gemm), a_b, a_dims, engine._nhwc_strides(a), gout.to(DEV), ohw, use_tc=True)
+        (_emu_conv(ConvSpec(taps, kc, w64.detach().clone().requires_grad_(True), n_gemm, n_gemm), a_b.cpu().double(), a_dims, None, ohw)).sum()
+        w65 = packed.clone().requires_grad_(True)
+        (_emu_conv(ConvSpec(taps, kc, w65, n_gemm, n_gemm), a_b.cpu().double(), a_dims, None, ohw) * gout.double()).sum().backward()
+        assert rel_l2(db_tc, w65.grad) < 1e-5, "tensor-core wgrad is not the exact fp32-accumulated product of its operands"
     # dgrad as a gather-GEMM on gout
     if kind == "s2d":
         wd = backward.pack_dgrad_s2d(wt, gdtype)
@@ -189,3 +196,14 @@ def test_pool_mask_sse_tv_backward(gdtype):
     (((i64[:, :, 1:] - i64[:, :, :-1]) ** 2).sum() + ((i64[:, :, :, 1:] - i64[:, :, :, :-1]) ** 2).sum()).backward()
     assert rel_l2(ops.tv_bwd(img.to(DEV), scale), 0.37 * i64.grad) < 1e-6
     assert rel_l2(ops.channel_sum(img.to(DEV)), img.double().sum((0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 24, 8, 128), (2, 12, 6, 256), (1, 4, 4, 512)])
+def test_gram_tc(shape, dtype):
+    g = torch.Generator().manual_seed(25)
+    f = torch.relu(torch.randn(shape, generator=g)).to(dtype)
+    ref = emu_ops.gram(f, False)                                   # exact Gram of the rounded features
+    got = ops.gram(f.to(DEV), use_tc=True)
+    assert rel_l2(got, ref) < 1e-5
+    assert rel_l2(ops.gram(f.to(DEV), use_tc=False), ref) < 1e-5
