@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("mask", C.c_void_p),
         ("mask_dtype", C.c_int32),
         ("reserved", C.c_int32),
+        ("g_stride_w", C.c_int64), ("g_stride_h", C.c_int64), ("g_stride_n", C.c_int64),
     ]
 
 

@@ -107,14 +107,34 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 
     # ---- final_conv (9x9, 32 -> 3) -------------------------------------------------------------------
     grads["final_conv.conv.bias"] = ops.channel_sum(dy)
-    g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
     act4 = tape["act4"]
     Hq, Wq = act4.shape[1], act4.shape[2]
     taps81 = taps_kxk(9)
-    db = _wgrad(tc, ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), g16, (H4, W4))
-    grads["final_conv.conv.weight"] = unpack_conv(db, 3, 32, 9)
-    wf_plain = engine.pack_final_plain(p["final_conv.conv.weight"], gdt)
-    d_act4 = dgrad(g16, (B, H4, W4, 16), wf_plain, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
+    wfin = p["final_conv.conv.weight"]
+    if tc:
+        # Tensor-core form: dy padded to 64 channels (one 128-byte row per pixel).
+        #  wgrad: M side = 4-pixel window view of act4 (128 = 4 x 32 channels, unshifted), N side = dy shifted by
+        #         (-kh, -4m): D[(jj,c)][(kh,m,j)] = dW[j][c][kh][4m+jj]   (27 taps instead of 81, K = pixels)
+        #  dgrad: gather-GEMM on dy64 with 81 negated taps, weights [c][(kh,kw)*64 + j]
+        g64 = ops.nchw_to_nhwc(dy, gdt, c_pad=64)
+        flat = tape["act4_flat"]
+        a_g = flat if flat.dtype == gdt else ops.cast(flat, gdt)
+        taps27 = [(-kh, -4 * m, 0) for kh in range(9) for m in range(3)]
+        db = ops.wgrad(ConvSpec(taps27, 64, None, 128, 128), g64, (B, H4, W4, 64), _nhwc_strides(g64), a_g, (Hq, Wq),
+                       use_tc=True, g_strides=(Hq * Wq * 32, Wq * 32, 32))
+        dwf = db.view(4, 32, 9, 3, 64)[..., :3].permute(4, 1, 2, 3, 0).reshape(3, 32, 9, 12)[..., :9]
+        grads["final_conv.conv.weight"] = dwf.contiguous()
+        wd = torch.zeros((32, 81, 64), dtype=torch.float32, device=dev)
+        wd[:, :, :3] = wfin.detach().float().permute(1, 2, 3, 0).reshape(32, 81, 3)
+        d_act4 = torch.empty((B, Hq, Wq, 32), dtype=gdt, device=dev)
+        ops.conv_gather(ConvSpec(_neg(taps81), 64, wd.reshape(32, 81 * 64).to(gdt), 32, 32), g64, (B, H4, W4, 64),
+                        _nhwc_strides(g64), d_act4, (Hq, Wq), None, True)
+    else:
+        g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
+        db = _wgrad(tc, ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), g16, (H4, W4))
+        grads["final_conv.conv.weight"] = unpack_conv(db, 3, 32, 9)
+        wf_plain = engine.pack_final_plain(wfin, gdt)
+        d_act4 = dgrad(g16, (B, H4, W4, 16), wf_plain, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
 
     # ---- norm4 + up2 ------------------------------------------------------------------------------------
     g4, b4 = plan._affine("norm4")

@@ -30,6 +30,9 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const __grid_constant__
   const int cw = min(64, d.kc - cc * 64);           // valid channels in this chunk
 
   const TG* G = reinterpret_cast<const TG*>(d.b);
+  const int64_t gsw = d.g_stride_w ? d.g_stride_w : d.n_gemm;
+  const int64_t gsh = d.g_stride_w ? d.g_stride_h : (int64_t)d.n_gemm * d.out_w;
+  const int64_t gsn = d.g_stride_w ? d.g_stride_n : (int64_t)d.n_gemm * d.out_w * d.out_h;
   const TA* A = reinterpret_cast<const TA*>(d.a) + (size_t)n * d.a_stride_n;
   const int lp = tid >> 4, lq = (tid & 15) * 4;     // loader: 16 pixels x 64 (4 per thread)
   const int tx = tid & 15, ty = tid >> 4;           // compute: ty -> j, tx -> c
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const __grid_constant__
     float gv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
     if (p < npix) {
       const int h = r0 + p / d.out_w, w = p % d.out_w;
-      const TG* gp = G + (((size_t)n * d.out_h + h) * d.out_w + w) * d.n_gemm + j0 + lq;
+      const TG* gp = G + (size_t)n * gsn + (size_t)h * gsh + (size_t)w * gsw + j0 + lq;
 #pragma unroll
       for (int i = 0; i < 4; ++i) if (j0 + lq + i < d.n_gemm) gv[i] = to_f32<TG>(gp[i]);
       const int ih = h + dh, iw = w + dw;

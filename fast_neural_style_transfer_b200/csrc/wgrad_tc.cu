@@ -224,7 +224,8 @@ static int run_pixel_gemm(const fnst_conv_desc* d, const void* g, int g_dtype, f
   CUtensorMap mg, ma;
   {
     const uint64_t dims[4] = {(uint64_t)d->n_gemm, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->out_n};
-    const uint64_t str[3] = {(uint64_t)d->n_gemm * 2, (uint64_t)d->n_gemm * d->out_w * 2, (uint64_t)d->n_gemm * d->out_w * d->out_h * 2};
+    uint64_t str[3] = {(uint64_t)d->n_gemm * 2, (uint64_t)d->n_gemm * d->out_w * 2, (uint64_t)d->n_gemm * d->out_w * d->out_h * 2};
+    if (d->g_stride_w) { str[0] = (uint64_t)d->g_stride_w * 2; str[1] = (uint64_t)d->g_stride_h * 2; str[2] = (uint64_t)d->g_stride_n * 2; }
     const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
     if (int r = encode_tensor_map_2b(&mg, g, 4, dims, str, box)) return r;
   }

@@ -216,8 +216,8 @@ class StyleNetPlan:
                         _nhwc_strides(act3), raw4, (H3, W3), st4, tc)
         # norm4 + relu -> reflect-4 halo buffer (+ slack so the paired view of the last pixel stays in bounds)
         Hq, Wq = H4 + 8, W4 + 8
-        flat = torch.empty(B * Hq * Wq * 32 + 64, dtype=dt, device=dev)
-        flat[-64:].zero_()
+        flat = torch.empty(B * Hq * Wq * 32 + 128, dtype=dt, device=dev)   # slack: paired / 4-pixel window views
+        flat[-128:].zero_()
         act4 = flat[:B * Hq * Wq * 32].view(B, Hq, Wq, 32)
         g, b = self._affine("norm4")
         ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT)
@@ -230,7 +230,7 @@ class StyleNetPlan:
             spec = ConvSpec(taps_kxk(9), 32, w["final"], 16, 3, epilogue=EPI_NCHW_F32, bias=self.final_bias)
             ops.conv_gather(spec, act4, (B, Hq, Wq, 32), _nhwc_strides(act4), y, (H4, W4), None, False)
         if tape is not None:
-            tape.update(raw3=raw3, st3=st3, act3=act3, raw4=raw4, st4=st4, act4=act4, x=x)
+            tape.update(raw3=raw3, st3=st3, act3=act3, raw4=raw4, st4=st4, act4=act4, act4_flat=flat, x=x)
         return y
 
 

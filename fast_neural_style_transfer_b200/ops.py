@@ -216,10 +216,15 @@ def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, c_pad: Optional[int] = Non
 
 # ---- backward operators -------------------------------------------------------------------------------
 
-def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, out_hw, use_tc: bool = False) -> torch.Tensor:
-    """dB fp32 [n_gemm, ntaps*kc] of the gather-GEMM `spec` (weights unused); g NHWC [n, oh, ow, n_gemm]."""
+def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, out_hw, use_tc: bool = False,
+          g_strides: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+    """dB fp32 [n_gemm, ntaps*kc] of the gather-GEMM `spec` (weights unused); g NHWC [n, oh, ow, n_gemm], or a
+    strided view of it given by g_strides = (n, h, w) element strides."""
     d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
-    assert g.is_contiguous() and g.shape == (a_dims[0], out_hw[0], out_hw[1], spec.n_gemm), (g.shape, spec.n_gemm)
+    if g_strides is None:
+        assert g.is_contiguous() and g.shape == (a_dims[0], out_hw[0], out_hw[1], spec.n_gemm), (g.shape, spec.n_gemm)
+    else:
+        d.g_stride_n, d.g_stride_h, d.g_stride_w = g_strides
     out = torch.empty((spec.n_gemm, len(spec.taps) * spec.kc), dtype=torch.float32, device=a.device)
     d.b, d.out = g.data_ptr(), out.data_ptr()
     dev, st = _ctx(a)

@@ -70,6 +70,8 @@ typedef struct fnst_conv_desc {
   const void* mask;              /* forward activation (ReLU output) of dtype mask_dtype, or NULL */
   int32_t mask_dtype;
   int32_t reserved;
+  /* wgrad only: element strides of the gradient operand g (all zero = contiguous NHWC [out_n,out_h,out_w,n_gemm]) */
+  int64_t g_stride_w, g_stride_h, g_stride_n;
 } fnst_conv_desc;
 
 int fnst_version(void);
