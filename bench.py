@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=os.environ.get("FNST_BENCH_WORKLOAD", "infer256"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("FNST_BENCH_WORKLOAD", "train"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
