@@ -11,7 +11,7 @@ import os
 
 MAX_TAPS = 96
 F32, F16, BF16 = 0, 1, 2
-EPI_NHWC, EPI_D2S, EPI_NCHW_F32 = 0, 1, 2
+EPI_NHWC, EPI_D2S, EPI_NCHW_F32, EPI_ROWSUM9 = 0, 1, 2, 3
 PAD_NONE, PAD_REFLECT, PAD_ZERO = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -144,7 +144,7 @@ int validate_conv_desc(const fnst_conv_desc* d) {
   FNST_CHECK_ARG(d->n_gemm > 0 && d->n_gemm % 16 == 0, "conv: n_gemm %d must be a multiple of 16", d->n_gemm);
   FNST_CHECK_ARG(d->out_n > 0 && d->out_h > 0 && d->out_w > 0, "conv: empty output");
   FNST_CHECK_ARG(d->out_n == d->a_n, "conv: batch mismatch");
-  FNST_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= 2, "conv: bad epilogue %d", d->epilogue);
+  FNST_CHECK_ARG(d->epilogue >= 0 && d->epilogue <= 3, "conv: bad epilogue %d", d->epilogue);
   if (d->epilogue == FNST_EPI_D2S) FNST_CHECK_ARG(d->n_gemm == 4 * d->c_out, "conv: d2s needs n_gemm == 4*c_out");
   else FNST_CHECK_ARG(d->c_out <= d->n_gemm, "conv: c_out > n_gemm");
   for (int t = 0; t < d->ntaps; ++t)
@@ -158,6 +158,7 @@ using namespace fnst;
 
 extern "C" int fnst_conv_simt(const fnst_conv_desc* d, int device, void* stream) {
   if (int r = validate_conv_desc(d)) return r;
+  FNST_CHECK_ARG(d->epilogue != FNST_EPI_ROWSUM9, "conv_simt: the ROWSUM9 epilogue exists on the tensor-core kernel only");
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
   if (d->stats) FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));

@@ -53,7 +53,7 @@ int encode_tensor_map_2b(CUtensorMap* map, const void* base, int rank, const uin
 
 struct ConvTcParams {
   int32_t out_n, out_h, out_w;
-  int32_t tiles_w, tiles_h, tw_log2;
+  int32_t tiles_w, tiles_h, tw_log2, h_step;     // h_step: rows between successive tiles (TH, or 8 for ROWSUM9)
   int32_t num_m_tiles, num_n_tiles, num_tiles;
   int32_t num_kblocks, chunks_per_tap;
   int32_t h0, w0;
@@ -116,6 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   __shared__ float s_sum[BLOCK_N], s_sq[BLOCK_N];
+  __shared__ float s_rows[BLOCK_N == 32 ? TC_BLOCK_M * 33 : 1];   // ROWSUM9 staging: 128 T-pixels x 27 partials
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -145,7 +146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
         const int th = m_tile % p.tiles_h;
         const int n = m_tile / p.tiles_h;
-        const int hb = th * TH + p.h0, wb = tw * TW + p.w0;
+        const int hb = th * p.h_step + p.h0, wb = tw * TW + p.w0;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           const int t = kb / p.chunks_per_tap, ch = kb - t * p.chunks_per_tap;
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -200,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int th = m_tile % p.tiles_h;
       const int n = m_tile / p.tiles_h;
       const int r = q * 32 + lane;
-      const int h = th * TH + (r >> p.tw_log2), w = tw * TW + (r & (TW - 1));
+      const int h = th * p.h_step + (r >> p.tw_log2), w = tw * TW + (r & (TW - 1));
       const bool valid = h < p.out_h && w < p.out_w;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -224,6 +225,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = i < CHUNK ? __uint_as_float(raw[i]) : 0.f;
+
+        if (BLOCK_N == 32 && p.epilogue == FNST_EPI_ROWSUM9) {
+          // stage the 27 horizontal partials of this T-pixel, then sum 9 rows per output pixel
+#pragma unroll
+          for (int i = 0; i < 27; ++i) s_rows[r * 33 + i] = v[i];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int co = p.c_out;
+          for (int idx = et; idx < 64 * co; idx += 128) {
+            const int o = idx / 64, pp = idx - o * 64;          // pp: output pixel (8 rows x 8 cols) of this tile
+            const int oh = th * 8 + (pp >> 3), ow = tw * 8 + (pp & 7);
+            if (oh < p.out_h && ow < p.out_w) {
+              float acc = p.bias ? p.bias[o] : 0.f;
+#pragma unroll
+              for (int kh = 0; kh < 9; ++kh) acc += s_rows[(pp + 8 * kh) * 33 + kh * co + o];
+              reinterpret_cast<float*>(p.out)[(((size_t)n * co + o) * p.out_h + oh) * p.out_w + ow] = acc;
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          continue;
+        }
 
         if (p.epilogue == FNST_EPI_NCHW_F32) {
           if (valid) {
@@ -355,6 +376,11 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   if (d->epilogue == FNST_EPI_D2S) FNST_CHECK_ARG(d->c_out % 32 == 0, "conv_tc: d2s needs c_out %% 32 == 0");
   if (d->epilogue == FNST_EPI_NHWC) FNST_CHECK_ARG(d->c_out == d->n_gemm && (d->n_gemm == 16 || d->n_gemm % 32 == 0), "conv_tc: NHWC epilogue needs c_out == n_gemm, a multiple of 32 (or 16)");
   if (d->epilogue == FNST_EPI_NCHW_F32) FNST_CHECK_ARG(d->c_out <= 16 && !d->stats && !d->relu, "conv_tc: NCHW epilogue supports c_out <= 16, no stats/relu");
+  const bool rowsum = d->epilogue == FNST_EPI_ROWSUM9;
+  if (rowsum) {
+    FNST_CHECK_ARG(d->n_gemm == 32 && 9 * d->c_out <= 27 && !d->stats && !d->relu, "conv_tc: ROWSUM9 needs n_gemm == 32, c_out <= 3, no stats/relu");
+    for (int t = 0; t < d->ntaps; ++t) FNST_CHECK_ARG(d->tap_dh[t] == 0, "conv_tc: ROWSUM9 taps must have dh == 0");
+  }
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
 
@@ -362,11 +388,12 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   memset(&p, 0, sizeof(p));
   p.out_n = d->out_n; p.out_h = d->out_h; p.out_w = d->out_w;
   // pixel tile TH x TW = 128: wide tiles for wide images, never wider than needed
-  const int tw_log2 = d->out_w <= 8 ? 3 : 4;
+  const int tw_log2 = (rowsum || d->out_w <= 8) ? 3 : 4;
   p.tw_log2 = tw_log2;
   const int TW = 1 << tw_log2, TH = TC_BLOCK_M >> tw_log2;
+  p.h_step = rowsum ? 8 : TH;                 // ROWSUM9: 16-row T tiles advance by 8 output rows (8-row halo below)
   p.tiles_w = (d->out_w + TW - 1) / TW;
-  p.tiles_h = (d->out_h + TH - 1) / TH;
+  p.tiles_h = (d->out_h + p.h_step - 1) / p.h_step;
   p.num_m_tiles = p.tiles_w * p.tiles_h * d->out_n;
   const int num_sms = device_sm_count(device);
 

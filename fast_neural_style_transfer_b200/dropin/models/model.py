@@ -21,7 +21,7 @@ _PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os
 if _PKG_PARENT not in sys.path:
     sys.path.append(_PKG_PARENT)
 
-from fast_neural_style_transfer_b200 import engine            # noqa: E402
+from fast_neural_style_transfer_b200 import engine, ops       # noqa: E402
 from fast_neural_style_transfer_b200 import autograd_fns      # noqa: E402
 
 
@@ -83,6 +83,7 @@ class StyleTransferNet(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_plan_cache", None)
+        state.pop("_graphs", None)
         return state
 
     def _plan(self) -> "engine.StyleNetPlan":
@@ -102,13 +103,45 @@ class StyleTransferNet(nn.Module):
         ones = torch.ones((x.shape[0], 256, 1, 1), device=x.device)
         return [F.dropout2d(ones, blk.dropout.p, True).view(x.shape[0], 256) for blk in self.res_blocks]
 
+    # Small no-grad forwards are launch-bound (59 launches): replay them as one CUDA graph per input shape.
+    GRAPH_MAX_PIXELS = 4 * 1080 * 1920
+
+    def _graph_forward(self, plan, x):
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = (id(plan), tuple(x.shape), x.device.index)
+        entry = graphs.get(key)
+        if entry is None:
+            for k in [k for k in graphs if k[0] != id(plan)]:      # weights changed: drop stale captures
+                del graphs[k]
+            static_x = x.detach().clone().float().contiguous()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    plan.forward(static_x)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count
+            with torch.cuda.graph(graph):
+                static_y = plan.forward(static_x)
+            entry = graphs[key] = (graph, static_x, static_y, ops.launch_count - n0)
+        graph, static_x, static_y, n_launches = entry
+        static_x.copy_(x)
+        graph.replay()
+        ops.launch_count += n_launches           # kernels replayed from the captured graph
+        return static_y.clone()
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
         plan = self._plan()
-        drop = self._dropout_scales(x)
         params = list(self.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             names = [n for n, _ in self.named_parameters()]
-            return autograd_fns.stylenet_apply(plan, names, x, drop, params)
-        return plan.forward(x, drop)
+            return autograd_fns.stylenet_apply(plan, names, x, self._dropout_scales(x), params)
+        use_graph = (not self.training and os.environ.get("FNST_CUDA_GRAPH", "1") != "0"
+                     and x.shape[0] * x.shape[2] * x.shape[3] <= self.GRAPH_MAX_PIXELS
+                     and not torch.cuda.is_current_stream_capturing())
+        if use_graph:
+            return self._graph_forward(plan, x)
+        return plan.forward(x, self._dropout_scales(x))

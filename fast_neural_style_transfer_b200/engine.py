@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from ._lib import EPI_NHWC, EPI_D2S, EPI_NCHW_F32, PAD_NONE, PAD_REFLECT, PAD_ZERO
+from ._lib import EPI_NHWC, EPI_D2S, EPI_NCHW_F32, EPI_ROWSUM9, PAD_NONE, PAD_REFLECT, PAD_ZERO
 from .ops import ConvSpec
 
 PRECISIONS = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
@@ -89,6 +89,25 @@ def pack_final_pairs(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return b.reshape(16, 45 * 64).to(dtype).contiguous()
 
 
+TAPS_ROWSUM = [(0, 2 * j, 0) for j in range(5)]
+
+
+def pack_final_rowsum(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """final_conv weight (3, 32, 9, 9) -> (32, 5*64) for the separable ROWSUM9 form: GEMM column kh*3 + o, K index
+    j*64 + jj*32 + c with kw = 2j + jj (pixel-pair view); the phantom tap kw = 9 and columns 27..31 are zero."""
+    o, c, k, _ = w.shape
+    assert (o, c, k) == (3, 32, 9)
+    b = torch.zeros((9, 3, 5, 2, 32), dtype=w.dtype, device=w.device)       # (kh, o, j, jj, c)
+    for j in range(5):
+        for jj in range(2):
+            kw = 2 * j + jj
+            if kw < 9:
+                b[:, :, j, jj, :] = w[:, :, :, kw].permute(2, 0, 1)
+    out = torch.zeros((32, 5 * 64), dtype=w.dtype, device=w.device)
+    out[:27] = b.reshape(27, 5 * 64)
+    return out.to(dtype).contiguous()
+
+
 def pack_final_plain(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     o = w.shape[0]
     b = torch.zeros((16, w.shape[2] * w.shape[3] * w.shape[1]), dtype=w.dtype, device=w.device)
@@ -132,7 +151,7 @@ class StyleNetPlan:
             w[f"res{i}b"] = pack_conv(p[f"res_blocks.{i}.conv2.conv.weight"], dt)
         w["up1"] = pack_conv_transpose(p["up1.upsample_conv.weight"], dt)
         w["up2"] = pack_conv_transpose(p["up2.upsample_conv.weight"], dt)
-        w["final"] = (pack_final_pairs if self.use_tc else pack_final_plain)(p["final_conv.conv.weight"], dt)
+        w["final"] = (pack_final_rowsum if self.use_tc else pack_final_plain)(p["final_conv.conv.weight"], dt)
         self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
         self.final_bias[:3] = p["final_conv.conv.bias"].float()
         self.w = w
@@ -224,7 +243,8 @@ class StyleNetPlan:
         # final_conv 9x9 -> NCHW fp32
         y = torch.empty((B, 3, H4, W4), dtype=torch.float32, device=dev)
         if tc:
-            spec = ConvSpec(taps_final_pairs(), 64, w["final"], 16, 3, epilogue=EPI_NCHW_F32, bias=self.final_bias)
+            # separable form: 5 pixel-pair taps along w, the 9 kernel rows live in the GEMM columns (ROWSUM9 epilogue)
+            spec = ConvSpec(TAPS_ROWSUM, 64, w["final"], 32, 3, epilogue=EPI_ROWSUM9, bias=self.final_bias)
             ops.conv_gather(spec, act4, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), y, (H4, W4), None, True)
         else:
             spec = ConvSpec(taps_kxk(9), 32, w["final"], 16, 3, epilogue=EPI_NCHW_F32, bias=self.final_bias)

@@ -39,7 +39,10 @@ enum { FNST_F32 = 0, FNST_F16 = 1, FNST_BF16 = 2 };
 enum {
   FNST_EPI_NHWC = 0,   /* out[n,h,w,j], j < c_out; optional bias, relu, per-(n,c) sum/sumsq      */
   FNST_EPI_D2S = 1,    /* j = (ph*2+pw)*c_out + o  ->  out[n,2h+ph,2w+pw,o]; stats indexed by o   */
-  FNST_EPI_NCHW_F32 = 2 /* out[n,j,h,w] fp32 (+bias), j < c_out                                  */
+  FNST_EPI_NCHW_F32 = 2, /* out[n,j,h,w] fp32 (+bias), j < c_out                                 */
+  FNST_EPI_ROWSUM9 = 3   /* 9-row separable form of a 9x9 conv (tensor cores only): GEMM column kh*c_out+o holds the
+                            horizontal partial T[(y,x)][kh,o] of input row y; out[n,o,h,w] = bias[o] +
+                            sum_kh T[(h+kh, w)][kh,o], fp32 NCHW.  n_gemm = 32, 9*c_out <= 32, taps have dh = 0.   */
 };
 
 enum { FNST_PAD_NONE = 0, FNST_PAD_REFLECT = 1, FNST_PAD_ZERO = 2 };

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-EPI_NHWC, EPI_D2S, EPI_NCHW_F32 = 0, 1, 2
+EPI_NHWC, EPI_D2S, EPI_NCHW_F32, EPI_ROWSUM9 = 0, 1, 2, 3
 PAD_NONE, PAD_REFLECT, PAD_ZERO = 0, 1, 2
 
 
@@ -25,6 +25,8 @@ def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc):
     view = a.as_strided((n, ah, aw, ac), (sn, sh, sw, 1), a.storage_offset()).double()
     oh, ow = out_hw
     wgt = spec.weight.double()
+    if spec.epilogue == EPI_ROWSUM9:
+        oh = oh + 8                     # the GEMM row space is the input rows (8-row halo below the output)
     acc = torch.zeros((n, oh, ow, spec.n_gemm), dtype=torch.float64)
     for t, (dh, dw, c0) in enumerate(spec.taps):
         hs = torch.arange(oh) + spec.h0 + dh
@@ -34,6 +36,13 @@ def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc):
         patch = view[:, hs.clamp(0, ah - 1)][:, :, ws.clamp(0, aw - 1)][..., c0:c0 + spec.kc] * hm * wm
         acc += patch @ wgt[:, t * spec.kc:(t + 1) * spec.kc].t()
     c = spec.c_out
+    if spec.epilogue == EPI_ROWSUM9:
+        oh -= 8
+        v = sum(acc[:, kh:kh + oh, :, kh * c:(kh + 1) * c] for kh in range(9))
+        if spec.bias is not None:
+            v = v + spec.bias.double()[:c]
+        out.copy_(v.permute(0, 3, 1, 2).to(out.dtype))
+        return
     if spec.epilogue == EPI_D2S:
         v = acc.view(n, oh, ow, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * oh, 2 * ow, c)
     else:

@@ -97,3 +97,23 @@ def test_vgg_and_losses_forward(dropin, precision, tol):
         # plain NCHW fp32 tensors (not produced by the drop-in VGG) are accepted as well
         g = ll.gram_matrix(rf[1].to(DEV))
         assert rel_l2(g, O.gram_matrix(rf[1])) < 1e-5
+
+
+def test_cuda_graph_replay_tracks_inputs_and_weights(dropin):
+    """Small no-grad forwards are replayed from a CUDA graph: new inputs and new weights must be honoured."""
+    mm, _, _ = dropin
+    p0, p1 = O.make_net_params(seed=0), O.make_net_params(seed=5, random_affine=True)
+    net = mm.StyleTransferNet().to(DEV)
+    net.load_state_dict(p0)
+    net.precision = "fp32"
+    net.eval()
+    xa, xb = O.make_image(1, 64, 64, seed=1), O.make_image(1, 64, 64, seed=2)
+    with torch.no_grad():
+        ya = net(xa.to(DEV)); yb = net(xb.to(DEV)); ya2 = net(xa.to(DEV))
+        assert len(net._graphs) == 1
+        assert rel_l2(ya, O.stylenet_forward(p0, xa)) < 1e-4 and rel_l2(yb, O.stylenet_forward(p0, xb)) < 1e-4
+        assert rel_l2(ya, ya2) < 1e-5          # (fp32 atomics in the statistics: not bitwise reproducible)
+        net.load_state_dict(p1)
+        yc = net(xa.to(DEV))
+        assert rel_l2(yc, O.stylenet_forward(p1, xa)) < 1e-4
+        assert len(net._graphs) == 1          # the stale capture was dropped

@@ -33,7 +33,7 @@ def _run_conv_pair(spec_cpu, a_cpu, a_dims, a_strides, out_shape, out_hw, with_s
     # keep any slack that follows the view in its storage (paired final-conv view reads 32 elements past the end)
     base = a_cpu._base if a_cpu._base is not None else a_cpu
     a_gpu = base.to(DEV).view(-1)[:a_cpu.numel()].view(a_cpu.shape)
-    out_gpu = torch.full(out_shape, float("nan"), dtype=torch.float32 if spec_cpu.epilogue == _lib.EPI_NCHW_F32 else out_dtype, device=DEV)
+    out_gpu = torch.full(out_shape, float("nan"), dtype=torch.float32 if spec_cpu.epilogue in (_lib.EPI_NCHW_F32, _lib.EPI_ROWSUM9) else out_dtype, device=DEV)
     st_gpu = torch.empty((n, spec_cpu.c_out, 2), device=DEV) if with_stats else None
     ops.conv_gather(spec_gpu, a_gpu, a_dims, a_strides, out_gpu, out_hw, st_gpu, use_tc)
     torch.cuda.synchronize()
@@ -52,6 +52,7 @@ CONV_CASES = {
     "convT_256_64": (1, 9, 12, 256, 64, "convT"),
     "convT_64_32": (2, 16, 16, 64, 32, "convT"),
     "final_pairs": (1, 20, 28, 32, 3, "final"),
+    "final_rowsum": (2, 21, 27, 32, 3, "final_rowsum"),
 }
 
 
@@ -81,13 +82,16 @@ def _make_case(name, dtype, tc):
         w = (rnd(cin, cout, 3, 3) / (3 * cin ** 0.5))
         spec = ConvSpec(engine.TAPS_2X2, cin, engine.pack_conv_transpose(w, dtype), 4 * cout, cout, epilogue=_lib.EPI_D2S)
         return spec, a, (B, H, W, cin), engine._nhwc_strides(a), (B, 2 * H, 2 * W, cout), (H, W), True
-    if kind == "final":
+    if kind in ("final", "final_rowsum"):
         hq, wq = H + 8, W + 8
         flat = torch.zeros(B * hq * wq * 32 + 64, dtype=dtype)
         flat[:B * hq * wq * 32] = rnd(B * hq * wq * 32).to(dtype)
         a = flat[:B * hq * wq * 32].view(B, hq, wq, 32)
         w = (rnd(3, 32, 9, 9) / (9 * 32 ** 0.5))
         bias = torch.zeros(16); bias[:3] = rnd(3)
+        if kind == "final_rowsum" and tc:
+            spec = ConvSpec(engine.TAPS_ROWSUM, 64, engine.pack_final_rowsum(w, dtype), 32, 3, epilogue=_lib.EPI_ROWSUM9, bias=bias)
+            return spec, a, (B, hq, wq, 64), (hq * wq * 32, wq * 32, 32), (B, 3, H, W), (H, W), False
         if tc:
             spec = ConvSpec(engine.taps_final_pairs(), 64, engine.pack_final_pairs(w, dtype), 16, 3, epilogue=_lib.EPI_NCHW_F32, bias=bias)
             return spec, a, (B, hq, wq, 64), (hq * wq * 32, wq * 32, 32), (B, 3, H, W), (H, W), False
