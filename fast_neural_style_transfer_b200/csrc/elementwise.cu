@@ -163,6 +163,33 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
   }
 }
 
+// NCHW fp32 3-channel image -> NHWC halo buffer [n][rows][pitch][CP] (CP = 4 or 8 channels, channel 3.. zero),
+// interior at (pad, pad), reflect or zero border, everything outside [-(pad), H+pad) x [-(pad), W+pad) zero.
+template <typename T, int CP>
+__global__ void __launch_bounds__(256) image_to_halo_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int H, int W,
+                                                            int pad, int reflect, int rows, int pitch) {
+  const int64_t total = (int64_t)N * rows * pitch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int wp = i % pitch; int64_t r = i / pitch;
+    const int hp = r % rows; const int n = r / rows;
+    int h = hp - pad, w = wp - pad;
+    bool ok = h >= -pad && h < H + pad && w >= -pad && w < W + pad;
+    if (ok && (h < 0 || h >= H || w < 0 || w >= W)) {
+      if (reflect) { h = reflect_index(h, H); w = reflect_index(w, W); } else ok = false;
+    }
+    T v[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) v[c] = from_f32<T>(0.f);
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = from_f32<T>(x[(((size_t)n * 3 + c) * H + h) * W + w]);
+    }
+    T* o = out + i * CP;
+    if (CP == 4) *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(v);
+    else *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t count8) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -260,4 +287,24 @@ extern "C" int fnst_cast(const void* in, void* out, int64_t count, int in_dtype,
     });
   });
   return launch_status("cast");
+}
+
+extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w, int pad, int pad_mode, int c_pad, int rows,
+                                  int pitch, int dtype, int device, void* stream) {
+  FNST_CHECK_ARG(x && out && n > 0 && h > 0 && w > 0, "image_to_halo: bad arguments");
+  FNST_CHECK_ARG((c_pad == 4 || c_pad == 8) && (dtype == FNST_F16 || dtype == FNST_BF16), "image_to_halo: c_pad must be 4 or 8, dtype fp16/bf16");
+  FNST_CHECK_ARG(rows >= h + 2 * pad && pitch >= w + 2 * pad, "image_to_halo: buffer smaller than the padded image");
+  if (pad_mode == FNST_PAD_REFLECT) FNST_CHECK_ARG(h > pad && w > pad, "image_to_halo: reflect pad %d needs h,w > pad", pad);
+  FNST_CUDA(cudaSetDevice(device));
+  const int grid = grid_for((int64_t)n * rows * pitch);
+  const int reflect = pad_mode == FNST_PAD_REFLECT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FNST_F16) {
+    if (c_pad == 4) image_to_halo_kernel<__half, 4><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch);
+    else image_to_halo_kernel<__half, 8><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch);
+  } else {
+    if (c_pad == 4) image_to_halo_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch);
+    else image_to_halo_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch);
+  }
+  return launch_status("image_to_halo");
 }

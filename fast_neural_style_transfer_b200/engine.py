@@ -46,6 +46,15 @@ def pack_first(w: torch.Tensor) -> torch.Tensor:
     return w.detach().float().permute(1, 2, 3, 0).reshape(-1, o).contiguous()
 
 
+def pack_first_tc(w: torch.Tensor, c_pad: int, dtype: torch.dtype) -> torch.Tensor:
+    """First-layer weight (O, 3, k, k) -> (O, k*64): K index kh*64 + kw*c_pad + c (window of 64/c_pad pixels per
+    kernel row; pixels >= k and channels >= 3 are zero)."""
+    o, c, k, _ = w.shape
+    b = torch.zeros((o, k, 64 // c_pad, c_pad), dtype=w.dtype, device=w.device)
+    b[:, :, :k, :c] = w.permute(0, 2, 3, 1)
+    return b.reshape(o, k * 64).to(dtype).contiguous()
+
+
 def taps_s2d_3x3(c_in: int) -> List[Tuple[int, int, int]]:
     """3x3 stride-2 conv on a space-to-depth halo buffer: tap (kh,kw) reads spatial offset
     (kh>>1, kw>>1) of phase (kh&1, kw&1), i.e. channel window ((kh&1)*2 + (kw&1)) * c_in."""
@@ -144,7 +153,7 @@ class StyleNetPlan:
         p = {k: v.detach() for k, v in params.items()}
         self.params = p
         dt = self.dtype
-        w = {"conv1": pack_first(p["conv1.conv.weight"]),
+        w = {"conv1": pack_first_tc(p["conv1.conv.weight"], 4, dt) if self.use_tc else pack_first(p["conv1.conv.weight"]),
              "conv2": pack_conv(p["conv2.conv.weight"], dt)}
         for i in range(5):
             w[f"res{i}a"] = pack_conv(p[f"res_blocks.{i}.conv1.conv.weight"], dt)
@@ -179,7 +188,16 @@ class StyleNetPlan:
         # conv1: 9x9 stride 2, reflect 4 -> raw1 (B,H1,W1,64)
         H1, W1 = _half_up(H), _half_up(W)
         raw1, st1 = new(B, H1, W1, 64), stats(64)
-        ops.conv_first(x, w["conv1"], None, 9, 2, 4, PAD_REFLECT, False, raw1, st1)
+        if tc:
+            # tensor-core form: 4-channel reflect-halo image; kernel row kh = tap (row pair kh>>1, row parity via the
+            # channel offset), the 9 kernel columns x 4 channels sit inside one 64-element window (16 pixels)
+            rows, pitch = 2 * (H1 + 4), (W + 8 + 1) // 2 * 2
+            img = ops.image_to_halo(x, 4, PAD_REFLECT, 4, rows, pitch, dt)
+            taps = [(kh >> 1, 0, (kh & 1) * pitch * 4) for kh in range(9)]
+            ops.conv_gather(ConvSpec(taps, 64, w["conv1"], 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64),
+                            (rows * pitch * 4, 2 * pitch * 4, 8), raw1, (H1, W1), st1, True)
+        else:
+            ops.conv_first(x, w["conv1"], None, 9, 2, 4, PAD_REFLECT, False, raw1, st1)
         # norm1 + relu -> space-to-depth halo buffer for the stride-2 conv2
         Hp, Wp = H1 + 2, W1 + 2
         Hs, Ws = _half_up(Hp), _half_up(Wp)
@@ -279,7 +297,10 @@ class VGGPlan:
         for name in VGG_LAYERS:
             wt = params[name + ".weight"].detach()
             self.b[name] = params[name + ".bias"].detach().float().contiguous()
-            self.w[name] = pack_first(wt) if name == "slice1.0" else pack_conv(wt, self.dtype)
+            if name == "slice1.0":
+                self.w[name] = pack_first_tc(wt, 8, self.dtype) if self.use_tc else pack_first(wt)
+            else:
+                self.w[name] = pack_conv(wt, self.dtype)
         return self
 
     def _conv(self, name: str, a: torch.Tensor, tape: Optional[dict]) -> torch.Tensor:
@@ -299,7 +320,14 @@ class VGGPlan:
         if H < 8 or W < 8:
             raise RuntimeError("VGG19 feature stack needs H, W >= 8 (three 2x2 max-pools)")
         h = torch.empty((B, H, W, 64), dtype=self.dtype, device=x.device)
-        ops.conv_first(x, self.w["slice1.0"], self.b["slice1.0"], 3, 1, 1, PAD_ZERO, True, h, None)
+        if self.use_tc:
+            # conv1_1 on tensor cores: 8-channel zero-halo image, 3 taps (kernel rows), 8-pixel windows
+            rows, pitch = H + 2, W + 2
+            img = ops.image_to_halo(x, 1, PAD_ZERO, 8, rows, pitch, self.dtype)
+            spec = ConvSpec([(kh, 0, 0) for kh in range(3)], 64, self.w["slice1.0"], 64, 64, bias=self.b["slice1.0"], relu=True)
+            ops.conv_gather(spec, img, (B, rows, W, 64), (rows * pitch * 8, pitch * 8, 8), h, (H, W), None, True)
+        else:
+            ops.conv_first(x, self.w["slice1.0"], self.b["slice1.0"], 3, 1, 1, PAD_ZERO, True, h, None)
         if tape is not None:
             tape["x"] = x
             tape["slice1.0"] = (x, h)

@@ -332,3 +332,17 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     check(lib.fnst_cast(_ptr(x), _ptr(out), x.numel(), dt(x.dtype), dt(dtype), dev, st), "cast")
     _count()
     return out
+
+
+def image_to_halo(x: torch.Tensor, pad: int, pad_mode: int, c_pad: int, rows: int, pitch: int, dtype: torch.dtype) -> torch.Tensor:
+    """(n,3,h,w) fp32 -> flat 2-byte halo buffer viewed as (n, rows, pitch, c_pad) plus 128 zero elements of slack
+    (window views of the last pixels read a little past the end)."""
+    n, c, h, w = x.shape
+    assert c == 3 and x.dtype == torch.float32 and x.is_contiguous()
+    numel = n * rows * pitch * c_pad
+    flat = torch.empty(numel + 128, dtype=dtype, device=x.device)
+    flat[numel:].zero_()
+    dev, st = _ctx(x)
+    check(lib.fnst_image_to_halo(_ptr(x), _ptr(flat), n, h, w, pad, pad_mode, c_pad, rows, pitch, dt(dtype), dev, st), "image_to_halo")
+    _count()
+    return flat

@@ -120,6 +120,15 @@ int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, co
                      int n, int h, int w, int c, int dtype, int relu, float eps,
                      int pad, int pad_mode, int s2d, int device, void* stream);
 
+/*
+ * NCHW fp32 3-channel image -> 2-byte NHWC halo buffer [n][rows][pitch][c_pad] (c_pad 4 or 8; channels >= 3 zero), interior at
+ * (pad, pad) with reflect / zero border, the rest of the buffer zero.  Feeds the tensor-core form of the first-layer
+ * convolutions: with 4 (8) channels per pixel a window of 16 (8) consecutive pixels is one 128-byte K row, so
+ * ConvLayer(3,64,9,stride=2) (models/model.py:28) is a 9-tap and VGG conv1_1 a 3-tap gather-GEMM (taps = kernel rows).
+ */
+int fnst_image_to_halo(const float* x, void* out, int n, int h, int w, int pad, int pad_mode, int c_pad, int rows,
+                       int pitch, int dtype, int device, void* stream);
+
 /* MaxPool2d(2,2) on NHWC (torchvision features[4], [9], [18]); h, w are input extents (floor). */
 int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream);
 

@@ -73,6 +73,16 @@ def conv_first(x, weight, bias, k, stride, pad, pad_mode, relu, out, stats):
     out.copy_(v.to(out.dtype))
 
 
+def image_to_halo(x, pad, pad_mode, c_pad, rows, pitch, dtype):
+    n, c, h, w = x.shape
+    xp = F.pad(x, (pad,) * 4, mode="reflect" if pad_mode == PAD_REFLECT else "constant")
+    buf = torch.zeros((n, rows, pitch, c_pad), dtype=torch.float32)
+    buf[:, :h + 2 * pad, :w + 2 * pad, :3] = xp.permute(0, 2, 3, 1)
+    flat = torch.zeros(buf.numel() + 128, dtype=dtype)
+    flat[:buf.numel()] = buf.reshape(-1).to(dtype)
+    return flat
+
+
 def inorm_apply(raw, stats, gamma, beta, out, relu, pad=0, pad_mode=PAD_NONE, s2d=False, drop=None, res=None,
                 res_pad=0, eps=1e-5):
     n, h, w, c = raw.shape
@@ -134,5 +144,5 @@ def nchw_to_nhwc(x, dtype):
 
 def install(monkeypatch, ops_module):
     """Substitute every operator of `ops_module` by its emulation."""
-    for name in ("conv_gather", "conv_first", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc"):
+    for name in ("conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc"):
         monkeypatch.setattr(ops_module, name, globals()[name])

@@ -42,11 +42,14 @@ def test_stylenet_plan_dropout(monkeypatch):
     assert rel_l2(y, ref) < 1e-5
 
 
-def test_vgg_plan_matches_oracle(monkeypatch):
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vgg_plan_matches_oracle(monkeypatch, precision):
     emu_ops.install(monkeypatch, ops)
     p = O.make_vgg_params(seed=1)
     x = O.make_image(2, 16, 24, seed=77, normalized=True)
-    plan = engine.VGGPlan("fp32").pack(p)
+    plan = engine.VGGPlan(precision)
+    plan.dtype = torch.float32          # tensor-core plan structure (windowed conv1_1) in fp32 arithmetic
+    plan.pack(p)
     feats = plan.forward(x)
     with torch.no_grad():
         ref = O.vgg_forward(p, x)
