@@ -93,6 +93,15 @@ def run(args, wl, net, rank, world, dev, peaks):
     B.barrier(world)
     ms_e2e = B.max_over_ranks(e0.elapsed_time(e1), world, dev)
 
+    if timer.count() == 0:
+        # the timed region replayed CUDA graphs (no per-launch events possible): time the same kernel launches in
+        # three extra eager steps
+        os.environ["FNST_CUDA_GRAPH"] = "0"
+        ops.kernel_timer = timer
+        for i in range(3):
+            step(dev_batches[i % n_host], False)
+        ops.kernel_timer = None
+        os.environ.pop("FNST_CUDA_GRAPH")
     k_ms = timer.mean_ms()
     flops = 2.0 * bsz * (h // 4) * (w // 4) * 256 * 2304
     achieved = flops / (k_ms * 1e-3) / 1e12 if k_ms else None
@@ -113,7 +122,7 @@ def run(args, wl, net, rank, world, dev, peaks):
                          "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["tf_sustained"] if achieved else None, "traffic": None,
                          "peak_source": peaks["src"] + " (sustained bf16/fp16)", "launches_timed": timer.count(), "kernel_ms": k_ms,
-                         "kernel_share_of_step": (k_ms * timer.count() / args.steps) / (ms / args.steps) if k_ms else None},
+                         "kernel_share_of_step": (k_ms * 10) / (ms / args.steps) if k_ms else None},
             "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": wl["unit"],
                     "h2d_bytes_per_step": host_batches[0].numel() * 4, "d2h_bytes_per_step": 16},
             "gpu_launches": launches, "clocks": clocks, "last_losses": losses}

@@ -164,3 +164,101 @@ class _VGG(torch.autograd.Function):
 
 def vgg_apply(plan, x: torch.Tensor) -> List[torch.Tensor]:
     return list(_VGG.apply(plan, x))
+
+
+# ---- CUDA-graph variants (training): one replay for the forward, one for the backward ----------------------------
+
+class StyleNetTrainGraph:
+    """Forward (incl. weight re-pack) and backward of StyleTransferNet captured as two CUDA graphs for one input shape."""
+
+    def __init__(self, params: "dict[str, torch.nn.Parameter]", precision: str, x: torch.Tensor, drops):
+        from . import engine, graphs
+        self.names = list(params)
+        self.params = params
+        self.numels = [params[n].numel() for n in self.names]
+        self.tape: dict = {}
+        self.plan = None
+        self.has_drop = drops is not None
+
+        def fwd(x_, *drops_):
+            self.tape.clear()
+            self.plan = engine.StyleNetPlan(precision).pack(self.params)
+            return self.plan.forward(x_, list(drops_) if self.has_drop else None, self.tape)
+
+        self.fwd = graphs.GraphedPlan(fwd, [x.float().contiguous()] + (list(drops) if self.has_drop else []))
+        self.bwd = None
+
+    def forward(self, x, drops):
+        return self.fwd(x, *(drops if self.has_drop else []))
+
+    def backward(self, dy):
+        from . import backward, graphs
+        if self.bwd is None:
+            def bwd(dy_):
+                g = backward.stylenet_backward(self.plan, self.tape, dy_)
+                return torch.cat([g[n].reshape(-1) for n in self.names])
+            self.bwd = graphs.GraphedPlan(bwd, [dy.float().contiguous()])
+        flat = self.bwd(dy).clone()
+        return [t.view_as(self.params[n]) for t, n in zip(torch.split(flat, self.numels), self.names)]
+
+
+class _StyleNetGraphed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, x, drops, *params):
+        ctx.state = state
+        return state.forward(x.detach(), drops).clone()
+
+    @staticmethod
+    def backward(ctx, dy):
+        return (None, None, None) + tuple(ctx.state.backward(dy.contiguous()))
+
+
+def stylenet_graphed_apply(state: StyleNetTrainGraph, x, drops, params):
+    return _StyleNetGraphed.apply(state, x, drops, *params)
+
+
+class VGGGraph:
+    """Graphed VGG feature stack for one input shape: forward (with or without tape) and data-gradient backward."""
+
+    def __init__(self, plan, x: torch.Tensor, with_tape: bool):
+        from . import graphs
+        self.plan = plan
+        self.tape: dict = {}
+        self.with_tape = with_tape
+
+        def fwd(x_):
+            self.tape.clear()
+            return tuple(plan.forward(x_, self.tape if with_tape else None))
+
+        self.fwd = graphs.GraphedPlan(fwd, [x.float().contiguous()])
+        self.bwd = {}
+
+    def forward(self, x):
+        return tuple(f.clone() for f in self.fwd(x))
+
+    def backward(self, dfeats):
+        from . import backward, graphs
+        pattern = tuple(g is not None for g in dfeats)
+        live = [g.contiguous() for g in dfeats if g is not None]
+        if pattern not in self.bwd:
+            def bwd(*gs):
+                it = iter(gs)
+                full = [next(it) if used else None for used in pattern]
+                return backward.vgg_backward(self.plan, self.tape, full)
+            self.bwd[pattern] = graphs.GraphedPlan(bwd, live)
+        return self.bwd[pattern](*live).clone()
+
+
+class _VGGGraphed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, x):
+        ctx.state = state
+        return state.forward(x.detach())
+
+    @staticmethod
+    def backward(ctx, *dfeats):
+        return None, ctx.state.backward(dfeats)
+
+
+def vgg_graphed_apply(state: VGGGraph, x) -> List[torch.Tensor]:
+    return list(_VGGGraphed.apply(state, x))

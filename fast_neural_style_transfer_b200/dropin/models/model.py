@@ -21,7 +21,7 @@ _PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os
 if _PKG_PARENT not in sys.path:
     sys.path.append(_PKG_PARENT)
 
-from fast_neural_style_transfer_b200 import engine, ops       # noqa: E402
+from fast_neural_style_transfer_b200 import engine, graphs, ops   # noqa: E402
 from fast_neural_style_transfer_b200 import autograd_fns      # noqa: E402
 
 
@@ -82,8 +82,8 @@ class StyleTransferNet(nn.Module):
     # plan cache (packed weights) is derived state: never pickled, rebuilt when parameters change
     def __getstate__(self):
         state = self.__dict__.copy()
-        state.pop("_plan_cache", None)
-        state.pop("_graphs", None)
+        for k in ("_plan_cache", "_graphs", "_train_graphs"):
+            state.pop(k, None)
         return state
 
     def _plan(self) -> "engine.StyleNetPlan":
@@ -134,11 +134,22 @@ class StyleTransferNet(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
-        plan = self._plan()
         params = list(self.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            drops = self._dropout_scales(x)
+            if graphs.enabled() and not torch.cuda.is_current_stream_capturing():
+                # training step as two CUDA-graph replays (forward incl. weight re-pack, backward) per input shape
+                cache = self.__dict__.setdefault("_train_graphs", {})
+                key = (self.precision, tuple(x.shape), x.device.index, self.training)
+                state = cache.get(key)
+                if state is None:
+                    if len(cache) >= 4:
+                        cache.clear()
+                    state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(self.named_parameters()), self.precision, x, drops)
+                return autograd_fns.stylenet_graphed_apply(state, x, drops, params)
             names = [n for n, _ in self.named_parameters()]
-            return autograd_fns.stylenet_apply(plan, names, x, self._dropout_scales(x), params)
+            return autograd_fns.stylenet_apply(self._plan(), names, x, drops, params)
+        plan = self._plan()
         use_graph = (not self.training and os.environ.get("FNST_CUDA_GRAPH", "1") != "0"
                      and x.shape[0] * x.shape[2] * x.shape[3] <= self.GRAPH_MAX_PIXELS
                      and not torch.cuda.is_current_stream_capturing())

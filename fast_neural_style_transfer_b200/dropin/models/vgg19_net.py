@@ -17,7 +17,7 @@ _PKG_PARENT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os
 if _PKG_PARENT not in sys.path:
     sys.path.append(_PKG_PARENT)
 
-from fast_neural_style_transfer_b200 import engine            # noqa: E402
+from fast_neural_style_transfer_b200 import engine, graphs    # noqa: E402
 from fast_neural_style_transfer_b200 import autograd_fns      # noqa: E402
 
 _SLICES = (("slice1", 0, 4), ("slice2", 4, 9), ("slice3", 9, 16), ("slice4", 16, 22), ("slice5", 22, 25))
@@ -44,6 +44,7 @@ class VGG19(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_plan_cache", None)
+        state.pop("_graphs", None)
         return state
 
     def _plan(self) -> "engine.VGGPlan":
@@ -59,7 +60,18 @@ class VGG19(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("VGG19 (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
         plan = self._plan()
-        if torch.is_grad_enabled() and x.requires_grad:
+        need_grad = torch.is_grad_enabled() and x.requires_grad
+        small = x.shape[0] * x.shape[2] * x.shape[3] <= 16 * 256 * 256
+        if graphs.enabled() and small and not torch.cuda.is_current_stream_capturing():
+            cache = self.__dict__.setdefault("_graphs", {})
+            key = (id(plan), tuple(x.shape), x.device.index, need_grad)
+            state = cache.get(key)
+            if state is None:
+                for k in [k for k in cache if k[0] != id(plan)] if len(cache) < 8 else list(cache):
+                    del cache[k]
+                state = cache[key] = autograd_fns.VGGGraph(plan, x, with_tape=need_grad)
+            feats = autograd_fns.vgg_graphed_apply(state, x) if need_grad else state.forward(x.detach())
+        elif need_grad:
             feats = autograd_fns.vgg_apply(plan, x)
         else:
             feats = plan.forward(x)
