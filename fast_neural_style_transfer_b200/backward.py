@@ -16,7 +16,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import engine, ops
-from ._lib import EPI_NHWC, EPI_NCHW_F32, PAD_NONE, PAD_REFLECT
+from ._lib import EPI_NHWC, EPI_NCHW_F32, PAD_NONE, PAD_REFLECT, PAD_ZERO
 from .engine import TAPS_2X2, _KT, _nhwc_strides, taps_kxk, taps_s2d_3x3
 from .ops import ConvSpec
 
@@ -112,23 +112,29 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     taps81 = taps_kxk(9)
     wfin = p["final_conv.conv.weight"]
     if tc:
-        # Tensor-core form: dy padded to 64 channels (one 128-byte row per pixel).
-        #  wgrad: M side = 4-pixel window view of act4 (128 = 4 x 32 channels, unshifted), N side = dy shifted by
-        #         (-kh, -4m): D[(jj,c)][(kh,m,j)] = dW[j][c][kh][4m+jj]   (27 taps instead of 81, K = pixels)
-        #  dgrad: gather-GEMM on dy64 with 81 negated taps, weights [c][(kh,kw)*64 + j]
-        g64 = ops.nchw_to_nhwc(dy, gdt, c_pad=64)
+        # Tensor-core forms on an 8-channel zero-halo copy of dy (halo 8; one pixel = 16 bytes, 8 pixels = one 128-byte row):
+        #  dgrad: window at halo position (y+8-kh, x[+8]) covers dy pixels x-kw for kw = 8..1 [and kw = 0]: 18 taps, K = 1152
+        #  wgrad: contraction over halo positions p; M side = 16-pixel dy window (128 = 16 px x 8 ch) at p, N side = act4
+        #         pixel-pair window at p + (kh-8, 0): D[(i,j)][kh*64 + jj*32 + c] = dW[j][c][kh][jj+8-i]  (9 taps)
+        rows_g, pitch_g = H4 + 16, W4 + 16
+        g8 = ops.image_to_halo(dy, 8, PAD_ZERO, 8, rows_g, pitch_g, gdt)
+        g_str = (rows_g * pitch_g * 8, pitch_g * 8, 8)
         flat = tape["act4_flat"]
         a_g = flat if flat.dtype == gdt else ops.cast(flat, gdt)
-        taps27 = [(-kh, -4 * m, 0) for kh in range(9) for m in range(3)]
-        db = ops.wgrad(ConvSpec(taps27, 64, None, 128, 128), g64, (B, H4, W4, 64), _nhwc_strides(g64), a_g, (Hq, Wq),
-                       use_tc=True, g_strides=(Hq * Wq * 32, Wq * 32, 32))
-        dwf = db.view(4, 32, 9, 3, 64)[..., :3].permute(4, 1, 2, 3, 0).reshape(3, 32, 9, 12)[..., :9]
-        grads["final_conv.conv.weight"] = dwf.contiguous()
-        wd = torch.zeros((32, 81, 64), dtype=torch.float32, device=dev)
-        wd[:, :, :3] = wfin.detach().float().permute(1, 2, 3, 0).reshape(32, 81, 3)
+        taps9 = [(kh - 8, 0, 0) for kh in range(9)]
+        db = ops.wgrad(ConvSpec(taps9, 64, None, 128, 128), a_g, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), g8,
+                       (rows_g, pitch_g), use_tc=True, g_strides=g_str)
+        d5 = db.view(16, 8, 9, 2, 32)                                         # (i, j, kh, jj, c)
+        idx = torch.arange(8, -1, -1, device=dev)                             # kw -> i = 8 - kw (jj = 0 entries)
+        grads["final_conv.conv.weight"] = d5[idx, :3, :, 0, :].permute(1, 3, 2, 0).contiguous()      # (j, c, kh, kw)
+        wd = torch.zeros((32, 9, 2, 8, 8), dtype=torch.float32, device=dev)   # (c, kh, a, i, j)
+        wperm = wfin.detach().float().permute(1, 2, 3, 0)                     # (c, kh, kw, j)
+        wd[:, :, 0, :, :3] = wperm[:, :, idx[:8], :]                          # a = 0: pixel i <-> kw = 8 - i
+        wd[:, :, 1, 0, :3] = wperm[:, :, 0, :]                                # a = 1: pixel 0 <-> kw = 0
+        taps18 = [(8 - kh, a * 8, 0) for kh in range(9) for a in (0, 1)]
         d_act4 = torch.empty((B, Hq, Wq, 32), dtype=gdt, device=dev)
-        ops.conv_gather(ConvSpec(_neg(taps81), 64, wd.reshape(32, 81 * 64).to(gdt), 32, 32), g64, (B, H4, W4, 64),
-                        _nhwc_strides(g64), d_act4, (Hq, Wq), None, True)
+        ops.conv_gather(ConvSpec(taps18, 64, wd.reshape(32, 18 * 64).to(gdt), 32, 32), g8, (B, rows_g, pitch_g, 64), g_str,
+                        d_act4, (Hq, Wq), None, True)
     else:
         g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
         db = _wgrad(tc, ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), g16, (H4, W4))
@@ -216,8 +222,19 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     gy, sums = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True)
     grads["norm1.weight"], grads["norm1.bias"] = _affine_grads(sums)
     d_raw1 = ops.inorm_bwd_apply(gy, raw1, tape["st1"], sums, g1)
-    dw1 = ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT)             # tap-major (243, 64)
-    grads["conv1.conv.weight"] = dw1.view(3, 9, 9, 64).permute(3, 0, 1, 2).contiguous()
+    if tc:
+        # same window view as the forward (engine.StyleNetPlan.forward): taps = kernel rows, 16-pixel x 4-channel windows
+        x = tape["x"]
+        H1, W1 = raw1.shape[1], raw1.shape[2]
+        rows, pitch = 2 * (H1 + 4), (x.shape[3] + 8 + 1) // 2 * 2
+        img = ops.image_to_halo(x, 4, PAD_REFLECT, 4, rows, pitch, gdt)
+        taps = [(kh >> 1, 0, (kh & 1) * pitch * 4) for kh in range(9)]
+        db = ops.wgrad(ConvSpec(taps, 64, None, 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64), (rows * pitch * 4, 2 * pitch * 4, 8),
+                       d_raw1, (H1, W1), use_tc=True)
+        grads["conv1.conv.weight"] = db.view(64, 9, 16, 4)[:, :, :9, :3].permute(0, 3, 1, 2).contiguous()
+    else:
+        dw1 = ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT)             # tap-major (243, 64)
+        grads["conv1.conv.weight"] = dw1.view(3, 9, 9, 64).permute(3, 0, 1, 2).contiguous()
     grads["conv1.conv.bias"] = zeros_like_param("conv1.conv.bias")
     return {k: v.to(p[k].dtype) for k, v in grads.items()}
 
