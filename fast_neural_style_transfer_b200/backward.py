@@ -62,21 +62,20 @@ def unpack_conv_transpose(db: torch.Tensor, cin: int, cout: int) -> torch.Tensor
     return dw
 
 
-def _affine_grads(sums: torch.Tensor):
-    s = sums.sum(dim=0)
-    return s[:, 1].contiguous(), s[:, 0].contiguous()      # d gamma, d beta
+def _affine_grads(dgb: torch.Tensor):
+    return dgb[0], dgb[1]                                   # d gamma, d beta (accumulated by inorm_bwd_reduce)
 
 
 def _tc_ok(use_tc: bool, kc: int, n_gemm: int) -> bool:
     return use_tc and kc % 64 == 0 and (n_gemm == 16 or n_gemm % 32 == 0)
 
 
-def _wgrad(tc: bool, spec: ConvSpec, a, a_dims, g, out_hw) -> torch.Tensor:
+def _wgrad(tc: bool, spec: ConvSpec, a, a_dims, g, out_hw, out=None) -> torch.Tensor:
     """Weight gradient of `spec`; tensor cores whenever the channel window is a multiple of 64."""
     use_tc = tc and spec.kc % 64 == 0
     if use_tc and a.dtype != g.dtype:
         a = ops.cast(a, g.dtype)         # kind::f16 MMAs need both operands in one 16-bit format
-    return ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc)
+    return ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, out=out)
 
 
 # -------------------------------------------------------------------------------------------------------
@@ -93,8 +92,12 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     B, _, H4, W4 = dy.shape
     grads: Dict[str, torch.Tensor] = {}
 
+    zero_names = [n for n in p if n.endswith(".bias") and ("conv" in n) and not n.startswith("final_conv")]
+    zero_flat = torch.zeros(sum(p[n].numel() for n in zero_names), dtype=torch.float32, device=dev)
+    zero_views = dict(zip(zero_names, torch.split(zero_flat, [p[n].numel() for n in zero_names])))
+
     def zeros_like_param(name):
-        return torch.zeros_like(p[name], dtype=torch.float32)
+        return zero_views[name]
 
     def dgrad(g, g_dims, fwd_packed, fwd_taps, fwd_kc, out_shape, out_hw, h0=0, w0=0):
         """Data gradient of a forward gather-GEMM with plain taps (c0 == 0)."""
@@ -144,8 +147,8 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 
     # ---- norm4 + up2 ------------------------------------------------------------------------------------
     g4, b4 = plan._affine("norm4")
-    gy, sums = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT)
-    grads["norm4.weight"], grads["norm4.bias"] = _affine_grads(sums)
+    gy, sums, dgb = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT)
+    grads["norm4.weight"], grads["norm4.bias"] = _affine_grads(dgb)
     d_raw4 = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
     act3 = tape["act3"]
     H3, W3 = act3.shape[1], act3.shape[2]
@@ -157,8 +160,8 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 
     # ---- norm3 + up1 ------------------------------------------------------------------------------------
     g3, b3 = plan._affine("norm3")
-    gy, sums = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True)
-    grads["norm3.weight"], grads["norm3.bias"] = _affine_grads(sums)
+    gy, sums, dgb = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True)
+    grads["norm3.weight"], grads["norm3.bias"] = _affine_grads(dgb)
     d_raw3 = ops.inorm_bwd_apply(gy, tape["raw3"], tape["st3"], sums, g3, out_s2d=True)     # (B,H2,W2,256)
     trunk = tape["trunk"]
     last = trunk[5]
@@ -173,38 +176,52 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     taps9 = taps_kxk(3)
     pdims = (B, H2 + 2, W2 + 2, 256)
     gsrc, extra = None, g_plain          # gradient of the block output = fold(gsrc) + extra
+    # the ten 3x3 weights are handled as one stacked tensor: one kernel packs all data-gradient operands, one kernel
+    # turns all ten weight gradients back into the OIHW parameter layout
+    res_fwd = plan.w["res_all"]                                              # (10, 256, 9*256) forward operands
+    res_dg = torch.empty((10, 256, 9 * 256), dtype=gdt, device=dev)
+    res_dg.view(10, 256, 9, 256).copy_(res_fwd.view(10, 256, 9, 256).permute(0, 3, 2, 1))
+    res_db = torch.empty((10, 256, 9 * 256), dtype=torch.float32, device=dev)
+
+    def res_dgrad(g, idx):
+        out = torch.empty(pdims, dtype=gdt, device=dev)
+        ops.conv_gather(ConvSpec(_neg(taps9), 256, res_dg[idx], 256, 256), g, (B, H2, W2, 256), _nhwc_strides(g), out,
+                        (H2 + 2, W2 + 2), None, tc)
+        return out
+
     for i in range(4, -1, -1):
         blk = tape["blocks"][i]
         pre = f"res_blocks.{i}"
         # in2 (no ReLU); the total output gradient also feeds the skip connection
         ga, ba = plan._affine(pre + ".in2")
-        g_out, sums = ops.inorm_bwd_reduce(gsrc, extra, blk["raw_b"], blk["st_b"], ga, ba, None, gdt, False,
+        g_out, sums, dgb = ops.inorm_bwd_reduce(gsrc, extra, blk["raw_b"], blk["st_b"], ga, ba, None, gdt, False,
                                            1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE)
-        grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(sums)
+        grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(dgb)
         d_raw_b = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
         mid = blk["mid"]
-        db = _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2))
-        grads[pre + ".conv2.conv.weight"] = unpack_conv(db, 256, 256, 3)
+        _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2), out=res_db[2 * i + 1])
         grads[pre + ".conv2.conv.bias"] = zeros_like_param(pre + ".conv2.conv.bias")
-        wb = plan.w[f"res{i}b"] if plan.w[f"res{i}b"].dtype == gdt else engine.pack_conv(p[pre + ".conv2.conv.weight"], gdt)
-        d_mid = dgrad(d_raw_b, (B, H2, W2, 256), wb, taps9, 256, pdims, (H2 + 2, W2 + 2))
+        d_mid = res_dgrad(d_raw_b, 2 * i + 1)
         # in1 + ReLU + Dropout2d
         ga, ba = plan._affine(pre + ".in1")
-        gy, sums = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT)
-        grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(sums)
+        gy, sums, dgb = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT)
+        grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(dgb)
         d_raw_a = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
         cur = trunk[i]
-        db = _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2))
-        grads[pre + ".conv1.conv.weight"] = unpack_conv(db, 256, 256, 3)
+        _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2), out=res_db[2 * i])
         grads[pre + ".conv1.conv.bias"] = zeros_like_param(pre + ".conv1.conv.bias")
-        wa = plan.w[f"res{i}a"] if plan.w[f"res{i}a"].dtype == gdt else engine.pack_conv(p[pre + ".conv1.conv.weight"], gdt)
-        gsrc = dgrad(d_raw_a, (B, H2, W2, 256), wa, taps9, 256, pdims, (H2 + 2, W2 + 2))
+        gsrc = res_dgrad(d_raw_a, 2 * i)
         extra = g_out
+    res_dw = torch.empty((10, 256, 256, 3, 3), dtype=torch.float32, device=dev)
+    res_dw.copy_(res_db.view(10, 256, 3, 3, 256).permute(0, 1, 4, 2, 3))
+    for i in range(5):
+        grads[f"res_blocks.{i}.conv1.conv.weight"] = res_dw[2 * i]
+        grads[f"res_blocks.{i}.conv2.conv.weight"] = res_dw[2 * i + 1]
 
     # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
     g2, b2 = plan._affine("norm2")
-    gy, sums = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT)
-    grads["norm2.weight"], grads["norm2.bias"] = _affine_grads(sums)
+    gy, sums, dgb = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT)
+    grads["norm2.weight"], grads["norm2.bias"] = _affine_grads(dgb)
     d_raw2 = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
     buf2 = tape["buf2"]
     Hs, Ws = buf2.shape[1], buf2.shape[2]
@@ -219,8 +236,8 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     # ---- norm1 + conv1 -----------------------------------------------------------------------------------------
     g1, b1 = plan._affine("norm1")
     raw1 = tape["raw1"]
-    gy, sums = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True)
-    grads["norm1.weight"], grads["norm1.bias"] = _affine_grads(sums)
+    gy, sums, dgb = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True)
+    grads["norm1.weight"], grads["norm1.bias"] = _affine_grads(dgb)
     d_raw1 = ops.inorm_bwd_apply(gy, raw1, tape["st1"], sums, g1)
     if tc:
         # same window view as the forward (engine.StyleNetPlan.forward): taps = kernel rows, 16-pixel x 4-channel windows

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(256) inorm_bwd_reduce_kernel(const TG* __restr
                                                                const TA* __restrict__ raw, const float* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                const float* __restrict__ drop, TG* __restrict__ gy,
-                                                               float* __restrict__ sums, HaloLayout L, int relu, float eps) {
+                                                               float* __restrict__ sums, float* __restrict__ dgb, HaloLayout L,
+                                                               int relu, float eps) {
   extern __shared__ float s_acc[];   // [2][C]
   const int n = blockIdx.y, h = blockIdx.x;
   const int C = L.C, CG = C >> 3, PL = 256 / CG;
@@ -246,6 +247,10 @@ __global__ void __launch_bounds__(256) inorm_bwd_reduce_kernel(const TG* __restr
   for (int i = threadIdx.x; i < C; i += 256) {
     atomicAdd(&sums[((size_t)n * C + i) * 2 + 0], s_acc[i]);
     atomicAdd(&sums[((size_t)n * C + i) * 2 + 1], s_acc[C + i]);
+    if (dgb) {                       // d gamma = sum_n sum gy*xhat ; d beta = sum_n sum gy
+      atomicAdd(&dgb[i], s_acc[C + i]);
+      atomicAdd(&dgb[C + i], s_acc[i]);
+    }
   }
 }
 
@@ -451,20 +456,21 @@ extern "C" int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const 
 
 extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
                                      const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
-                                     int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
+                                     float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
                                      int pad, int pad_mode, int s2d, int device, void* stream) {
   FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && gy && sums, "inorm_bwd_reduce: null pointer");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_reduce: unsupported channel count %d", c);
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
   FNST_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, st));
+  if (dgb) FNST_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * 2 * (size_t)c, st));
   HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d};
   dim3 grid(h, n);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
       inorm_bwd_reduce_kernel<TA, TG><<<grid, 256, sizeof(float) * 2 * c, st>>>(
           reinterpret_cast<const TG*>(gsrc), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(raw), stats, gamma,
-          beta, drop, reinterpret_cast<TG*>(gy), sums, L, relu, eps);
+          beta, drop, reinterpret_cast<TG*>(gy), sums, dgb, L, relu, eps);
     });
   });
   return launch_status("inorm_bwd_reduce");

@@ -155,9 +155,14 @@ class StyleNetPlan:
         dt = self.dtype
         w = {"conv1": pack_first_tc(p["conv1.conv.weight"], 4, dt) if self.use_tc else pack_first(p["conv1.conv.weight"]),
              "conv2": pack_conv(p["conv2.conv.weight"], dt)}
+        # the ten 3x3 256->256 weights are packed by two kernels (stack, permute+cast) into one (10, 256, 2304) tensor
+        names = [f"res_blocks.{i}.{c}.conv.weight" for i in range(5) for c in ("conv1", "conv2")]
+        stacked = torch.stack([p[n] for n in names])                              # (10, O, C, 3, 3)
+        res_all = torch.empty((10, 256, 9 * 256), dtype=dt, device=stacked.device)
+        res_all.view(10, 256, 3, 3, 256).copy_(stacked.permute(0, 1, 3, 4, 2))
+        w["res_all"] = res_all
         for i in range(5):
-            w[f"res{i}a"] = pack_conv(p[f"res_blocks.{i}.conv1.conv.weight"], dt)
-            w[f"res{i}b"] = pack_conv(p[f"res_blocks.{i}.conv2.conv.weight"], dt)
+            w[f"res{i}a"], w[f"res{i}b"] = res_all[2 * i], res_all[2 * i + 1]
         w["up1"] = pack_conv_transpose(p["up1.upsample_conv.weight"], dt)
         w["up2"] = pack_conv_transpose(p["up2.upsample_conv.weight"], dt)
         w["final"] = (pack_final_rowsum if self.use_tc else pack_final_plain)(p["final_conv.conv.weight"], dt)

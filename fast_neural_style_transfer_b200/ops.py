@@ -217,7 +217,7 @@ def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, c_pad: Optional[int] = Non
 # ---- backward operators -------------------------------------------------------------------------------
 
 def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, out_hw, use_tc: bool = False,
-          g_strides: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+          g_strides: Optional[Tuple[int, int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dB fp32 [n_gemm, ntaps*kc] of the gather-GEMM `spec` (weights unused); g NHWC [n, oh, ow, n_gemm], or a
     strided view of it given by g_strides = (n, h, w) element strides."""
     d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
@@ -225,7 +225,9 @@ def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, o
         assert g.is_contiguous() and g.shape == (a_dims[0], out_hw[0], out_hw[1], spec.n_gemm), (g.shape, spec.n_gemm)
     else:
         d.g_stride_n, d.g_stride_h, d.g_stride_w = g_strides
-    out = torch.empty((spec.n_gemm, len(spec.taps) * spec.kc), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((spec.n_gemm, len(spec.taps) * spec.kc), dtype=torch.float32, device=a.device)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == spec.n_gemm * len(spec.taps) * spec.kc
     d.b, d.out = g.data_ptr(), out.data_ptr()
     dev, st = _ctx(a)
     fn = lib.fnst_wgrad_tc if use_tc else lib.fnst_wgrad_simt
@@ -254,14 +256,15 @@ def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, p
     n, h, w, c = raw.shape
     gy = torch.empty((n, h, w, c), dtype=gdtype, device=raw.device)
     sums = torch.empty((n, c, 2), dtype=torch.float32, device=raw.device)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device)          # rows: d gamma, d beta
     for t in (gsrc, extra):
         assert t is None or (t.dtype == gdtype and t.is_contiguous())
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_bwd_reduce(_ptr(gsrc), _ptr(extra), _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(gy),
-                                    _ptr(sums), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
+                                    _ptr(sums), _ptr(dgb), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
                                     dev, st), "inorm_bwd_reduce")
-    _count(2)
-    return gy, sums
+    _count(3)
+    return gy, sums, dgb
 
 
 def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-5):

@@ -176,11 +176,12 @@ int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const void* g, in
  *   gy = ( fold(gsrc) + extra ) * drop * [relu ? (y > 0) : 1],    y = raw*a + b  (a, b from stats/gamma/beta)
  * where gsrc is the gradient of the consumer's halo buffer (layout pad / pad_mode / s2d exactly as written by
  * fnst_inorm_apply; fold = ReflectionPad2d backward) and extra an optional plain [n,h,w,c] gradient (residual
- * branch).  Writes gy [n,h,w,c] (g_dtype) and accumulates sums[n][c] = (sum gy, sum gy*xhat) (zeroed by the call).
+ * branch).  Writes gy [n,h,w,c] (g_dtype) and accumulates sums[n][c] = (sum gy, sum gy*xhat) (zeroed by the call);
+ * dgb (optional, fp32 [2][c], zeroed by the call) receives d gamma = sum_n sum gy*xhat and d beta = sum_n sum gy.
  */
 int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
                           const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
-                          int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
+                          float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
                           int pad, int pad_mode, int s2d, int device, void* stream);
 /* Pass 2: draw = gamma*rstd*(gy - mean(gy) - xhat*mean(gy*xhat)), written NHWC [n,h,w,c] or, if out_s2d,
  * space-to-depth [n,h/2,w/2,4c] (channel = ((h&1)*2+(w&1))*c + ch; h, w even). */
