@@ -14,6 +14,7 @@
 //   warps 2..5  epilogue: tcgen05.ld -> red.global.add.v4.f32 into the (zeroed) fp32 result; split-K
 //           partial tiles of different CTAs meet in L2 atomics.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace fnst {
 
@@ -204,7 +205,8 @@ static int run_pixel_gemm(const fnst_conv_desc* d, const void* g, int g_dtype, f
   p.per_image = per_image;
   const int base_tasks = p.ntaps * p.cblocks * p.jblocks * (per_image ? d->out_n : 1);
   const int kb_avail = per_image ? p.kblocks_per_image : p.kblocks_total;
-  int splits = (2 * sms + base_tasks - 1) / base_tasks;          // aim for ~2 tasks per SM
+  static const int waves_x2 = [] { const char* e = getenv("FNST_WGRAD_WAVES_X2"); return e ? atoi(e) : 4; }();
+  int splits = (waves_x2 * sms / 2 + base_tasks - 1) / base_tasks;   // aim for ~waves_x2/2 tasks per SM
   if (splits > kb_avail / 4) splits = kb_avail / 4;               // keep >= 4 k-blocks per task
   if (splits < 1) splits = 1;
   p.splits = splits;
