@@ -93,6 +93,30 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Raw (unconverted) 8-element vectors: keep loads in flight in few registers, convert at the point of use.
+template <typename T> struct Raw8 { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+template <typename T> __device__ __forceinline__ Raw8<T> load_raw8(const T* p) {
+  Raw8<T> r; r.u = *reinterpret_cast<const uint4*>(p); return r;
+}
+template <> __device__ __forceinline__ Raw8<float> load_raw8<float>(const float* p) {
+  Raw8<float> r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+}
+template <typename T> __device__ __forceinline__ void raw8_to_f32(const Raw8<T>& r, float (&v)[8]);
+template <> __device__ __forceinline__ void raw8_to_f32<float>(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+template <> __device__ __forceinline__ void raw8_to_f32<__half>(const Raw8<__half>& r, float (&v)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void raw8_to_f32<__nv_bfloat16>(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
 // Runtime-typed scalar / 8-vector loads (epilogue extras whose dtype differs from the kernel's template types).
 __device__ __forceinline__ float load_scalar_f32(const void* base, int dtype, size_t idx) {
   if (dtype == FNST_F32) return reinterpret_cast<const float*>(base)[idx];
