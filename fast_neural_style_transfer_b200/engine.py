@@ -79,25 +79,6 @@ def pack_conv_transpose(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return b.reshape(4 * cout, 4 * cin).to(dtype).contiguous()
 
 
-def taps_final_pairs() -> List[Tuple[int, int, int]]:
-    return [(kh, 2 * j, 0) for kh in range(9) for j in range(5)]
-
-
-def pack_final_pairs(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """final_conv weight (3, 32, 9, 9) -> (16, 45*64): the activation view pairs two adjacent
-    pixels (64 = 2 x 32 channels) per tap so that every K block is a full 128-byte row; the
-    phantom tap kw = 9 and output rows 3..15 are zero."""
-    o, c, k, _ = w.shape
-    assert (c, k) == (32, 9) and o <= 16
-    b = torch.zeros((16, 9, 5, 2, 32), dtype=w.dtype, device=w.device)
-    for j in range(5):
-        for jj in range(2):
-            kw = 2 * j + jj
-            if kw < 9:
-                b[:o, :, j, jj, :] = w[:, :, :, kw].permute(0, 2, 1)
-    return b.reshape(16, 45 * 64).to(dtype).contiguous()
-
-
 TAPS_ROWSUM = [(0, 2 * j, 0) for j in range(5)]
 
 

@@ -40,6 +40,28 @@ def _run_conv_pair(spec_cpu, a_cpu, a_dims, a_strides, out_shape, out_hw, with_s
     return out_gpu, out_cpu, st_gpu, st_cpu
 
 
+# Paired-pixel view of a 9x9 / 32-channel conv with the plain NCHW-fp32 epilogue (the form final_conv used before the
+# separable ROWSUM9 epilogue; kept as a test of overlapping-stride activation views + the NCHW epilogue).
+def taps_final_pairs():
+    return [(kh, 2 * j, 0) for kh in range(9) for j in range(5)]
+
+
+def pack_final_pairs(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """final_conv weight (3, 32, 9, 9) -> (16, 45*64): the activation view pairs two adjacent
+    pixels (64 = 2 x 32 channels) per tap so that every K block is a full 128-byte row; the
+    phantom tap kw = 9 and output rows 3..15 are zero."""
+    o, c, k, _ = w.shape
+    assert (c, k) == (32, 9) and o <= 16
+    b = torch.zeros((16, 9, 5, 2, 32), dtype=w.dtype, device=w.device)
+    for j in range(5):
+        for jj in range(2):
+            kw = 2 * j + jj
+            if kw < 9:
+                b[:o, :, j, jj, :] = w[:, :, :, kw].permute(0, 2, 1)
+    return b.reshape(16, 45 * 64).to(dtype).contiguous()
+
+
+
 CONV_CASES = {
     # name: (B, H, W, Cin, Cout, kind)
     "res3x3_small": (2, 16, 16, 256, 256, "reflect3"),
@@ -93,7 +115,7 @@ def _make_case(name, dtype, tc):
             spec = ConvSpec(engine.TAPS_ROWSUM, 64, engine.pack_final_rowsum(w, dtype), 32, 3, epilogue=_lib.EPI_ROWSUM9, bias=bias)
             return spec, a, (B, hq, wq, 64), (hq * wq * 32, wq * 32, 32), (B, 3, H, W), (H, W), False
         if tc:
-            spec = ConvSpec(engine.taps_final_pairs(), 64, engine.pack_final_pairs(w, dtype), 16, 3, epilogue=_lib.EPI_NCHW_F32, bias=bias)
+            spec = ConvSpec(taps_final_pairs(), 64, pack_final_pairs(w, dtype), 16, 3, epilogue=_lib.EPI_NCHW_F32, bias=bias)
             return spec, a, (B, hq, wq, 64), (hq * wq * 32, wq * 32, 32), (B, 3, H, W), (H, W), False
         spec = ConvSpec(engine.taps_kxk(9), 32, engine.pack_final_plain(w, dtype), 16, 3, epilogue=_lib.EPI_NCHW_F32, bias=bias)
         return spec, a, (B, hq, wq, 32), engine._nhwc_strides(a), (B, 3, H, W), (H, W), False
