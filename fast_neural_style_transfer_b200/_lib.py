@@ -43,7 +43,7 @@ class ConvDesc(C.Structure):
         ("addend", C.c_void_p),
         ("mask", C.c_void_p),
         ("mask_dtype", C.c_int32),
-        ("reserved", C.c_int32),
+        ("b_image_rows", C.c_int32),
         ("g_stride_w", C.c_int64), ("g_stride_h", C.c_int64), ("g_stride_n", C.c_int64),
     ]
 

@@ -330,14 +330,13 @@ def vgg_backward(plan: "engine.VGGPlan", tape: dict, dfeats: Sequence[Optional[t
 # -------------------------------------------------------------------------------------------------------
 
 def gram_backward(f: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
-    """f NHWC (B,H,W,C); dg (B,C,C) fp32.  dF[p,i] = sum_j F[p,j] * (dG + dG^T)[i,j]: one 1x1 gather-GEMM per image."""
+    """f NHWC (B,H,W,C); dg (B,C,C) fp32.  dF[p,i] = sum_j F[p,j] * (dG + dG^T)[i,j]: a 1x1 gather-GEMM with per-image weights."""
     B, H, W, C = f.shape
     s = (dg + dg.transpose(1, 2)).to(f.dtype).contiguous()
     out = torch.empty_like(f)
     use_tc = f.dtype != torch.float32 and C % 64 == 0
-    for n in range(B):
-        spec = ConvSpec([(0, 0, 0)], C, s[n], C, C)
-        ops.conv_gather(spec, f[n:n + 1], (1, H, W, C), _nhwc_strides(f[n:n + 1]), out[n:n + 1], (H, W), None, use_tc)
+    spec = ConvSpec([(0, 0, 0)], C, s, C, C, per_image_weights=True)      # one launch, image n multiplies by s[n]
+    ops.conv_gather(spec, f, (B, H, W, C), _nhwc_strides(f), out, (H, W), None, use_tc)
     return out
 
 

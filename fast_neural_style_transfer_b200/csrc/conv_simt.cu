@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
     const bool in_ok = lvalid && ih >= 0 && ih < d.a_h && iw >= 0 && iw < d.a_w;
     const T* ap = A + (size_t)n * d.a_stride_n + (size_t)(in_ok ? ih : 0) * d.a_stride_h +
                   (size_t)(in_ok ? iw : 0) * d.a_stride_w + s_c0[t] + kq;
-    const T* bp = B + (size_t)(cvalid ? lcol : 0) * ktot + (size_t)t * d.kc + kq;
+    const T* bp = B + ((size_t)n * d.b_image_rows + (size_t)(cvalid ? lcol : 0)) * ktot + (size_t)t * d.kc + kq;
     for (int c = 0; c < d.kc; c += SB_K) {
       float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
       if (in_ok) {

@@ -16,6 +16,7 @@
 //               atomic per column per tile), vector stores as NHWC / depth-to-space / NCHW fp32.
 #include "tc_common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace fnst {
@@ -57,7 +58,7 @@ struct ConvTcParams {
   int32_t num_m_tiles, num_n_tiles, num_tiles;
   int32_t num_kblocks, chunks_per_tap;
   int32_t h0, w0;
-  int32_t epilogue, c_out, n_gemm, relu, out_is_bf16, out_is_f32;
+  int32_t epilogue, c_out, n_gemm, relu, out_is_bf16, out_is_f32, b_image_rows;
   uint32_t idesc;
   int32_t out_dtype, mask_dtype;
   void* out;
@@ -154,7 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sb = sa + TC_A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, wb + p.tap_dw[t], hb + p.tap_dh[t], n);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, n_tile * BLOCK_N);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, n * p.b_image_rows + n_tile * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -397,14 +398,20 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   p.num_m_tiles = p.tiles_w * p.tiles_h * d->out_n;
   const int num_sms = device_sm_count(device);
 
-  // column tile: largest that keeps the grid reasonably full
+  // column tile: the widest one that still puts a tile on at least ~60 % of the SMs (measured at batch 1..16 of the
+  // 3x3 256->256 conv: N=256 beats N=128 as soon as it yields >= ~90 tiles; N=64 is shared-memory-bandwidth bound)
   int block_n;
+  const int64_t fill = (int64_t)num_sms * 6 / 10;
   if (d->n_gemm <= 16) block_n = 16;
   else if (d->n_gemm <= 32) block_n = 32;
   else if (d->n_gemm <= 64 || d->n_gemm % 128 != 0) block_n = 64;
-  else if (d->n_gemm % 256 == 0 && (int64_t)p.num_m_tiles * (d->n_gemm / 256) >= num_sms) block_n = 256;
-  else if ((int64_t)p.num_m_tiles * (d->n_gemm / 128) >= num_sms) block_n = 128;
+  else if (d->n_gemm % 256 == 0 && (int64_t)p.num_m_tiles * (d->n_gemm / 256) >= fill) block_n = 256;
+  else if ((int64_t)p.num_m_tiles * (d->n_gemm / 128) >= fill) block_n = 128;
   else block_n = 64;
+  {
+    static const int force_n = [] { const char* e = getenv("FNST_CONV_BLOCK_N"); return e ? atoi(e) : 0; }();
+    if (force_n && d->n_gemm % force_n == 0 && d->n_gemm >= 64) block_n = force_n;     // tuning override
+  }
   FNST_CHECK_ARG(d->n_gemm % block_n == 0 || d->n_gemm < block_n, "conv_tc: n_gemm %d not tileable", d->n_gemm);
   p.num_n_tiles = (d->n_gemm + block_n - 1) / block_n;
   p.num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -415,7 +422,7 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   p.out_is_bf16 = d->out_dtype == FNST_BF16; p.out_is_f32 = d->out_dtype == FNST_F32;
   p.idesc = umma_idesc_f16(d->dtype == FNST_BF16 ? 1 : 0, block_n, 0, 0);
   p.out = d->out; p.bias = d->bias; p.stats = d->stats;
-  p.out_dtype = d->out_dtype; p.mask_dtype = d->mask_dtype;
+  p.out_dtype = d->out_dtype; p.mask_dtype = d->mask_dtype; p.b_image_rows = d->b_image_rows;
   p.addend = d->epilogue == FNST_EPI_NHWC ? d->addend : nullptr;
   p.mask = d->epilogue == FNST_EPI_NHWC ? d->mask : nullptr;
   memcpy(p.tap_dh, d->tap_dh, sizeof(p.tap_dh));
@@ -431,7 +438,7 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   }
   {
     const uint64_t ktot = (uint64_t)d->ntaps * d->kc;
-    const uint64_t dims[2] = {ktot, (uint64_t)d->n_gemm};
+    const uint64_t dims[2] = {ktot, (uint64_t)(d->b_image_rows ? (int64_t)d->b_image_rows * d->out_n : d->n_gemm)};
     const uint64_t str[1] = {ktot * 2};
     const uint32_t box[2] = {TC_BLOCK_K, (uint32_t)block_n};
     if (int r = encode_tensor_map_2b(&mb, d->b, 2, dims, str, box)) return r;

@@ -90,6 +90,7 @@ class ConvSpec:
     tag: str = ""
     addend: Optional[torch.Tensor] = None      # dgrad epilogue: out = (acc + addend) * (mask > 0)
     mask: Optional[torch.Tensor] = None
+    per_image_weights: bool = False            # weight is (n, n_gemm, K): image i uses weight[i]
 
 
 def _fill_desc(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, out_hw) -> ConvDesc:
@@ -113,7 +114,11 @@ def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, in
                 out: torch.Tensor, out_hw: Tuple[int, int], stats: Optional[torch.Tensor], use_tc: bool) -> None:
     """a_dims = (n, h, w, c) logical extents of the activation view; a_strides = (n, h, w) element strides."""
     d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
-    assert spec.weight.is_contiguous() and spec.weight.shape == (spec.n_gemm, len(spec.taps) * spec.kc), spec.weight.shape
+    wshape = (spec.n_gemm, len(spec.taps) * spec.kc)
+    if spec.per_image_weights:
+        wshape = (a_dims[0],) + wshape
+        d.b_image_rows = spec.n_gemm
+    assert spec.weight.is_contiguous() and tuple(spec.weight.shape) == wshape, (spec.weight.shape, wshape)
     assert spec.weight.dtype == a.dtype
     d.b = spec.weight.data_ptr()
     d.out_dtype = dt(out.dtype)

@@ -72,7 +72,7 @@ typedef struct fnst_conv_desc {
   const void* addend;            /* same shape/dtype as out, or NULL                              */
   const void* mask;              /* forward activation (ReLU output) of dtype mask_dtype, or NULL */
   int32_t mask_dtype;
-  int32_t reserved;
+  int32_t b_image_rows;          /* 0: one weight matrix for all images; else image n uses rows [n*b_image_rows, +n_gemm) of b */
   /* wgrad only: element strides of the gradient operand g (all zero = contiguous NHWC [out_n,out_h,out_w,n_gemm]) */
   int64_t g_stride_w, g_stride_h, g_stride_n;
 } fnst_conv_desc;

@@ -34,7 +34,10 @@ def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc):
         hm = ((hs >= 0) & (hs < ah)).double().view(1, -1, 1, 1)
         wm = ((ws >= 0) & (ws < aw)).double().view(1, 1, -1, 1)
         patch = view[:, hs.clamp(0, ah - 1)][:, :, ws.clamp(0, aw - 1)][..., c0:c0 + spec.kc] * hm * wm
-        acc += patch @ wgt[:, t * spec.kc:(t + 1) * spec.kc].t()
+        if getattr(spec, "per_image_weights", False):
+            acc += torch.einsum("nhwc,njc->nhwj", patch, wgt[:, :, t * spec.kc:(t + 1) * spec.kc])
+        else:
+            acc += patch @ wgt[:, t * spec.kc:(t + 1) * spec.kc].t()
     c = spec.c_out
     if spec.epilogue == EPI_ROWSUM9:
         oh -= 8

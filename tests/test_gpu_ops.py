@@ -29,7 +29,8 @@ def _run_conv_pair(spec_cpu, a_cpu, a_dims, a_strides, out_shape, out_hw, with_s
     st_cpu = torch.zeros((n, spec_cpu.c_out, 2)) if with_stats else None
     emu_ops.conv_gather(spec_cpu, a_cpu, a_dims, a_strides, out_cpu, out_hw, st_cpu, False)
     spec_gpu = ConvSpec(spec_cpu.taps, spec_cpu.kc, spec_cpu.weight.to(DEV), spec_cpu.n_gemm, spec_cpu.c_out, spec_cpu.h0,
-                        spec_cpu.w0, spec_cpu.epilogue, None if spec_cpu.bias is None else spec_cpu.bias.to(DEV), spec_cpu.relu)
+                        spec_cpu.w0, spec_cpu.epilogue, None if spec_cpu.bias is None else spec_cpu.bias.to(DEV), spec_cpu.relu,
+                        per_image_weights=spec_cpu.per_image_weights)
     # keep any slack that follows the view in its storage (paired final-conv view reads 32 elements past the end)
     base = a_cpu._base if a_cpu._base is not None else a_cpu
     a_gpu = base.to(DEV).view(-1)[:a_cpu.numel()].view(a_cpu.shape)
@@ -228,3 +229,15 @@ def test_error_reporting():
         _run_conv_pair(spec, a, dims, strides, oshape, ohw, True, use_tc=True)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         ops.maxpool2(torch.zeros(1, 4, 4, 8))
+
+
+@pytest.mark.parametrize("dtype,use_tc", [(torch.float32, False), (torch.bfloat16, True), (torch.float16, False)])
+def test_conv_per_image_weights(dtype, use_tc):
+    """b_image_rows: image n multiplies by its own weight matrix (Gram backward: dF[n] = F[n] (dG[n] + dG[n]^T))."""
+    g = torch.Generator().manual_seed(31)
+    B, H, W, C = 3, 10, 12, 128
+    a = torch.randn((B, H, W, C), generator=g).to(dtype)
+    wts = (torch.randn((B, C, C), generator=g) / C ** 0.5).to(dtype)
+    spec = ConvSpec([(0, 0, 0)], C, wts, C, C, per_image_weights=True)
+    got, ref, _, _ = _run_conv_pair(spec, a, (B, H, W, C), engine._nhwc_strides(a), (B, H, W, C), (H, W), False, use_tc)
+    assert rel_l2(got, ref) < {torch.float32: 2e-6, torch.float16: 1e-3, torch.bfloat16: 6e-3}[dtype]
