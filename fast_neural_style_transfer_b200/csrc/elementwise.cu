@@ -10,8 +10,11 @@ namespace fnst {
 // InstanceNorm apply.  One block per (padded output row, image).  256 threads = CG channel
 // groups of 8 channels x PL pixel lanes; per-channel scale/shift are computed once per thread.
 // -------------------------------------------------------------------------------------------
-template <typename T, int U>
-__global__ void __launch_bounds__(256) inorm_apply_kernel(const T* __restrict__ raw, const float* __restrict__ stats,
+// TI: element type of the raw conv output; T: element type of the activation written (and of the residual).
+// SPLIT: the activation is an error-compensated pair, stored as 2C channels per pixel [hi(C) | lo(C)] with
+// hi = T(y), lo = T(y - hi) (fp16x3 path); the residual buffer then has the same split layout.
+template <typename TI, typename T, int U, bool SPLIT>
+__global__ void __launch_bounds__(256) inorm_apply_kernel(const TI* __restrict__ raw, const float* __restrict__ stats,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ drop, const T* __restrict__ res, int res_pad,
                                                           T* __restrict__ out, int H, int W, int C, int relu, float eps,
@@ -35,6 +38,7 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const T* __restrict__ 
   const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
   if (pl >= PL) return;
   const int c0 = cg * 8;
+  const int CO = SPLIT ? 2 * C : C;        // channels per pixel of the activation buffers
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int Hp2 = (Hp + 1) >> 1, Wp2 = (Wp + 1) >> 1;
 
@@ -46,10 +50,11 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const T* __restrict__ 
     if (sh < 0 || sh >= H) {
       if (pad_mode == FNST_PAD_REFLECT) sh = reflect_index(sh, H); else row_zero = true;
     }
-    const T* raw_row = raw + ((size_t)n * H + sh) * W * C + c0;
-    const T* res_row = res ? res + (((size_t)n * (H + 2 * res_pad) + sh + res_pad) * (W + 2 * res_pad) + res_pad) * C + c0 : nullptr;
+    const TI* raw_row = raw + ((size_t)n * H + sh) * W * C + c0;
+    const T* res_row = res ? res + (((size_t)n * (H + 2 * res_pad) + sh + res_pad) * (W + 2 * res_pad) + res_pad) * CO + c0 : nullptr;
     for (int wp0 = pl; wp0 < Wp; wp0 += U * PL) {
-      Raw8<T> rv[U], sv[U];
+      Raw8<TI> rv[U];
+      Raw8<T> sv[U], sl[U];
       bool live[U], zero[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {          // U pixels in flight: issue all loads of the group first (raw registers)
@@ -61,8 +66,11 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const T* __restrict__ 
           if (pad_mode == FNST_PAD_REFLECT) sw = reflect_index(sw, W); else zero[u] = true;
         }
         if (live[u] && !zero[u]) {
-          rv[u] = load_raw8<T>(raw_row + (size_t)sw * C);
-          if (res) sv[u] = load_raw8<T>(res_row + (size_t)sw * C);
+          rv[u] = load_raw8<TI>(raw_row + (size_t)sw * C);
+          if (res) {
+            sv[u] = load_raw8<T>(res_row + (size_t)sw * CO);
+            if (SPLIT) sl[u] = load_raw8<T>(res_row + (size_t)sw * CO + C);
+          }
         }
       }
 #pragma unroll
@@ -70,12 +78,11 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const T* __restrict__ 
         if (!live[u]) continue;
         const int wp = wp0 + u * PL;
         float vv[8];
-        float (&vref)[8] = vv;
         if (zero[u]) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) vv[i] = 0.f;
         } else {
-          raw8_to_f32<T>(rv[u], vv);
+          raw8_to_f32<TI>(rv[u], vv);
           const float4 a0 = *reinterpret_cast<const float4*>(s_ab + c0), a1 = *reinterpret_cast<const float4*>(s_ab + c0 + 4);
           const float4 b0 = *reinterpret_cast<const float4*>(s_ab + C + c0), b1 = *reinterpret_cast<const float4*>(s_ab + C + c0 + 4);
           const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -90,12 +97,25 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const T* __restrict__ 
             raw8_to_f32<T>(sv[u], r);
 #pragma unroll
             for (int i = 0; i < 8; ++i) vv[i] += r[i];
+            if (SPLIT) {
+              raw8_to_f32<T>(sl[u], r);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vv[i] += r[i];
+            }
           }
         }
         T* dst;
-        if (!s2d) dst = out + (((size_t)n * Hp + hp) * Wp + wp) * C + c0;
-        else dst = out + (((size_t)n * Hp2 + (hp >> 1)) * Wp2 + (wp >> 1)) * (4 * C) + ((hp & 1) * 2 + (wp & 1)) * C + c0;
-        store8<T>(dst, vref);
+        if (!s2d) dst = out + (((size_t)n * Hp + hp) * Wp + wp) * CO + c0;
+        else dst = out + (((size_t)n * Hp2 + (hp >> 1)) * Wp2 + (wp >> 1)) * (4 * CO) + ((hp & 1) * 2 + (wp & 1)) * CO + c0;
+        if (SPLIT) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { hi[i] = to_f32<T>(from_f32<T>(vv[i])); lo[i] = vv[i] - hi[i]; }
+          store8<T>(dst, hi);
+          store8<T>(dst + C, lo);
+        } else {
+          store8<T>(dst, vv);
+        }
       }
     }
   }
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
 // interior at (pad, pad), reflect or zero border, everything outside [-(pad), H+pad) x [-(pad), W+pad) zero.
 template <typename T, int CP>
 __global__ void __launch_bounds__(256) image_to_halo_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int H, int W,
-                                                            int pad, int reflect, int rows, int pitch) {
+                                                            int pad, int reflect, int rows, int pitch, int split) {
   const int64_t total = (int64_t)N * rows * pitch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int wp = i % pitch; int64_t r = i / pitch;
@@ -208,7 +228,11 @@ __global__ void __launch_bounds__(256) image_to_halo_kernel(const float* __restr
     for (int c = 0; c < CP; ++c) v[c] = from_f32<T>(0.f);
     if (ok) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = from_f32<T>(x[(((size_t)n * 3 + c) * H + h) * W + w]);
+      for (int c = 0; c < 3; ++c) {
+        const float f = x[(((size_t)n * 3 + c) * H + h) * W + w];
+        v[c] = from_f32<T>(f);
+        if (CP == 8 && split) v[4 + c] = from_f32<T>(f - to_f32<T>(v[c]));      // channels 4..6: low part (hi|lo pair)
+      }
     }
     T* o = out + i * CP;
     if (CP == 4) *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(v);
@@ -238,7 +262,10 @@ using namespace fnst;
 extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, const float* beta,
                                 const float* drop, const void* res, int res_pad, void* out,
                                 int n, int h, int w, int c, int dtype, int relu, float eps,
-                                int pad, int pad_mode, int s2d, int device, void* stream) {
+                                int pad, int pad_mode, int s2d, int raw_dtype, int split, int device, void* stream) {
+  FNST_CHECK_ARG(raw_dtype == dtype || (raw_dtype == FNST_F32 && dtype == FNST_F16 && split),
+                 "inorm_apply: raw/activation dtypes must match, except the fp32 -> split fp16 (hi|lo) form");
+  FNST_CHECK_ARG(!split || (raw_dtype == FNST_F32 && dtype == FNST_F16), "inorm_apply: split output needs fp32 raw and fp16 activations");
   FNST_CHECK_ARG(raw && stats && gamma && beta && out, "inorm_apply: null pointer");
   FNST_CHECK_ARG(n > 0 && h > 0 && w > 0, "inorm_apply: empty tensor");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_apply: unsupported channel count %d", c);
@@ -252,8 +279,14 @@ extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float
   int rows_per_block = 1;
   while (rows_per_block < 4 && (int64_t)n * ((hp + 2 * rows_per_block - 1) / (2 * rows_per_block)) >= 148 * 16) rows_per_block *= 2;
   dim3 grid((hp + rows_per_block - 1) / rows_per_block, n);
+  if (split) {
+    inorm_apply_kernel<float, __half, 2, true><<<grid, 256, sizeof(float) * 2 * c, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float*>(raw), stats, gamma, beta, drop, reinterpret_cast<const __half*>(res), res_pad,
+        reinterpret_cast<__half*>(out), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
+    return launch_status("inorm_apply");
+  }
   FNST_DISPATCH_DTYPE(dtype, T, {
-    auto kern = inorm_apply_kernel<T, 2>;      // 2 pixels (x raw + residual) in flight per thread: measured best, 77-96 % of copy peak
+    auto kern = inorm_apply_kernel<T, T, 2, false>;   // 2 pixels (x raw + residual) in flight per thread: measured best, 77-96 % of copy peak
     kern<<<grid, 256, sizeof(float) * 2 * c, (cudaStream_t)stream>>>(
         reinterpret_cast<const T*>(raw), stats, gamma, beta, drop, reinterpret_cast<const T*>(res), res_pad,
         reinterpret_cast<T*>(out), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
@@ -322,7 +355,8 @@ extern "C" int fnst_cast(const void* in, void* out, int64_t count, int in_dtype,
 }
 
 extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w, int pad, int pad_mode, int c_pad, int rows,
-                                  int pitch, int dtype, int device, void* stream) {
+                                  int pitch, int dtype, int split, int device, void* stream) {
+  FNST_CHECK_ARG(!split || c_pad == 8, "image_to_halo: the hi|lo split form needs c_pad == 8");
   FNST_CHECK_ARG(x && out && n > 0 && h > 0 && w > 0, "image_to_halo: bad arguments");
   FNST_CHECK_ARG((c_pad == 4 || c_pad == 8) && (dtype == FNST_F16 || dtype == FNST_BF16), "image_to_halo: c_pad must be 4 or 8, dtype fp16/bf16");
   FNST_CHECK_ARG(rows >= h + 2 * pad && pitch >= w + 2 * pad, "image_to_halo: buffer smaller than the padded image");
@@ -332,11 +366,11 @@ extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w
   const int reflect = pad_mode == FNST_PAD_REFLECT;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FNST_F16) {
-    if (c_pad == 4) image_to_halo_kernel<__half, 4><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch);
-    else image_to_halo_kernel<__half, 8><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch);
+    if (c_pad == 4) image_to_halo_kernel<__half, 4><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch, split);
+    else image_to_halo_kernel<__half, 8><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch, split);
   } else {
-    if (c_pad == 4) image_to_halo_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch);
-    else image_to_halo_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch);
+    if (c_pad == 4) image_to_halo_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch, split);
+    else image_to_halo_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch, split);
   }
   return launch_status("image_to_halo");
 }

@@ -17,7 +17,10 @@ from . import ops
 from ._lib import EPI_NHWC, EPI_D2S, EPI_NCHW_F32, EPI_ROWSUM9, PAD_NONE, PAD_REFLECT, PAD_ZERO
 from .ops import ConvSpec
 
-PRECISIONS = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+# "fp16x3": error-compensated tensor-core path for the 1e-4 class (inference forward): every activation and weight is
+# an fp16 pair (hi, lo) and each product is hi*hi + hi*lo + lo*hi accumulated in fp32 -- expressed on the ordinary
+# tcgen05 gather-GEMM as three "virtual taps" per real tap that read different channel windows of [hi | lo] buffers.
+PRECISIONS = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16, "fp16x3": torch.float16}
 
 
 def act_dtype(precision: str) -> torch.dtype:
@@ -55,10 +58,62 @@ def pack_first_tc(w: torch.Tensor, c_pad: int, dtype: torch.dtype) -> torch.Tens
     return b.reshape(o, k * 64).to(dtype).contiguous()
 
 
-def taps_s2d_3x3(c_in: int) -> List[Tuple[int, int, int]]:
+def taps_s2d_3x3(c_in: int, cm: int = 1) -> List[Tuple[int, int, int]]:
     """3x3 stride-2 conv on a space-to-depth halo buffer: tap (kh,kw) reads spatial offset
-    (kh>>1, kw>>1) of phase (kh&1, kw&1), i.e. channel window ((kh&1)*2 + (kw&1)) * c_in."""
-    return [(kh >> 1, kw >> 1, ((kh & 1) * 2 + (kw & 1)) * c_in) for kh in range(3) for kw in range(3)]
+    (kh>>1, kw>>1) of phase (kh&1, kw&1), i.e. channel window ((kh&1)*2 + (kw&1)) * c_in * cm
+    (cm = 2 when every phase holds a [hi | lo] pair)."""
+    return [(kh >> 1, kw >> 1, ((kh & 1) * 2 + (kw & 1)) * c_in * cm) for kh in range(3) for kw in range(3)]
+
+
+# ---- fp16x3 helpers ------------------------------------------------------------------------------------------------
+
+def split_hi_lo(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    hi = w.float().to(torch.float16)
+    return hi, (w.float() - hi.float()).to(torch.float16)
+
+
+def taps_x3(taps: Sequence[Tuple[int, int, int]], lo_offset: int) -> List[Tuple[int, int, int]]:
+    """Each tap becomes (A_hi x B_hi), (A_hi x B_lo), (A_lo x B_hi): the third reads the lo channel window."""
+    out = []
+    for dh, dw, c0 in taps:
+        out += [(dh, dw, c0), (dh, dw, c0), (dh, dw, c0 + lo_offset)]
+    return out
+
+
+def pack_x3(packed_f32: torch.Tensor, ntaps: int, kc: int) -> torch.Tensor:
+    """fp32 operand [n, ntaps*kc] -> fp16 operand [n, ntaps*3*kc] with per-tap blocks (hi, lo, hi)."""
+    n = packed_f32.shape[0]
+    hi, lo = split_hi_lo(packed_f32)
+    h, l = hi.view(n, ntaps, 1, kc), lo.view(n, ntaps, 1, kc)
+    return torch.cat([h, l, h], dim=2).reshape(n, ntaps * 3 * kc).contiguous()
+
+
+def pack_first_x3(w: torch.Tensor) -> torch.Tensor:
+    """conv1 (O,3,9,9) for the split 8-channel image [hi0..2, 0, lo0..2, 0]: taps (kh, window 0/1, block 0/1), 8-pixel
+    windows; block 0 multiplies hi and lo channels by w_hi, block 1 multiplies the hi channels by w_lo."""
+    o, c, k, _ = w.shape
+    hi, lo = split_hi_lo(w)
+    b = torch.zeros((o, k, 2, 2, 8, 8), dtype=torch.float16, device=w.device)       # (o, kh, win, blk, px, ch)
+    for kw in range(k):
+        win, px = divmod(kw, 8)
+        b[:, :, win, 0, px, 0:3] = hi[:, :, :, kw].permute(0, 2, 1)
+        b[:, :, win, 0, px, 4:7] = hi[:, :, :, kw].permute(0, 2, 1)
+        b[:, :, win, 1, px, 0:3] = lo[:, :, :, kw].permute(0, 2, 1)
+    return b.reshape(o, k * 4 * 64).contiguous()
+
+
+def pack_final_rowsum_x3(w: torch.Tensor) -> torch.Tensor:
+    """final_conv (3,32,9,9) for split activations (one pixel = [hi32 | lo32] = one 128-byte row): 18 taps (kw, block),
+    GEMM column kh*3 + o; block 0 = [w_hi | w_hi], block 1 = [w_lo | 0]."""
+    hi, lo = split_hi_lo(w)
+    b = torch.zeros((9, 3, 9, 2, 2, 32), dtype=torch.float16, device=w.device)       # (kh, o, kw, blk, half, c)
+    hp, lp = hi.permute(2, 0, 3, 1), lo.permute(2, 0, 3, 1)                          # (kh, o, kw, c)
+    b[:, :, :, 0, 0, :] = hp
+    b[:, :, :, 0, 1, :] = hp
+    b[:, :, :, 1, 0, :] = lp
+    out = torch.zeros((32, 18 * 64), dtype=torch.float16, device=w.device)
+    out[:27] = b.reshape(27, 18 * 64)
+    return out.contiguous()
 
 
 TAPS_2X2 = [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)]
@@ -126,14 +181,32 @@ class StyleNetPlan:
         self.precision = precision
         self.dtype = act_dtype(precision)
         self.use_tc = precision != "fp32"
+        self.split = precision == "fp16x3"
         self.w: Dict[str, torch.Tensor] = {}
         self.params: Dict[str, torch.Tensor] = {}
 
     # -- weights ---------------------------------------------------------------------------------
+    def _pack_x3(self, p) -> Dict[str, torch.Tensor]:
+        f32 = torch.float32
+        w = {"conv1": pack_first_x3(p["conv1.conv.weight"]),
+             "conv2": pack_x3(pack_conv(p["conv2.conv.weight"], f32), 9, 64)}
+        for i in range(5):
+            w[f"res{i}a"] = pack_x3(pack_conv(p[f"res_blocks.{i}.conv1.conv.weight"], f32), 9, 256)
+            w[f"res{i}b"] = pack_x3(pack_conv(p[f"res_blocks.{i}.conv2.conv.weight"], f32), 9, 256)
+        w["up1"] = pack_x3(pack_conv_transpose(p["up1.upsample_conv.weight"], f32), 4, 256)
+        w["up2"] = pack_x3(pack_conv_transpose(p["up2.upsample_conv.weight"], f32), 4, 64)
+        w["final"] = pack_final_rowsum_x3(p["final_conv.conv.weight"])
+        return w
+
     def pack(self, params: Dict[str, torch.Tensor]) -> "StyleNetPlan":
         p = {k: v.detach() for k, v in params.items()}
         self.params = p
         dt = self.dtype
+        if self.split:
+            self.w = self._pack_x3(p)
+            self.final_bias = torch.zeros(16, dtype=torch.float32, device=self.w["final"].device)
+            self.final_bias[:3] = p["final_conv.conv.bias"].float()
+            return self
         w = {"conv1": pack_first_tc(p["conv1.conv.weight"], 4, dt) if self.use_tc else pack_first(p["conv1.conv.weight"]),
              "conv2": pack_conv(p["conv2.conv.weight"], dt)}
         # the ten 3x3 256->256 weights are packed by two kernels (stack, permute+cast) into one (10, 256, 2304) tensor
@@ -170,6 +243,10 @@ class StyleNetPlan:
         stats = lambda c: torch.empty((B, c, 2), dtype=torch.float32, device=dev)
         if H <= 4 or W <= 4:
             raise RuntimeError("StyleTransferNet needs H, W >= 5 (ReflectionPad2d(4))")
+        if self.split:
+            if tape is not None:
+                raise RuntimeError("precision 'fp16x3' is a forward-only (inference) path; train with 'fp16' or 'fp32'")
+            return self._forward_x3(x, drop_scales)
 
         # conv1: 9x9 stride 2, reflect 4 -> raw1 (B,H1,W1,64)
         H1, W1 = _half_up(H), _half_up(W)
@@ -255,6 +332,74 @@ class StyleNetPlan:
             ops.conv_gather(spec, act4, (B, Hq, Wq, 32), _nhwc_strides(act4), y, (H4, W4), None, False)
         if tape is not None:
             tape.update(raw3=raw3, st3=st3, act3=act3, raw4=raw4, st4=st4, act4=act4, act4_flat=flat, x=x)
+        return y
+
+
+    def _forward_x3(self, x: torch.Tensor, drop_scales) -> torch.Tensor:
+        """fp16x3 forward: same operator sequence; activations are fp16 [hi | lo] pairs (2C channels per pixel), raw conv
+        outputs are fp32, every gather-GEMM runs three virtual taps per real tap (hi*hi, hi*lo, lo*hi)."""
+        B, _, H, W = x.shape
+        dev, w = x.device, self.w
+        act = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)
+        raw = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        stats = lambda c: torch.empty((B, c, 2), dtype=torch.float32, device=dev)
+
+        def conv(taps, kc, lo_off, weight, n_gemm, c_out, a, a_dims, out, out_hw, st, epilogue=EPI_NHWC, strides=None, bias=None):
+            spec = ConvSpec(taps_x3(taps, lo_off), kc, weight, n_gemm, c_out, epilogue=epilogue, bias=bias)
+            ops.conv_gather(spec, a, a_dims, strides or _nhwc_strides(a), out, out_hw, st, True)
+
+        # conv1: split 8-channel image (hi0..2,0,lo0..2,0); 8-pixel windows, two windows per kernel row, two weight blocks
+        H1, W1 = _half_up(H), _half_up(W)
+        rows, pitch = 2 * (H1 + 4), (W + 16 + 1) // 2 * 2
+        img = ops.image_to_halo(x, 4, PAD_REFLECT, 8, rows, pitch, torch.float16, split=True)
+        taps = [(kh >> 1, win * 4, (kh & 1) * pitch * 8) for kh in range(9) for win in (0, 1) for _blk in (0, 1)]
+        raw1, st1 = raw(B, H1, W1, 64), stats(64)
+        ops.conv_gather(ConvSpec(taps, 64, w["conv1"], 64, 64), img, (B, H1 + 4, W1 + 4, pitch * 8 + 64),
+                        (rows * pitch * 8, 2 * pitch * 8, 16), raw1, (H1, W1), st1, True)
+        Hp, Wp = H1 + 2, W1 + 2
+        Hs, Ws = _half_up(Hp), _half_up(Wp)
+        buf2 = torch.zeros((B, Hs, Ws, 512), dtype=torch.float16, device=dev)
+        g, b = self._affine("norm1")
+        ops.inorm_apply(raw1, st1, g, b, buf2, relu=True, pad=1, pad_mode=PAD_REFLECT, s2d=True, split=True)
+        H2, W2 = _half_up(H1), _half_up(W1)
+        raw2, st2 = raw(B, H2, W2, 256), stats(256)
+        conv(taps_s2d_3x3(64, 2), 64, 64, w["conv2"], 256, 256, buf2, (B, Hs, Ws, 512), raw2, (H2, W2), st2)
+        cur = act(B, H2 + 2, W2 + 2, 512)
+        g, b = self._affine("norm2")
+        ops.inorm_apply(raw2, st2, g, b, cur, relu=True, pad=1, pad_mode=PAD_REFLECT, split=True)
+        taps9 = taps_kxk(3)
+        for i in range(5):
+            raw_a, st_a = raw(B, H2, W2, 256), stats(256)
+            conv(taps9, 256, 256, w[f"res{i}a"], 256, 256, cur, (B, H2 + 2, W2 + 2, 512), raw_a, (H2, W2), st_a)
+            mid = act(B, H2 + 2, W2 + 2, 512)
+            g, b = self._affine(f"res_blocks.{i}.in1")
+            drop = None if drop_scales is None else drop_scales[i].float().contiguous()
+            ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop, split=True)
+            raw_b, st_b = raw(B, H2, W2, 256), stats(256)
+            conv(taps9, 256, 256, w[f"res{i}b"], 256, 256, mid, (B, H2 + 2, W2 + 2, 512), raw_b, (H2, W2), st_b)
+            last = i == 4
+            nxt = act(B, H2, W2, 512) if last else act(B, H2 + 2, W2 + 2, 512)
+            g, b = self._affine(f"res_blocks.{i}.in2")
+            ops.inorm_apply(raw_b, st_b, g, b, nxt, relu=False, pad=0 if last else 1,
+                            pad_mode=PAD_NONE if last else PAD_REFLECT, res=cur, res_pad=1, split=True)
+            cur = nxt
+        H3, W3 = 2 * H2, 2 * W2
+        raw3, st3 = raw(B, H3, W3, 64), stats(64)
+        conv(TAPS_2X2, 256, 256, w["up1"], 256, 64, cur, (B, H2, W2, 512), raw3, (H2, W2), st3, epilogue=EPI_D2S)
+        act3 = act(B, H3, W3, 128)
+        g, b = self._affine("norm3")
+        ops.inorm_apply(raw3, st3, g, b, act3, relu=True, split=True)
+        H4, W4 = 2 * H3, 2 * W3
+        raw4, st4 = raw(B, H4, W4, 32), stats(32)
+        conv(TAPS_2X2, 64, 64, w["up2"], 128, 32, act3, (B, H3, W3, 128), raw4, (H3, W3), st4, epilogue=EPI_D2S)
+        Hq, Wq = H4 + 8, W4 + 8
+        act4 = act(B, Hq, Wq, 64)                           # one pixel = [hi32 | lo32] = one 128-byte row
+        g, b = self._affine("norm4")
+        ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT, split=True)
+        y = torch.empty((B, 3, H4, W4), dtype=torch.float32, device=dev)
+        taps = [(0, kw, 0) for kw in range(9) for _blk in (0, 1)]
+        ops.conv_gather(ConvSpec(taps, 64, w["final"], 32, 3, epilogue=EPI_ROWSUM9, bias=self.final_bias), act4,
+                        (B, Hq, Wq, 64), _nhwc_strides(act4), y, (H4, W4), None, True)
         return y
 
 

@@ -155,11 +155,13 @@ def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
 def inorm_apply(raw: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
                 relu: bool, pad: int = 0, pad_mode: int = _lib.PAD_NONE, s2d: bool = False,
                 drop: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, res_pad: int = 0,
-                eps: float = 1e-5) -> None:
+                eps: float = 1e-5, split: bool = False) -> None:
+    """split: raw is fp32, out/res are fp16 buffers with 2c channels per pixel [hi | lo] (fp16x3 path)."""
     n, h, w, c = raw.shape
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_apply(_ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(res), res_pad, _ptr(out),
-                               n, h, w, c, dt(raw.dtype), int(relu), eps, pad, pad_mode, int(s2d), dev, st), "inorm_apply")
+                               n, h, w, c, dt(out.dtype), int(relu), eps, pad, pad_mode, int(s2d), dt(raw.dtype), int(split),
+                               dev, st), "inorm_apply")
     _count()
 
 
@@ -342,7 +344,8 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out
 
 
-def image_to_halo(x: torch.Tensor, pad: int, pad_mode: int, c_pad: int, rows: int, pitch: int, dtype: torch.dtype) -> torch.Tensor:
+def image_to_halo(x: torch.Tensor, pad: int, pad_mode: int, c_pad: int, rows: int, pitch: int, dtype: torch.dtype,
+                  split: bool = False) -> torch.Tensor:
     """(n,3,h,w) fp32 -> flat 2-byte halo buffer viewed as (n, rows, pitch, c_pad) plus 128 zero elements of slack
     (window views of the last pixels read a little past the end)."""
     n, c, h, w = x.shape
@@ -351,6 +354,7 @@ def image_to_halo(x: torch.Tensor, pad: int, pad_mode: int, c_pad: int, rows: in
     flat = torch.empty(numel + 128, dtype=dtype, device=x.device)
     flat[numel:].zero_()
     dev, st = _ctx(x)
-    check(lib.fnst_image_to_halo(_ptr(x), _ptr(flat), n, h, w, pad, pad_mode, c_pad, rows, pitch, dt(dtype), dev, st), "image_to_halo")
+    check(lib.fnst_image_to_halo(_ptr(x), _ptr(flat), n, h, w, pad, pad_mode, c_pad, rows, pitch, dt(dtype), int(split), dev, st),
+          "image_to_halo")
     _count()
     return flat

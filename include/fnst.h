@@ -114,11 +114,14 @@ int fnst_conv_first(const float* x, int n, int h, int w, const float* wgt, const
  *   res   or NULL                  residual source: NHWC buffer with halo `res_pad`
  *   out                            [n, h+2*pad, w+2*pad, c]; if s2d: [n, ceil((h+2p)/2), ceil((w+2p)/2), 4c]
  *                                  with channel = ((hp&1)*2 + (wp&1))*c + ch
+ *   raw_dtype                      element type of raw (== dtype, or FNST_F32 with split)
+ *   split                          error-compensated fp16 pair: out (and res) hold 2c channels per pixel [hi(c) | lo(c)],
+ *                                  hi = fp16(y), lo = fp16(y - hi)  (fp16x3 path: hi*hi + hi*lo + lo*hi on tensor cores)
  */
 int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, const float* beta,
                      const float* drop, const void* res, int res_pad, void* out,
                      int n, int h, int w, int c, int dtype, int relu, float eps,
-                     int pad, int pad_mode, int s2d, int device, void* stream);
+                     int pad, int pad_mode, int s2d, int raw_dtype, int split, int device, void* stream);
 
 /*
  * NCHW fp32 3-channel image -> 2-byte NHWC halo buffer [n][rows][pitch][c_pad] (c_pad 4 or 8; channels >= 3 zero), interior at
@@ -127,7 +130,8 @@ int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, co
  * ConvLayer(3,64,9,stride=2) (models/model.py:28) is a 9-tap and VGG conv1_1 a 3-tap gather-GEMM (taps = kernel rows).
  */
 int fnst_image_to_halo(const float* x, void* out, int n, int h, int w, int pad, int pad_mode, int c_pad, int rows,
-                       int pitch, int dtype, int device, void* stream);
+                       int pitch, int dtype, int split, int device, void* stream);
+/* split (c_pad == 8 only): channels 0..2 hold fp16(x), channels 4..6 hold fp16(x - hi) (hi|lo pair of the fp16x3 path). */
 
 /* MaxPool2d(2,2) on NHWC (torchvision features[4], [9], [18]); h, w are input extents (floor). */
 int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream);

@@ -76,18 +76,22 @@ def conv_first(x, weight, bias, k, stride, pad, pad_mode, relu, out, stats):
     out.copy_(v.to(out.dtype))
 
 
-def image_to_halo(x, pad, pad_mode, c_pad, rows, pitch, dtype):
+def image_to_halo(x, pad, pad_mode, c_pad, rows, pitch, dtype, split=False):
     n, c, h, w = x.shape
     xp = F.pad(x, (pad,) * 4, mode="reflect" if pad_mode == PAD_REFLECT else "constant")
     buf = torch.zeros((n, rows, pitch, c_pad), dtype=torch.float32)
     buf[:, :h + 2 * pad, :w + 2 * pad, :3] = xp.permute(0, 2, 3, 1)
+    if split:
+        hi = buf[..., :3].to(dtype).float()
+        buf[..., 4:7] = buf[..., :3] - hi
+        buf[..., :3] = hi
     flat = torch.zeros(buf.numel() + 128, dtype=dtype)
     flat[:buf.numel()] = buf.reshape(-1).to(dtype)
     return flat
 
 
 def inorm_apply(raw, stats, gamma, beta, out, relu, pad=0, pad_mode=PAD_NONE, s2d=False, drop=None, res=None,
-                res_pad=0, eps=1e-5):
+                res_pad=0, eps=1e-5, split=False):
     n, h, w, c = raw.shape
     cnt = h * w
     mean = stats[:, :, 0].double() / cnt
@@ -100,7 +104,12 @@ def inorm_apply(raw, stats, gamma, beta, out, relu, pad=0, pad_mode=PAD_NONE, s2
     if drop is not None:
         y = y * drop.double().view(n, 1, 1, c)
     if res is not None:
-        y = y + res.double()[:, res_pad:res_pad + h, res_pad:res_pad + w, :]
+        r = res.double()[:, res_pad:res_pad + h, res_pad:res_pad + w, :]
+        y = y + (r[..., :c] + r[..., c:] if split else r)
+    if split:                                              # [hi | lo] fp16 pair per pixel
+        hi = y.to(out.dtype).double()
+        y = torch.cat([hi, y - hi], dim=-1)
+        c = 2 * c
     if pad:
         if pad_mode == PAD_REFLECT:
             hi = _reflect(torch.arange(-pad, h + pad), h)

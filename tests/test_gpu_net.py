@@ -78,3 +78,17 @@ def test_vgg_features(precision, tol):
         err = rel_l2(f.permute(0, 3, 1, 2), r)
         print(f"vgg {precision} feat{i}: {err:.3e}")
         assert err < tol, i
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64), (2, 37, 45), (1, 256, 256)])
+def test_stylenet_fp16x3_tensor_core_path_meets_fp32_tolerance(shape):
+    """Error-compensated fp16 (hi, lo) split on the tcgen05 kernel: the 1e-4 class on tensor cores."""
+    p = O.make_net_params(seed=0, random_affine=True)
+    b, h, w = shape
+    x = O.make_image(b, h, w, seed=1234)
+    with torch.no_grad():
+        ref = O.stylenet_forward(p, x)
+    y = engine.StyleNetPlan("fp16x3").pack(_cuda(p)).forward(x.to(DEV))
+    err = rel_l2(y, ref)
+    print(f"fp16x3 {shape}: rel_l2={err:.3e}")
+    assert y.shape == ref.shape and err < 1e-4

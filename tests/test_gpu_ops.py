@@ -241,3 +241,35 @@ def test_conv_per_image_weights(dtype, use_tc):
     spec = ConvSpec([(0, 0, 0)], C, wts, C, C, per_image_weights=True)
     got, ref, _, _ = _run_conv_pair(spec, a, (B, H, W, C), engine._nhwc_strides(a), (B, H, W, C), (H, W), False, use_tc)
     assert rel_l2(got, ref) < {torch.float32: 2e-6, torch.float16: 1e-3, torch.bfloat16: 6e-3}[dtype]
+
+
+def test_split_producers():
+    """fp16 (hi | lo) split writers of the fp16x3 path: inorm_apply(split) and image_to_halo(split)."""
+    g = torch.Generator().manual_seed(41)
+    n, h, w, c = 2, 9, 13, 64
+    raw = torch.randn((n, h, w, c), generator=g) * 2 + 0.5
+    st = torch.stack([raw.double().sum(dim=(1, 2)), (raw.double() ** 2).sum(dim=(1, 2))], dim=-1).float()
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    res_f = torch.randn((n, h + 2, w + 2, c), generator=g)
+    res_hi = res_f.half()
+    res = torch.cat([res_hi, (res_f - res_hi.float()).half()], dim=-1)
+    for s2d in (False, True):
+        hp, wp = h + 2, w + 2
+        oshape = (n, (hp + 1) // 2, (wp + 1) // 2, 8 * c) if s2d else (n, hp, wp, 2 * c)
+        ref = torch.zeros(oshape, dtype=torch.float16)
+        r = None if s2d else res
+        emu_ops.inorm_apply(raw, st, gamma, beta, ref, True, 1, 1, s2d, None, r, 1, split=True)
+        out = torch.zeros(oshape, dtype=torch.float16, device=DEV)
+        ops.inorm_apply(raw.to(DEV), st.to(DEV), gamma.to(DEV), beta.to(DEV), out, True, 1, 1, s2d, None,
+                        None if r is None else r.to(DEV), 1, split=True)
+        if s2d:
+            got = out.cpu().float().view(n, oshape[1], oshape[2], 4, 2, c).sum(4)
+            want = ref.float().view(n, oshape[1], oshape[2], 4, 2, c).sum(4)
+        else:
+            got = out.cpu().float().view(*oshape[:3], 2, c).sum(3)           # hi + lo recombined
+            want = ref.float().view(*oshape[:3], 2, c).sum(3)
+        assert rel_l2(got, want) < 3e-6
+    x = torch.rand((2, 3, 11, 14), generator=g)
+    ref = emu_ops.image_to_halo(x, 4, 1, 8, 20, 24, torch.float16, split=True)
+    got = ops.image_to_halo(x.to(DEV), 4, 1, 8, 20, 24, torch.float16, split=True)
+    assert torch.equal(got.cpu(), ref)

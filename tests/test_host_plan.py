@@ -68,3 +68,19 @@ def test_pack_conv_transpose_is_subpixel_form():
     cols = torch.cat([xp[:, dh:dh + 5, dw:dw + 6, :] for dh, dw, _ in engine.TAPS_2X2], dim=-1)
     out = (cols @ b.t()).view(1, 5, 6, 2, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(1, 10, 12, 4).permute(0, 3, 1, 2)
     assert torch.allclose(out, ref, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 21, 27)])
+def test_stylenet_plan_fp16x3_is_fp32_accurate(monkeypatch, shape):
+    """Error-compensated split: real fp16 (hi, lo) pairs, three virtual taps per tap -> 1e-4 class accuracy."""
+    emu_ops.install(monkeypatch, ops)
+    p = O.make_net_params(seed=3, random_affine=True)
+    b, h, w = shape
+    x = O.make_image(b, h, w, seed=11)
+    y = engine.StyleNetPlan("fp16x3").pack(p).forward(x)
+    with torch.no_grad():
+        ref = O.stylenet_forward(p, x)
+    assert y.shape == ref.shape
+    err = rel_l2(y, ref)
+    print("fp16x3 emulated rel_l2", err)
+    assert err < 1e-4
