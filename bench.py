@@ -122,12 +122,15 @@ def time_dominant_kernel(net, per_rank, h, w, dev):
     plan = net._plan()
     dt = plan.dtype
     h2, w2 = (h + 3) // 4, (w + 3) // 4
-    set_bytes = per_rank * ((h2 + 2) * (w2 + 2) + h2 * w2) * 256 * dt.itemsize
+    set_bytes = per_rank * ((h2 + 2) * (w2 + 2) + h2 * w2) * 256 * dt.itemsize     # (fp16x3 sets are larger still)
     n_sets = max(2, min(64, int(2.5 * 126e6 / set_bytes) + 1))
-    ins = [torch.randn((per_rank, h2 + 2, w2 + 2, 256), device=dev).to(dt) for _ in range(n_sets)]
-    outs = [torch.empty((per_rank, h2, w2, 256), dtype=dt, device=dev) for _ in range(n_sets)]
+    split = getattr(plan, "split", False)                 # fp16x3: [hi | lo] activations, three virtual taps per tap, fp32 raw output
+    cin = 512 if split else 256
+    ins = [torch.randn((per_rank, h2 + 2, w2 + 2, cin), device=dev).to(dt) for _ in range(n_sets)]
+    outs = [torch.empty((per_rank, h2, w2, 256), dtype=torch.float32 if split else dt, device=dev) for _ in range(n_sets)]
     stats = [torch.empty((per_rank, 256, 2), dtype=torch.float32, device=dev) for _ in range(n_sets)]
-    spec = ConvSpec(engine.taps_kxk(3), 256, plan.w["res0a"], 256, 256)
+    taps = engine.taps_x3(engine.taps_kxk(3), 256) if split else engine.taps_kxk(3)
+    spec = ConvSpec(taps, 256, plan.w["res0a"], 256, 256)
     def launch_all():
         for a, o, st in zip(ins, outs, stats):
             ops.conv_gather(spec, a, tuple(a.shape), engine._nhwc_strides(a), o, (h2, w2), st, plan.use_tc)
@@ -242,7 +245,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=os.environ.get("FNST_BENCH_WORKLOAD", "train"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32", "fp16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2-flush", action="store_true", help="write a 256 MB buffer between timed iterations (small workloads)")
     args = ap.parse_args()
@@ -343,7 +346,7 @@ def main():
         return
     line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
-            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32", "fp16x3": "f16x3 (hi,lo split, fp32-class)"}[args.precision], "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "per_gpu_batch": per_rank, "image": [wl["h"], wl["w"]],
                        "l2": ("L2 flushed (256 MB write) between timed iterations; each iteration timed with its own event pair" if small
                               else "inputs+activations per step exceed the 126 MB L2 (no flush needed)"),

@@ -92,3 +92,17 @@ def test_stylenet_fp16x3_tensor_core_path_meets_fp32_tolerance(shape):
     err = rel_l2(y, ref)
     print(f"fp16x3 {shape}: rel_l2={err:.3e}")
     assert y.shape == ref.shape and err < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 135, 240), (3, 50, 34)])
+def test_stylenet_odd_aspect_and_batch(shape):
+    """1080p-like aspect (1/8 scale) and an odd batch: ragged tiles on every layer of the tensor-core path."""
+    p = O.make_net_params(seed=0, random_affine=True)
+    b, h, w = shape
+    x = O.make_image(b, h, w, seed=99)
+    with torch.no_grad():
+        ref = O.stylenet_forward(p, x)
+    for precision, tol in (("fp16", 1e-2), ("fp16x3", 1e-4)):
+        y = engine.StyleNetPlan(precision).pack(_cuda(p)).forward(x.to(DEV))
+        assert y.shape == ref.shape
+        assert rel_l2(y, ref) < tol, precision

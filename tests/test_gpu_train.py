@@ -124,6 +124,12 @@ def test_training_step_tensor_core_path(dropin):
     _check(got, grads, rl, rg, tol_loss=1e-2, tol_grad=1.2e-1, label="tc 2x64x64")
 
 
+def test_training_step_tensor_core_path_odd_size(dropin):
+    """Ragged tiles through forward, dgrad and wgrad of every layer (11x13 trunk planes)."""
+    got, grads, rl, rg = _step(dropin, "fp16", "bf16", 1, 44, 52, seed=2)
+    _check(got, grads, rl, rg, tol_loss=1e-2, tol_grad=1.5e-1, label="tc 1x44x52")
+
+
 def test_loss_functions_backward_standalone(dropin):
     """gram / sse / tv backward on plain fp32 NCHW tensors vs torch autograd of the oracle formulas."""
     _, _, ll = dropin
