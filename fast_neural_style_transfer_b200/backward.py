@@ -11,6 +11,7 @@ reach 1e7-5e8 at random init, SURVEY 7.2, which overflows fp16).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -99,6 +100,31 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     def zeros_like_param(name):
         return zero_views[name]
 
+    # Weight gradients are off the critical path (nothing downstream in this backward consumes them): they run on a
+    # side stream forked from the main stream right after their operands are produced and joined at the end.  Under
+    # CUDA-graph capture this becomes a parallel branch; operands are kept alive until the join so the allocator cannot
+    # hand their memory to a later main-stream tensor while the side branch still reads it.
+    main_stream = torch.cuda.current_stream(dev)
+    side_stream = torch.cuda.Stream(device=dev) if os.environ.get("FNST_WGRAD_STREAM", "1") != "0" else None
+    keep_alive = []
+
+    class _Side:
+        def __enter__(self_inner):
+            if side_stream is not None:
+                side_stream.wait_stream(main_stream)
+                self_inner.ctx = torch.cuda.stream(side_stream)
+                self_inner.ctx.__enter__()
+            return self_inner
+
+        def __exit__(self_inner, *exc):
+            if side_stream is not None:
+                self_inner.ctx.__exit__(*exc)
+            return False
+
+    def on_side(*tensors):
+        keep_alive.extend(tensors)
+        return _Side()
+
     def dgrad(g, g_dims, fwd_packed, fwd_taps, fwd_kc, out_shape, out_hw, h0=0, w0=0):
         """Data gradient of a forward gather-GEMM with plain taps (c0 == 0)."""
         n_gemm_f = fwd_packed.shape[0]
@@ -123,13 +149,15 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         g8 = ops.image_to_halo(dy, 8, PAD_ZERO, 8, rows_g, pitch_g, gdt)
         g_str = (rows_g * pitch_g * 8, pitch_g * 8, 8)
         flat = tape["act4_flat"]
-        a_g = flat if flat.dtype == gdt else ops.cast(flat, gdt)
         taps9 = [(kh - 8, 0, 0) for kh in range(9)]
-        db = ops.wgrad(ConvSpec(taps9, 64, None, 128, 128), a_g, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), g8,
-                       (rows_g, pitch_g), use_tc=True, g_strides=g_str)
-        d5 = db.view(16, 8, 9, 2, 32)                                         # (i, j, kh, jj, c)
         idx = torch.arange(8, -1, -1, device=dev)                             # kw -> i = 8 - kw (jj = 0 entries)
-        grads["final_conv.conv.weight"] = d5[idx, :3, :, 0, :].permute(1, 3, 2, 0).contiguous()      # (j, c, kh, kw)
+        with on_side(g8, flat):
+            a_g = flat if flat.dtype == gdt else ops.cast(flat, gdt)
+            db = ops.wgrad(ConvSpec(taps9, 64, None, 128, 128), a_g, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), g8,
+                           (rows_g, pitch_g), use_tc=True, g_strides=g_str)
+            d5 = db.view(16, 8, 9, 2, 32)                                     # (i, j, kh, jj, c)
+            grads["final_conv.conv.weight"] = d5[idx, :3, :, 0, :].permute(1, 3, 2, 0).contiguous()  # (j, c, kh, kw)
+            keep_alive.extend([a_g, db])
         wd = torch.zeros((32, 9, 2, 8, 8), dtype=torch.float32, device=dev)   # (c, kh, a, i, j)
         wperm = wfin.detach().float().permute(1, 2, 3, 0)                     # (c, kh, kw, j)
         wd[:, :, 0, :, :3] = wperm[:, :, idx[:8], :]                          # a = 0: pixel i <-> kw = 8 - i
@@ -152,8 +180,10 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     d_raw4 = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
     act3 = tape["act3"]
     H3, W3 = act3.shape[1], act3.shape[2]
-    db = _wgrad(tc, ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, (B, H3, W3, 64), d_raw4, (H3, W3))
-    grads["up2.upsample_conv.weight"] = unpack_conv_transpose(db, 64, 32)
+    with on_side(act3, d_raw4):
+        db = _wgrad(tc, ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, (B, H3, W3, 64), d_raw4, (H3, W3))
+        grads["up2.upsample_conv.weight"] = unpack_conv_transpose(db, 64, 32)
+        keep_alive.append(db)
     grads["up2.upsample_conv.bias"] = zeros_like_param("up2.upsample_conv.bias")
     wup2 = plan.w["up2"] if plan.w["up2"].dtype == gdt else engine.pack_conv_transpose(p["up2.upsample_conv.weight"], gdt)
     d_act3 = dgrad(d_raw4, (B, H3, W3, 128), wup2, TAPS_2X2, 64, (B, H3, W3, 64), (H3, W3))
@@ -166,8 +196,10 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     trunk = tape["trunk"]
     last = trunk[5]
     H2, W2 = last.shape[1], last.shape[2]
-    db = _wgrad(tc, ConvSpec(TAPS_2X2, 256, None, 256, 64), last, (B, H2, W2, 256), d_raw3, (H2, W2))
-    grads["up1.upsample_conv.weight"] = unpack_conv_transpose(db, 256, 64)
+    with on_side(last, d_raw3):
+        db = _wgrad(tc, ConvSpec(TAPS_2X2, 256, None, 256, 64), last, (B, H2, W2, 256), d_raw3, (H2, W2))
+        grads["up1.upsample_conv.weight"] = unpack_conv_transpose(db, 256, 64)
+        keep_alive.append(db)
     grads["up1.upsample_conv.bias"] = zeros_like_param("up1.upsample_conv.bias")
     wup1 = plan.w["up1"] if plan.w["up1"].dtype == gdt else engine.pack_conv_transpose(p["up1.upsample_conv.weight"], gdt)
     g_plain = dgrad(d_raw3, (B, H2, W2, 256), wup1, TAPS_2X2, 256, (B, H2, W2, 256), (H2, W2))
@@ -199,7 +231,8 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(dgb)
         d_raw_b = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
         mid = blk["mid"]
-        _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2), out=res_db[2 * i + 1])
+        with on_side(mid, d_raw_b):
+            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2), out=res_db[2 * i + 1])
         grads[pre + ".conv2.conv.bias"] = zeros_like_param(pre + ".conv2.conv.bias")
         d_mid = res_dgrad(d_raw_b, 2 * i + 1)
         # in1 + ReLU + Dropout2d
@@ -208,12 +241,14 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(dgb)
         d_raw_a = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
         cur = trunk[i]
-        _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2), out=res_db[2 * i])
+        with on_side(cur, d_raw_a):
+            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2), out=res_db[2 * i])
         grads[pre + ".conv1.conv.bias"] = zeros_like_param(pre + ".conv1.conv.bias")
         gsrc = res_dgrad(d_raw_a, 2 * i)
         extra = g_out
     res_dw = torch.empty((10, 256, 256, 3, 3), dtype=torch.float32, device=dev)
-    res_dw.copy_(res_db.view(10, 256, 3, 3, 256).permute(0, 1, 4, 2, 3))
+    with on_side(res_db):
+        res_dw.copy_(res_db.view(10, 256, 3, 3, 256).permute(0, 1, 4, 2, 3))
     for i in range(5):
         grads[f"res_blocks.{i}.conv1.conv.weight"] = res_dw[2 * i]
         grads[f"res_blocks.{i}.conv2.conv.weight"] = res_dw[2 * i + 1]
@@ -225,8 +260,10 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     d_raw2 = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
     buf2 = tape["buf2"]
     Hs, Ws = buf2.shape[1], buf2.shape[2]
-    db = _wgrad(tc, ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, (B, Hs, Ws, 256), d_raw2, (H2, W2))
-    grads["conv2.conv.weight"] = unpack_conv(db, 256, 64, 3)
+    with on_side(buf2, d_raw2):
+        db = _wgrad(tc, ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, (B, Hs, Ws, 256), d_raw2, (H2, W2))
+        grads["conv2.conv.weight"] = unpack_conv(db, 256, 64, 3)
+        keep_alive.append(db)
     grads["conv2.conv.bias"] = zeros_like_param("conv2.conv.bias")
     wd2 = pack_dgrad_s2d(p["conv2.conv.weight"], gdt)
     d_buf2 = torch.empty((B, Hs, Ws, 256), dtype=gdt, device=dev)
@@ -253,7 +290,11 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         dw1 = ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT)             # tap-major (243, 64)
         grads["conv1.conv.weight"] = dw1.view(3, 9, 9, 64).permute(3, 0, 1, 2).contiguous()
     grads["conv1.conv.bias"] = zeros_like_param("conv1.conv.bias")
-    return {k: v.to(p[k].dtype) for k, v in grads.items()}
+    if side_stream is not None:
+        main_stream.wait_stream(side_stream)             # join the weight-gradient branch
+    out = {k: v.to(p[k].dtype) for k, v in grads.items()}
+    del keep_alive[:]
+    return out
 
 
 # -------------------------------------------------------------------------------------------------------
