@@ -53,7 +53,26 @@ class GradientAllReduce:
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
 
+    def _flat_view(self):
+        """If every gradient is a view into one contiguous fp32 buffer in parameter order (the CUDA-graph backward
+        returns them that way), return that buffer as a 1-D tensor -- the all-reduce then runs in place, no copies."""
+        grads = [p.grad for p in self.params]
+        if any(g is None or g.dtype != torch.float32 or not g.is_contiguous() for g in grads):
+            return None
+        storage = grads[0].untyped_storage()
+        offset = grads[0].storage_offset()
+        for g in grads:
+            if g.untyped_storage().data_ptr() != storage.data_ptr() or g.storage_offset() != offset:
+                return None
+            offset += g.numel()
+        return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(storage, grads[0].storage_offset(), (self.numel,))
+
     def all_reduce(self) -> torch.Tensor:
+        flat = self._flat_view()
+        if flat is not None:
+            if self.world > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            return flat
         p0 = self.params[0]
         if self.flat is None or self.flat.device != p0.device:
             self.flat = torch.empty(self.numel, dtype=torch.float32, device=p0.device)

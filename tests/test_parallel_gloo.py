@@ -37,6 +37,17 @@ def _worker(rank, world, port, out_dir):
         for k, v in grads.items():
             holder[k.replace(".", "/")].grad = v.clone()
         parallel.GradientAllReduce(holder, world).all_reduce()
+        # zero-copy path: gradients that are views of one flat buffer are reduced in place
+        holder2 = torch.nn.ParameterDict({k.replace(".", "/"): torch.nn.Parameter(v.clone()) for k, v in p.items()})
+        order = [n.replace("/", ".") for n, _ in holder2.named_parameters()]       # the module's own parameter order
+        flat = torch.cat([grads[k].reshape(-1) for k in order])
+        for k, piece in zip(order, torch.split(flat, [p[k].numel() for k in order])):
+            holder2[k.replace(".", "/")].grad = piece.view_as(p[k])
+        ar = parallel.GradientAllReduce(holder2, world)
+        assert ar._flat_view() is not None and ar._flat_view().data_ptr() == flat.data_ptr()
+        ar.all_reduce()
+        for k in p:
+            assert torch.allclose(holder2[k.replace(".", "/")].grad, holder[k.replace(".", "/")].grad, rtol=1e-6, atol=0)
         assert parallel.all_finite(torch.tensor(1.0), world)
         assert not parallel.all_finite(torch.tensor(float("nan") if rank == 1 else 1.0), world)
         if rank == 0:
