@@ -96,6 +96,52 @@ def sse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return _sse_forward(an, bn)
 
 
+# ---- fused style loss ----------------------------------------------------------------------------------------
+
+class _StyleLoss(torch.autograd.Function):
+    """sum_l w_l * SSE(gram(F_l), T_l) / c_l^2 over the given layers as ONE autograd node (losses/losses.py:15-44).
+    Backward per layer: one kernel builds S = g*w/c^2 * 2*((G-T) + (G-T)^T)/... in the feature dtype, one batched 1x1
+    gather-GEMM computes dF = F S -- instead of ~10 autograd nodes per layer on the critical path after the NaN check."""
+
+    @staticmethod
+    def forward(ctx, weights, targets, cs, *feats):
+        fs = [_as_nhwc(f.detach()) for f in feats]
+        grams = [ops.gram(f, use_tc=_gram_tc_ok(f)) for f in fs]
+        acc = torch.zeros(len(fs), dtype=torch.float64, device=fs[0].device)
+        coefs = []
+        for i, (g, t, w, c) in enumerate(zip(grams, targets, weights, cs)):
+            ops.sse(g, t, acc[i:i + 1].view(()))
+            coefs.append(w / (c * c))
+        ctx.fs, ctx.grams, ctx.targets, ctx.coefs = fs, grams, targets, coefs
+        coef_t = torch.tensor(coefs, dtype=torch.float64, device=acc.device)
+        return (acc * coef_t).sum().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import backward
+        scale = g.reshape(1).float()
+        outs = []
+        for f, gram_, t, coef in zip(ctx.fs, ctx.grams, ctx.targets, ctx.coefs):
+            s = ops.gram_diff_sym(gram_, t, scale, 2.0 * coef, f.dtype)     # d/dG of coef*sum(G-T)^2 is 2*coef*(G-T); dF = F (dG + dG^T)
+            outs.append(backward.gram_apply(f, s).permute(0, 3, 1, 2))
+        ctx.fs = ctx.grams = None
+        return (None, None, None) + tuple(outs)
+
+
+def style_loss_fused(feats: Sequence[torch.Tensor], targets: Sequence[torch.Tensor], weights: Sequence[float],
+                     cs: Sequence[int]) -> torch.Tensor:
+    for f in feats:
+        _need_cuda(f, "style_loss")
+    targets = [t.detach().float().contiguous() for t in targets]
+    if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+        return _StyleLoss.apply(list(weights), targets, list(cs), *feats)
+    total = None
+    for f, t, w, c in zip(feats, targets, weights, cs):
+        term = (w * sse(gram(f), t)) / (c * c)
+        total = term if total is None else total + term
+    return total
+
+
 # ---- total variation ---------------------------------------------------------------------------------
 
 class _TV(torch.autograd.Function):

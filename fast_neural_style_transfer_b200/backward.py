@@ -372,8 +372,12 @@ def vgg_backward(plan: "engine.VGGPlan", tape: dict, dfeats: Sequence[Optional[t
 
 def gram_backward(f: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
     """f NHWC (B,H,W,C); dg (B,C,C) fp32.  dF[p,i] = sum_j F[p,j] * (dG + dG^T)[i,j]: a 1x1 gather-GEMM with per-image weights."""
+    return gram_apply(f, (dg + dg.transpose(1, 2)).to(f.dtype).contiguous())
+
+
+def gram_apply(f: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """dF[n] = F[n] S[n] for per-image symmetric factors S (B,C,C) in the feature dtype."""
     B, H, W, C = f.shape
-    s = (dg + dg.transpose(1, 2)).to(f.dtype).contiguous()
     out = torch.empty_like(f)
     use_tc = f.dtype != torch.float32 and C % 64 == 0
     spec = ConvSpec([(0, 0, 0)], C, s, C, C, per_image_weights=True)      # one launch, image n multiplies by s[n]

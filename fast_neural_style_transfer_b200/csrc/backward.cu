@@ -373,6 +373,22 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const TG* __restrict__ g
   }
 }
 
+// Style-loss backward factor: S[n][i][j] = scale[0] * coef * ((G - Gt)[n][i][j] + (G - Gt)[n][j][i]), written in the
+// feature element type; dF[n] = F[n] * S[n]  (gradient of coef' * sum (G - Gt)^2 through G = F^T F, losses.py:6-44).
+template <typename TG>
+__global__ void __launch_bounds__(256) gram_diff_sym_kernel(const float* __restrict__ G, const float* __restrict__ Gt, int64_t period,
+                                                            int C, int64_t total, const float* __restrict__ scale, float coef,
+                                                            TG* __restrict__ S) {
+  const float k = scale[0] * coef;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / ((int64_t)C * C), r = i - n * (int64_t)C * C;
+    const int a = r / C, b = r - (int64_t)a * C;
+    const int64_t t = n * (int64_t)C * C + (int64_t)b * C + a;
+    const float d = (G[i] - Gt[i % period]) + (G[t] - Gt[t % period]);
+    S[i] = from_f32<TG>(k * d);
+  }
+}
+
 __global__ void __launch_bounds__(256) tv_bwd_kernel(const float* __restrict__ img, int planes, int H, int W,
                                                      const float* __restrict__ scale, float* __restrict__ dimg) {
   const int64_t total = (int64_t)planes * H * W;
@@ -536,6 +552,18 @@ extern "C" int fnst_relu_mask(const void* g, const void* extra, const void* act,
     });
   });
   return launch_status("relu_mask");
+}
+
+extern "C" int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c, int64_t gt_numel, const float* scale, float coef,
+                                  void* s_out, int out_dtype, int device, void* stream) {
+  FNST_CHECK_ARG(g && gt && scale && s_out && n > 0 && c > 0 && gt_numel > 0, "gram_diff_sym: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  const int64_t total = (int64_t)n * c * c;
+  FNST_DISPATCH_DTYPE(out_dtype, TG, {
+    gram_diff_sym_kernel<TG><<<grid_cap(total), 256, 0, (cudaStream_t)stream>>>(g, gt, gt_numel, c, total, scale, coef,
+                                                                              reinterpret_cast<TG*>(s_out));
+  });
+  return launch_status("gram_diff_sym");
 }
 
 extern "C" int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream) {

@@ -21,15 +21,16 @@ def gram_matrix(input_feat):
 def style_loss(input_features, target_grams):
     """sum over (idx, weight) in zip([0,1,2,4], [.25,.3,.45]) of weight * SSE(G, G*) / c^2
     (losses/losses.py:15-44; the zip stops after three layers)."""
-    total = 0.0
-    for idx, weight in zip([0, 1, 2, 4], [0.25, 0.3, 0.45]):
-        target = target_grams[idx]
-        c = target.shape[0]
-        g = gram_matrix(input_features[idx])
-        if target.dim() == 3 and target.size(0) != g.size(0) and target.size(0) != 1:
+    pairs = list(zip([0, 1, 2, 4], [0.25, 0.3, 0.45]))
+    feats, targets, cs = [], [], []
+    for idx, _ in pairs:
+        target, feat = target_grams[idx], input_features[idx]
+        if target.dim() == 3 and target.size(0) not in (1, feat.size(0)):
             raise RuntimeError("target gram batch does not match input batch")
-        total = total + (weight * _fn.sse(g, target)) / (c * c)
-    return total
+        cs.append(target.shape[0])          # taken before the unsqueeze in the reference (losses.py:30): C for (C,C) targets
+        feats.append(feat)
+        targets.append(target.squeeze(0) if target.dim() == 3 and target.size(0) == 1 else target)
+    return _fn.style_loss_fused(feats, targets, [w for _, w in pairs], cs)
 
 
 def content_loss(input_features, target_features):

@@ -358,3 +358,15 @@ def image_to_halo(x: torch.Tensor, pad: int, pad_mode: int, c_pad: int, rows: in
           "image_to_halo")
     _count()
     return flat
+
+
+def gram_diff_sym(g: torch.Tensor, gt: torch.Tensor, scale: torch.Tensor, coef: float, dtype: torch.dtype) -> torch.Tensor:
+    """scale[0]*coef*((g-gt) + (g-gt)^T) per image, in `dtype`; gt is (C,C) or (B,C,C)."""
+    n, c, _ = g.shape
+    assert g.dtype == torch.float32 and gt.dtype == torch.float32 and g.is_contiguous() and gt.is_contiguous()
+    out = torch.empty((n, c, c), dtype=dtype, device=g.device)
+    dev, st = _ctx(g)
+    check(lib.fnst_gram_diff_sym(_ptr(g), _ptr(gt), n, c, gt.numel(), _ptr(scale), float(coef), _ptr(out), dt(dtype), dev, st),
+          "gram_diff_sym")
+    _count()
+    return out

@@ -206,6 +206,11 @@ int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t b_period, 
 int fnst_relu_mask(const void* g, const void* extra, const void* act, void* out, int64_t count, int act_dtype,
                    int g_dtype, int device, void* stream);
 
+/* Style-loss backward factor (losses/losses.py:15-44): S[n] = scale[0]*coef*((G[n]-Gt) + (G[n]-Gt)^T) in element type
+ * out_dtype; gt is broadcast with period gt_numel.  The feature gradient is then the per-image 1x1 gather-GEMM F[n] * S[n]. */
+int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c, int64_t gt_numel, const float* scale, float coef,
+                       void* s_out, int out_dtype, int device, void* stream);
+
 /* Gradient of fnst_tv: dimg = scale[0] * d/dimg sum(dh^2 + dw^2), NCHW fp32. */
 int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream);
 
