@@ -233,13 +233,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int i = 0; i < 27; ++i) s_rows[r * 33 + i] = v[i];
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int co = p.c_out;
-          for (int idx = et; idx < 64 * co; idx += 128) {
-            const int o = idx / 64, pp = idx - o * 64;          // pp: output pixel (8 rows x 8 cols) of this tile
-            const int oh = th * 8 + (pp >> 3), ow = tw * 8 + (pp & 7);
+          const int npix = p.h_step * TW;                       // output pixels of this tile: h_step rows x TW columns
+          for (int idx = et; idx < npix * co; idx += 128) {
+            const int o = idx / npix, pp = idx - o * npix;
+            const int oh = th * p.h_step + (pp >> p.tw_log2), ow = tw * TW + (pp & (TW - 1));
             if (oh < p.out_h && ow < p.out_w) {
               float acc = p.bias ? p.bias[o] : 0.f;
 #pragma unroll
-              for (int kh = 0; kh < 9; ++kh) acc += s_rows[(pp + 8 * kh) * 33 + kh * co + o];
+              for (int kh = 0; kh < 9; ++kh) acc += s_rows[(pp + TW * kh) * 33 + kh * co + o];
               reinterpret_cast<float*>(p.out)[(((size_t)n * co + o) * p.out_h + oh) * p.out_w + ow] = acc;
             }
           }
@@ -389,10 +390,11 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   memset(&p, 0, sizeof(p));
   p.out_n = d->out_n; p.out_h = d->out_h; p.out_w = d->out_w;
   // pixel tile TH x TW = 128: wide tiles for wide images, never wider than needed
-  const int tw_log2 = (rowsum || d->out_w <= 8) ? 3 : 4;
+  // ROWSUM9: tall 4 x 32 T tiles advance by 24 output rows (8-row halo below): 75 % of the loaded rows are new
+  const int tw_log2 = rowsum ? 2 : (d->out_w <= 8 ? 3 : 4);
   p.tw_log2 = tw_log2;
   const int TW = 1 << tw_log2, TH = TC_BLOCK_M >> tw_log2;
-  p.h_step = rowsum ? 8 : TH;                 // ROWSUM9: 16-row T tiles advance by 8 output rows (8-row halo below)
+  p.h_step = rowsum ? TH - 8 : TH;
   p.tiles_w = (d->out_w + TW - 1) / TW;
   p.tiles_h = (d->out_h + p.h_step - 1) / p.h_step;
   p.num_m_tiles = p.tiles_w * p.tiles_h * d->out_n;

@@ -111,8 +111,8 @@ class StyleTransferNet(nn.Module):
         key = (id(plan), tuple(x.shape), x.device.index)
         entry = graphs.get(key)
         if entry is None:
-            for k in [k for k in graphs if k[0] != id(plan)]:      # weights changed: drop stale captures
-                del graphs[k]
+            for k in [k for k in graphs if k[0] != id(plan)] if len(graphs) < 8 else list(graphs):
+                del graphs[k]                                      # weights changed (or too many shapes): drop captures
             static_x = x.detach().clone().float().contiguous()
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream(x.device))
@@ -140,7 +140,8 @@ class StyleTransferNet(nn.Module):
             if graphs.enabled() and not torch.cuda.is_current_stream_capturing():
                 # training step as two CUDA-graph replays (forward incl. weight re-pack, backward) per input shape
                 cache = self.__dict__.setdefault("_train_graphs", {})
-                key = (self.precision, tuple(x.shape), x.device.index, self.training)
+                # (the parameter addresses are part of the key: the captured graphs read the weights in place)
+                key = (self.precision, tuple(x.shape), x.device.index, self.training, params[0].data_ptr(), params[-1].data_ptr())
                 state = cache.get(key)
                 if state is None:
                     if len(cache) >= 4:

@@ -243,6 +243,8 @@ class StyleNetPlan:
         stats = lambda c: torch.empty((B, c, 2), dtype=torch.float32, device=dev)
         if H <= 4 or W <= 4:
             raise RuntimeError("StyleTransferNet needs H, W >= 5 (ReflectionPad2d(4))")
+        if tc:
+            ops.require_tensor_cores(dev)
         if self.split:
             if tape is not None:
                 raise RuntimeError("precision 'fp16x3' is a forward-only (inference) path; train with 'fp16' or 'fp32'")
@@ -450,6 +452,8 @@ class VGGPlan:
         B, _, H, W = x.shape
         if H < 8 or W < 8:
             raise RuntimeError("VGG19 feature stack needs H, W >= 8 (three 2x2 max-pools)")
+        if self.use_tc:
+            ops.require_tensor_cores(x.device)
         h = torch.empty((B, H, W, 64), dtype=self.dtype, device=x.device)
         if self.use_tc:
             # conv1_1 on tensor cores: 8-channel zero-halo image, 3 taps (kernel rows), 8-pixel windows

@@ -69,6 +69,19 @@ def _ctx(t: torch.Tensor) -> Tuple[int, C.c_void_p]:
     return dev, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+_TC_OK = {}
+
+
+def require_tensor_cores(device: torch.device) -> None:
+    """The tcgen05 / TMA kernels exist for sm_100a only: fail loudly on any other device (no fallback)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _TC_OK:
+        _TC_OK[idx] = bool(lib.fnst_device_supports_tc(idx))
+    if not _TC_OK[idx]:
+        raise RuntimeError(f"cuda:{idx} is not a compute-capability 10.x (Blackwell B200) device: the tcgen05/TMA kernels of "
+                           "libfnst cannot run on it; use precision='fp32' (CUDA-core path) or a B200")
+
+
 def _count(n: int = 1) -> None:
     global launch_count
     launch_count += n
