@@ -66,6 +66,19 @@ def test_pickle_and_cpu_guard(dropin):
         ll.total_variation_loss(torch.zeros(1, 3, 8, 8))
 
 
+def test_every_declared_symbol_is_exported_and_bound():
+    """include/fnst.h is the contract: every declared entry point must be exported by libfnst.so and bound in _lib.EXPORTS."""
+    import re
+    from fast_neural_style_transfer_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "fnst.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(fnst_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 25
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+
+
 def test_vgg_contract(dropin):
     _, mv, _ = dropin
     vgg = mv.VGG19()
