@@ -114,7 +114,11 @@ def _fill_desc(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, out_hw) -> Co
     d.a_n, d.a_h, d.a_w, d.a_c = n, ah, aw, ac
     d.ntaps, d.kc = len(spec.taps), spec.kc
     d.h0, d.w0 = spec.h0, spec.w0
+    if len(spec.taps) > _lib.MAX_TAPS:
+        raise RuntimeError(f"gather-GEMM with {len(spec.taps)} taps exceeds FNST_MAX_TAPS = {_lib.MAX_TAPS}")
     for i, (dh, dw, c0) in enumerate(spec.taps):
+        if not (-128 <= dh <= 127 and -128 <= dw <= 127 and 0 <= c0 <= 32767):      # int8 / int16 fields of fnst_conv_desc
+            raise RuntimeError(f"tap {i} = ({dh}, {dw}, {c0}) does not fit the descriptor (image too wide for the window view?)")
         d.tap_dh[i], d.tap_dw[i], d.tap_c0[i] = dh, dw, c0
     d.n_gemm = spec.n_gemm
     d.out_n, d.out_h, d.out_w = n, out_hw[0], out_hw[1]
