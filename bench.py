@@ -330,6 +330,19 @@ def main():
         barrier(world)
         ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, dev)
 
+        # ---- same, through the uint8 extension: uint8 HWC host buffers, pre/post-processing on the GPU
+        u8_host = (x_host.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().pin_memory()
+        u8_out = torch.empty((per_rank, y.shape[2], y.shape[3], 3), dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            u8_out.copy_(net.stylize_uint8(u8_host.to(dev, non_blocking=True)), non_blocking=True)
+        barrier(world)
+        e0.record()
+        for _ in range(args.steps):
+            u8_out.copy_(net.stylize_uint8(u8_host.to(dev, non_blocking=True)), non_blocking=True)
+        e1.record()
+        barrier(world)
+        ms_u8 = max_over_ranks(e0.elapsed_time(e1), world, dev)
+
     # ---- roofline of the dominant kernel: the 3x3 256->256 gather-GEMM (ten launches per forward) -----
     k_ms, flops, k_launches = time_dominant_kernel(net, per_rank, wl["h"], wl["w"], dev)
     step_share = timer.mean_ms() * 10 / (ms / args.steps) if timer.count() else (k_ms * 10) / (ms / args.steps)
@@ -357,6 +370,9 @@ def main():
             "roofline": roofline,
             "e2e": {"value": total_images * args.steps / (ms_e2e / 1e3), "unit": wl["unit"],
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+            "e2e_uint8": {"value": total_images * args.steps / (ms_u8 / 1e3), "unit": wl["unit"],
+                          "h2d_bytes_per_step": u8_host.numel(), "d2h_bytes_per_step": u8_out.numel(),
+                          "note": "extension beyond the reference API: StyleTransferNet.stylize_uint8 (uint8 HWC in/out)"},
             "gpu_launches": launches, "clocks": clocks}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, wl)

@@ -249,6 +249,33 @@ __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO
   }
 }
 
+// uint8 HWC images <-> NCHW fp32 (inference pre/post-processing on the device, inference.py:28-31,52-60):
+//   u8 -> f32:  x[n,c,h,w] = (u8[n,h,w,c] / 255 - mean[c]) / std[c]        (mean = 0, std = 1: plain ToTensor)
+//   f32 -> u8:  u8[n,h,w,c] = round(clamp(y[n,c,h,w] * std[c] + mean[c], 0, 1) * 255)
+__global__ void __launch_bounds__(256) u8_to_nchw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t pixels,
+                                                         int HW, float m0, float m1, float m2, float s0, float s1, float s2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, p = i - n * HW;
+    const uint8_t* px = in + i * 3;
+    float* o = out + n * 3 * (int64_t)HW + p;
+    o[0] = (px[0] * (1.f / 255.f) - m0) / s0;
+    o[HW] = (px[1] * (1.f / 255.f) - m1) / s1;
+    o[2 * (int64_t)HW] = (px[2] * (1.f / 255.f) - m2) / s2;
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int64_t pixels,
+                                                         int HW, float m0, float m1, float m2, float s0, float s1, float s2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, p = i - n * HW;
+    const float* y = in + n * 3 * (int64_t)HW + p;
+    uint8_t* px = out + i * 3;
+    px[0] = (uint8_t)__float2int_rn(fminf(fmaxf(y[0] * s0 + m0, 0.f), 1.f) * 255.f);
+    px[1] = (uint8_t)__float2int_rn(fminf(fmaxf(y[HW] * s1 + m1, 0.f), 1.f) * 255.f);
+    px[2] = (uint8_t)__float2int_rn(fminf(fmaxf(y[2 * (int64_t)HW] * s2 + m2, 0.f), 1.f) * 255.f);
+  }
+}
+
 static int grid_for(int64_t work_items, int threads = 256) {
   int64_t b = (work_items + threads - 1) / threads;
   const int64_t cap = 148 * 16;
@@ -373,4 +400,24 @@ extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w
     else image_to_halo_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch, split);
   }
   return launch_status("image_to_halo");
+}
+
+extern "C" int fnst_u8_to_nchw(const void* in, float* out, int n, int h, int w, const float* mean3, const float* std3,
+                               int device, void* stream) {
+  FNST_CHECK_ARG(in && out && mean3 && std3 && n > 0 && h > 0 && w > 0, "u8_to_nchw: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  const int64_t pixels = (int64_t)n * h * w;
+  u8_to_nchw_kernel<<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(in), out, pixels, h * w,
+                                                                         mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+  return launch_status("u8_to_nchw");
+}
+
+extern "C" int fnst_nchw_to_u8(const float* in, void* out, int n, int h, int w, const float* mean3, const float* std3,
+                               int device, void* stream) {
+  FNST_CHECK_ARG(in && out && mean3 && std3 && n > 0 && h > 0 && w > 0, "nchw_to_u8: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  const int64_t pixels = (int64_t)n * h * w;
+  nchw_to_u8_kernel<<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<uint8_t*>(out), pixels, h * w,
+                                                                         mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+  return launch_status("nchw_to_u8");
 }

@@ -131,6 +131,20 @@ class StyleTransferNet(nn.Module):
         ops.launch_count += n_launches           # kernels replayed from the captured graph
         return static_y.clone()
 
+    IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+    @torch.no_grad()
+    def stylize_uint8(self, img_u8: torch.Tensor, normalize_input: bool = False) -> torch.Tensor:
+        """Extension beyond the reference API: uint8 HWC in, uint8 HWC out, pre/post-processing on the GPU.
+        Equivalent to inference.py:44-60: ToTensor (optionally ImageNet-normalised, as the training monitor does),
+        forward, de-normalise, clamp to [0,1], x255 -- with 4x fewer PCIe bytes than float tensors."""
+        if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 4 or img_u8.shape[-1] != 3:
+            raise RuntimeError("stylize_uint8 expects a CUDA uint8 tensor of shape (n, h, w, 3)")
+        mean, std = (self.IMAGENET_MEAN, self.IMAGENET_STD) if normalize_input else ((0.0,) * 3, (1.0,) * 3)
+        x = ops.u8_to_nchw(img_u8.contiguous(), mean, std)
+        y = self.forward(x)
+        return ops.nchw_to_u8(y.contiguous(), self.IMAGENET_MEAN, self.IMAGENET_STD)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback")

@@ -387,3 +387,29 @@ def gram_diff_sym(g: torch.Tensor, gt: torch.Tensor, scale: torch.Tensor, coef: 
           "gram_diff_sym")
     _count()
     return out
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(t) for t in v])
+
+
+def u8_to_nchw(img_u8: torch.Tensor, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)) -> torch.Tensor:
+    """(n,h,w,3) uint8 -> (n,3,h,w) fp32: (u8/255 - mean)/std."""
+    n, h, w, c = img_u8.shape
+    assert c == 3 and img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    out = torch.empty((n, 3, h, w), dtype=torch.float32, device=img_u8.device)
+    dev, st = _ctx(img_u8)
+    check(lib.fnst_u8_to_nchw(_ptr(img_u8), _ptr(out), n, h, w, _f3(mean), _f3(std), dev, st), "u8_to_nchw")
+    _count()
+    return out
+
+
+def nchw_to_u8(y: torch.Tensor, mean, std) -> torch.Tensor:
+    """(n,3,h,w) fp32 -> (n,h,w,3) uint8: round(clamp(y*std + mean, 0, 1)*255)."""
+    n, c, h, w = y.shape
+    assert c == 3 and y.dtype == torch.float32 and y.is_contiguous()
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=y.device)
+    dev, st = _ctx(y)
+    check(lib.fnst_nchw_to_u8(_ptr(y), _ptr(out), n, h, w, _f3(mean), _f3(std), dev, st), "nchw_to_u8")
+    _count()
+    return out

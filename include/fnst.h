@@ -156,6 +156,11 @@ int fnst_tv(const float* img, int planes, int h, int w, double* acc, int device,
 int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w, int c, int dtype, int device, void* stream);
 int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int c_pad, int dtype, int device, void* stream);
 
+/* uint8 HWC images <-> NCHW fp32 on the device (inference.py:28-31 ToTensor, :52-60 de-normalise/clamp).
+ * mean3/std3 are HOST pointers to three floats.  u8->f32: (u8/255 - mean)/std;  f32->u8: round(clamp(y*std + mean, 0, 1)*255). */
+int fnst_u8_to_nchw(const void* in, float* out, int n, int h, int w, const float* mean3, const float* std3, int device, void* stream);
+int fnst_nchw_to_u8(const float* in, void* out, int n, int h, int w, const float* mean3, const float* std3, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backward operators (autograd of train.py:200 `total_loss.backward()` through the same modules).
  * Data gradients (dgrad) of every convolution are gather-GEMMs again (fnst_conv_tc / fnst_conv_simt

@@ -117,3 +117,19 @@ def test_cuda_graph_replay_tracks_inputs_and_weights(dropin):
         yc = net(xa.to(DEV))
         assert rel_l2(yc, O.stylenet_forward(p1, xa)) < 1e-4
         assert len(net._graphs) == 1          # the stale capture was dropped
+
+
+def test_stylize_uint8_matches_reference_postprocessing(dropin):
+    """uint8 in / uint8 out on the GPU == inference.py:44-60 (ToTensor, forward, de-normalise, clamp, x255)."""
+    mm, _, _ = dropin
+    p = O.make_net_params(seed=0)
+    net = mm.StyleTransferNet().to(DEV); net.load_state_dict(p); net.precision = "fp32"; net.eval()
+    g = torch.Generator().manual_seed(8)
+    img = torch.randint(0, 256, (2, 40, 48, 3), generator=g, dtype=torch.uint8)
+    out = net.stylize_uint8(img.to(DEV)).cpu()
+    x = img.permute(0, 3, 1, 2).float() / 255.0                            # transforms.ToTensor()
+    with torch.no_grad():
+        ref = O.to_pixels(O.stylenet_forward(p, x)).round().clamp(0, 255).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape and out.dtype == torch.uint8
+    diff = (out.float() - ref).abs()
+    assert float(diff.max()) <= 1.0 and float((diff > 0).float().mean()) < 0.01     # rounding ties only
