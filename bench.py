@@ -130,12 +130,13 @@ def time_dominant_kernel(net, per_rank, h, w, dev):
     cin = 512 if split else 256
     ins = [torch.randn((per_rank, h2 + 2, w2 + 2, cin), device=dev).to(dt) for _ in range(n_sets)]
     outs = [torch.empty((per_rank, h2, w2, 256), dtype=torch.float32 if split else dt, device=dev) for _ in range(n_sets)]
-    stats = [torch.empty((per_rank, 256, 2), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+    arena = ops.ZeroArena(n_sets * per_rank * 256 * 2, dev)      # as in the product path: statistics zeroed once per forward
+    stats = [arena.take(per_rank, 256, 2) for _ in range(n_sets)]
     taps = engine.taps_x3(engine.taps_kxk(3), 256) if split else engine.taps_kxk(3)
     spec = ConvSpec(taps, 256, plan.w["res0a"], 256, 256)
     def launch_all():
         for a, o, st in zip(ins, outs, stats):
-            ops.conv_gather(spec, a, tuple(a.shape), engine._nhwc_strides(a), o, (h2, w2), st, plan.use_tc)
+            ops.conv_gather(spec, a, tuple(a.shape), engine._nhwc_strides(a), o, (h2, w2), st, plan.use_tc, stats_zeroed=True)
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):

@@ -13,6 +13,7 @@ MAX_TAPS = 96
 F32, F16, BF16 = 0, 1, 2
 EPI_NHWC, EPI_D2S, EPI_NCHW_F32, EPI_ROWSUM9 = 0, 1, 2, 3
 PAD_NONE, PAD_REFLECT, PAD_ZERO = 0, 1, 2
+DESC_PREZEROED = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FNST_LIB", os.path.join(_HERE, "libfnst.so"))
@@ -45,6 +46,7 @@ class ConvDesc(C.Structure):
         ("mask_dtype", C.c_int32),
         ("b_image_rows", C.c_int32),
         ("g_stride_w", C.c_int64), ("g_stride_h", C.c_int64), ("g_stride_n", C.c_int64),
+        ("flags", C.c_int32),
     ]
 
 
@@ -52,6 +54,7 @@ EXPORTS = {
     # name: (restype, argtypes)
     "fnst_version": (C.c_int, []),
     "fnst_last_error": (C.c_char_p, []),
+    "fnst_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "fnst_device_supports_tc": (C.c_int, [C.c_int]),
     "fnst_conv_tc": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "fnst_conv_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
@@ -73,7 +76,7 @@ EXPORTS = {
     "fnst_wgrad_tc": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_void_p]),
     "fnst_conv_first_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
-    "fnst_inorm_bwd_reduce": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_inorm_bwd_reduce": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fnst_inorm_bwd_apply": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "fnst_maxpool2_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "fnst_sse_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -71,12 +71,12 @@ def _tc_ok(use_tc: bool, kc: int, n_gemm: int) -> bool:
     return use_tc and kc % 64 == 0 and (n_gemm == 16 or n_gemm % 32 == 0)
 
 
-def _wgrad(tc: bool, spec: ConvSpec, a, a_dims, g, out_hw, out=None) -> torch.Tensor:
+def _wgrad(tc: bool, spec: ConvSpec, a, a_dims, g, out_hw, out=None, out_zeroed=False) -> torch.Tensor:
     """Weight gradient of `spec`; tensor cores whenever the channel window is a multiple of 64."""
     use_tc = tc and spec.kc % 64 == 0
     if use_tc and a.dtype != g.dtype:
         a = ops.cast(a, g.dtype)         # kind::f16 MMAs need both operands in one 16-bit format
-    return ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, out=out)
+    return ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, out=out, out_zeroed=out_zeroed)
 
 
 # -------------------------------------------------------------------------------------------------------
@@ -96,6 +96,9 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     zero_names = [n for n in p if n.endswith(".bias") and ("conv" in n) and not n.startswith("final_conv")]
     zero_flat = torch.zeros(sum(p[n].numel() for n in zero_names), dtype=torch.float32, device=dev)
     zero_views = dict(zip(zero_names, torch.split(zero_flat, [p[n].numel() for n in zero_names])))
+    # reduction buffers of the 14 InstanceNorm backward passes ([B,C,2] sums + [2,C] d gamma / d beta each), zeroed once:
+    # no memset in front of the individual kernels, so programmatic dependent launch can chain them
+    arena = ops.ZeroArena((2 * B + 2) * engine.STATS_CHANNELS + 64 * 14, dev)
 
     def zeros_like_param(name):
         return zero_views[name]
@@ -175,7 +178,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 
     # ---- norm4 + up2 ------------------------------------------------------------------------------------
     g4, b4 = plan._affine("norm4")
-    gy, sums, dgb = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT)
+    gy, sums, dgb = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT, arena=arena)
     grads["norm4.weight"], grads["norm4.bias"] = _affine_grads(dgb)
     d_raw4 = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
     act3 = tape["act3"]
@@ -190,7 +193,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 
     # ---- norm3 + up1 ------------------------------------------------------------------------------------
     g3, b3 = plan._affine("norm3")
-    gy, sums, dgb = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True)
+    gy, sums, dgb = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True, arena=arena)
     grads["norm3.weight"], grads["norm3.bias"] = _affine_grads(dgb)
     d_raw3 = ops.inorm_bwd_apply(gy, tape["raw3"], tape["st3"], sums, g3, out_s2d=True)     # (B,H2,W2,256)
     trunk = tape["trunk"]
@@ -213,7 +216,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     res_fwd = plan.w["res_all"]                                              # (10, 256, 9*256) forward operands
     res_dg = torch.empty((10, 256, 9 * 256), dtype=gdt, device=dev)
     res_dg.view(10, 256, 9, 256).copy_(res_fwd.view(10, 256, 9, 256).permute(0, 3, 2, 1))
-    res_db = torch.empty((10, 256, 9 * 256), dtype=torch.float32, device=dev)
+    res_db = torch.zeros((10, 256, 9 * 256), dtype=torch.float32, device=dev)    # split-K targets, zeroed once
 
     def res_dgrad(g, idx):
         out = torch.empty(pdims, dtype=gdt, device=dev)
@@ -227,22 +230,22 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         # in2 (no ReLU); the total output gradient also feeds the skip connection
         ga, ba = plan._affine(pre + ".in2")
         g_out, sums, dgb = ops.inorm_bwd_reduce(gsrc, extra, blk["raw_b"], blk["st_b"], ga, ba, None, gdt, False,
-                                           1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE)
+                                           1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE, arena=arena)
         grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(dgb)
         d_raw_b = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
         mid = blk["mid"]
         with on_side(mid, d_raw_b):
-            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2), out=res_db[2 * i + 1])
+            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2), out=res_db[2 * i + 1], out_zeroed=True)
         grads[pre + ".conv2.conv.bias"] = zeros_like_param(pre + ".conv2.conv.bias")
         d_mid = res_dgrad(d_raw_b, 2 * i + 1)
         # in1 + ReLU + Dropout2d
         ga, ba = plan._affine(pre + ".in1")
-        gy, sums, dgb = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT)
+        gy, sums, dgb = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT, arena=arena)
         grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(dgb)
         d_raw_a = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
         cur = trunk[i]
         with on_side(cur, d_raw_a):
-            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2), out=res_db[2 * i])
+            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2), out=res_db[2 * i], out_zeroed=True)
         grads[pre + ".conv1.conv.bias"] = zeros_like_param(pre + ".conv1.conv.bias")
         gsrc = res_dgrad(d_raw_a, 2 * i)
         extra = g_out
@@ -255,7 +258,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 
     # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
     g2, b2 = plan._affine("norm2")
-    gy, sums, dgb = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT)
+    gy, sums, dgb = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT, arena=arena)
     grads["norm2.weight"], grads["norm2.bias"] = _affine_grads(dgb)
     d_raw2 = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
     buf2 = tape["buf2"]
@@ -273,7 +276,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     # ---- norm1 + conv1 -----------------------------------------------------------------------------------------
     g1, b1 = plan._affine("norm1")
     raw1 = tape["raw1"]
-    gy, sums, dgb = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True)
+    gy, sums, dgb = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True, arena=arena)
     grads["norm1.weight"], grads["norm1.bias"] = _affine_grads(dgb)
     d_raw1 = ops.inorm_bwd_apply(gy, raw1, tape["st1"], sums, g1)
     if tc:

@@ -1,5 +1,7 @@
 // Library-level entry points: version, thread-local error message.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace fnst {
 static thread_local char g_err[512] = "";
@@ -9,7 +11,29 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning v;
+    if (const char* e = getenv("FNST_CONV_BLOCK_N")) v.conv_block_n = atoi(e);
+    if (const char* e = getenv("FNST_WGRAD_WAVES_X2")) v.wgrad_waves_x2 = atoi(e);
+    if (const char* e = getenv("FNST_WGRAD_BN")) v.wgrad_bn = atoi(e);
+    if (const char* e = getenv("FNST_PDL")) v.pdl = atoi(e);
+    return v;
+  }();
+  return t;
+}
+bool pdl_enabled() { return tuning().pdl != 0; }
 }  // namespace fnst
 
-extern "C" int fnst_version(void) { return 100; }
+extern "C" int fnst_version(void) { return 101; }
+
+extern "C" int fnst_set_tuning(const char* name, int value) {
+  fnst::Tuning& t = fnst::tuning();
+  if (!strcmp(name, "conv_block_n")) t.conv_block_n = value;
+  else if (!strcmp(name, "wgrad_waves_x2")) t.wgrad_waves_x2 = value;
+  else if (!strcmp(name, "wgrad_bn")) t.wgrad_bn = value;
+  else if (!strcmp(name, "pdl")) t.pdl = value;
+  else { fnst::set_error("fnst_set_tuning: unknown knob '%s'", name); return -1; }
+  return 0;
+}
 extern "C" const char* fnst_last_error(void) { return fnst::g_err; }

@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(256) inorm_bwd_reduce_kernel(const TG* __restr
                                                                const float* __restrict__ drop, TG* __restrict__ gy,
                                                                float* __restrict__ sums, float* __restrict__ dgb, HaloLayout L,
                                                                int relu, float eps) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_acc[];   // [2][C]
   const int n = blockIdx.y, h = blockIdx.x;
   const int C = L.C, CG = C >> 3, PL = 256 / CG;
@@ -259,6 +261,8 @@ __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restri
                                                               const float* __restrict__ stats, const float* __restrict__ sums,
                                                               const float* __restrict__ gamma, TG* __restrict__ draw,
                                                               int H, int W, int C, float eps, int out_s2d) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y, h = blockIdx.x;
   const int CG = C >> 3, PL = 256 / CG;
   const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, c0 = cg * 8;
@@ -291,6 +295,8 @@ template <typename TA, typename TG>
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const TA* __restrict__ in, const TG* __restrict__ gout,
                                                            const TG* __restrict__ extra, TG* __restrict__ gin,
                                                            int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H >> 1, Wo = W >> 1, CG = C >> 3;
   // one thread per (2x2 window incl. the odd tail handled below, 8 channels)
   const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
@@ -345,6 +351,8 @@ template <typename TA, typename TB, typename TG>
 __global__ void __launch_bounds__(256) sse_bwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t count,
                                                       int64_t period, const float* __restrict__ scale, TG* __restrict__ da,
                                                       int relu_mask) {
+  pdl_trigger();
+  pdl_wait();
   const float s = 2.f * scale[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     const float av = to_f32<TA>(a[i]);
@@ -357,6 +365,8 @@ __global__ void __launch_bounds__(256) sse_bwd_kernel(const TA* __restrict__ a, 
 template <typename TA, typename TG>
 __global__ void __launch_bounds__(256) relu_mask_kernel(const TG* __restrict__ g, const TG* __restrict__ extra,
                                                         const TA* __restrict__ act, TG* __restrict__ out, int64_t count8) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count8; i += (int64_t)gridDim.x * blockDim.x) {
     float v[8], a[8];
     load8<TG>(g + i * 8, v);
@@ -379,6 +389,8 @@ template <typename TG>
 __global__ void __launch_bounds__(256) gram_diff_sym_kernel(const float* __restrict__ G, const float* __restrict__ Gt, int64_t period,
                                                             int C, int64_t total, const float* __restrict__ scale, float coef,
                                                             TG* __restrict__ S) {
+  pdl_trigger();
+  pdl_wait();
   const float k = scale[0] * coef;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = i / ((int64_t)C * C), r = i - n * (int64_t)C * C;
@@ -391,6 +403,8 @@ __global__ void __launch_bounds__(256) gram_diff_sym_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) tv_bwd_kernel(const float* __restrict__ img, int planes, int H, int W,
                                                      const float* __restrict__ scale, float* __restrict__ dimg) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)planes * H * W;
   const float s = 2.f * scale[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -406,6 +420,8 @@ __global__ void __launch_bounds__(256) tv_bwd_kernel(const float* __restrict__ i
 }
 
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, int N, int C, int HW, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   // grid = (chunks, C); each block reduces a chunk of one channel over all images
   const int c = blockIdx.y;
   float s = 0.f;
@@ -440,7 +456,7 @@ extern "C" int fnst_wgrad_simt(const fnst_conv_desc* d, int g_dtype, int device,
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t ktot = (size_t)d->ntaps * d->kc;
-  FNST_CUDA(cudaMemsetAsync(d->out, 0, sizeof(float) * ktot * d->n_gemm, st));
+  if (!(d->flags & FNST_DESC_PREZEROED)) FNST_CUDA(cudaMemsetAsync(d->out, 0, sizeof(float) * ktot * d->n_gemm, st));
   const int slabs = (d->out_h + WG_ROWS - 1) / WG_ROWS;
   dim3 grid(d->ntaps * ((d->kc + 63) / 64), (d->n_gemm + 63) / 64, d->out_n * slabs);
   FNST_CHECK_ARG(grid.z <= 65535, "wgrad: too many pixel slabs (%u)", grid.z);
@@ -473,18 +489,20 @@ extern "C" int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const 
 extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
                                      const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
                                      float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
-                                     int pad, int pad_mode, int s2d, int device, void* stream) {
+                                     int pad, int pad_mode, int s2d, int prezeroed, int device, void* stream) {
   FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && gy && sums, "inorm_bwd_reduce: null pointer");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_reduce: unsupported channel count %d", c);
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
-  FNST_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, st));
-  if (dgb) FNST_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * 2 * (size_t)c, st));
+  if (!prezeroed) {
+    FNST_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, st));
+    if (dgb) FNST_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * 2 * (size_t)c, st));
+  }
   HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d};
   dim3 grid(h, n);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
-      inorm_bwd_reduce_kernel<TA, TG><<<grid, 256, sizeof(float) * 2 * c, st>>>(
+      launch_pdl(inorm_bwd_reduce_kernel<TA, TG>, dim3(grid), dim3(256), sizeof(float) * 2 * c, st, 
           reinterpret_cast<const TG*>(gsrc), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(raw), stats, gamma,
           beta, drop, reinterpret_cast<TG*>(gy), sums, dgb, L, relu, eps);
     });
@@ -502,7 +520,7 @@ extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float
   dim3 grid(h, n);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
-      inorm_bwd_apply_kernel<TA, TG><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      launch_pdl(inorm_bwd_apply_kernel<TA, TG>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
           reinterpret_cast<const TG*>(gy), reinterpret_cast<const TA*>(raw), stats, sums, gamma, reinterpret_cast<TG*>(draw),
           h, w, c, eps, out_s2d);
     });
@@ -517,7 +535,7 @@ extern "C" int fnst_maxpool2_bwd(const void* in, const void* gout, const void* e
   const int64_t items = (int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
-      maxpool2_bwd_kernel<TA, TG><<<grid_cap(items), 256, 0, (cudaStream_t)stream>>>(
+      launch_pdl(maxpool2_bwd_kernel<TA, TG>, dim3(grid_cap(items)), dim3(256), 0, (cudaStream_t)stream, 
           reinterpret_cast<const TA*>(in), reinterpret_cast<const TG*>(gout), reinterpret_cast<const TG*>(extra),
           reinterpret_cast<TG*>(gin), n, h, w, c);
     });
@@ -532,7 +550,7 @@ extern "C" int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t
   FNST_DISPATCH_DTYPE(dtype_a, TA, {
     FNST_DISPATCH_DTYPE(dtype_b, TB, {
       FNST_DISPATCH_DTYPE(g_dtype, TG, {
-        sse_bwd_kernel<TA, TB, TG><<<grid_cap(count / 4), 256, 0, (cudaStream_t)stream>>>(
+        launch_pdl(sse_bwd_kernel<TA, TB, TG>, dim3(grid_cap(count / 4)), dim3(256), 0, (cudaStream_t)stream, 
             reinterpret_cast<const TA*>(a), reinterpret_cast<const TB*>(b), count, b_period, scale, reinterpret_cast<TG*>(da), relu_mask);
       });
     });
@@ -546,7 +564,7 @@ extern "C" int fnst_relu_mask(const void* g, const void* extra, const void* act,
   FNST_CUDA(cudaSetDevice(device));
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
-      relu_mask_kernel<TA, TG><<<grid_cap(count / 8), 256, 0, (cudaStream_t)stream>>>(
+      launch_pdl(relu_mask_kernel<TA, TG>, dim3(grid_cap(count / 8)), dim3(256), 0, (cudaStream_t)stream, 
           reinterpret_cast<const TG*>(g), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(act),
           reinterpret_cast<TG*>(out), count / 8);
     });
@@ -560,7 +578,7 @@ extern "C" int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c,
   FNST_CUDA(cudaSetDevice(device));
   const int64_t total = (int64_t)n * c * c;
   FNST_DISPATCH_DTYPE(out_dtype, TG, {
-    gram_diff_sym_kernel<TG><<<grid_cap(total), 256, 0, (cudaStream_t)stream>>>(g, gt, gt_numel, c, total, scale, coef,
+    launch_pdl(gram_diff_sym_kernel<TG>, dim3(grid_cap(total)), dim3(256), 0, (cudaStream_t)stream, g, gt, gt_numel, c, total, scale, coef,
                                                                               reinterpret_cast<TG*>(s_out));
   });
   return launch_status("gram_diff_sym");
@@ -569,7 +587,7 @@ extern "C" int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c,
 extern "C" int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream) {
   FNST_CHECK_ARG(img && scale && dimg && planes > 0 && h > 0 && w > 0, "tv_bwd: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
-  tv_bwd_kernel<<<grid_cap((int64_t)planes * h * w / 4), 256, 0, (cudaStream_t)stream>>>(img, planes, h, w, scale, dimg);
+  launch_pdl(tv_bwd_kernel, dim3(grid_cap((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w, scale, dimg);
   return launch_status("tv_bwd");
 }
 
@@ -581,6 +599,6 @@ extern "C" int fnst_channel_sum(const float* x, int n, int c, int hw, float* out
   int chunks = (int)(((int64_t)n * hw + 256 * 16 - 1) / (256 * 16));
   if (chunks > 512) chunks = 512;
   dim3 grid(chunks, c);
-  channel_sum_kernel<<<grid, 256, 0, st>>>(x, n, c, hw, out);
+  launch_pdl(channel_sum_kernel, dim3(grid), dim3(256), 0, st, x, n, c, hw, out);
   return launch_status("channel_sum");
 }

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 
 #include "../../include/fnst.h"
 
@@ -38,6 +39,64 @@ inline int launch_status(const char* what) {
     return (int)e;
   }
   return 0;
+}
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// Every kernel of the tensor-core path starts with pdl_trigger() (lets the next kernel on the stream be
+// scheduled as soon as all CTAs of this grid are resident) and calls pdl_wait() before its first access to
+// global memory (blocks until the preceding grid has completed and its writes are visible).  The set-up in
+// between -- barrier init, TMEM allocation, tensor-map prefetch, index math -- overlaps the tail of the
+// predecessor.  Under stream capture the attribute becomes a programmatic edge of the CUDA graph.  A kernel
+// launched through launch_pdl MUST execute pdl_wait() in every CTA, otherwise ordering is not transitive.
+// FNST_PDL=0 disables the launch attribute (both device calls are then no-ops).
+bool pdl_enabled();
+
+// Tuning knobs (defaults from measurement; fnst_set_tuning / FNST_* environment variables override them).
+struct Tuning {
+  int conv_block_n = 0;        // 0 = heuristic; else force the column tile of conv_tc (64/128/256)
+  int wgrad_waves_x2 = 2;      // wgrad_tc split-K target: tasks <= waves_x2/2 * SM count (one wave measured best: fewer L2 atomics)
+  int wgrad_bn = 0;            // 0 = widest column block that divides kc; else force 64/128/256
+  int pdl = 1;
+};
+Tuning& tuning();
+
+// Where griddepcontrol.launch_dependents is issued -- measured on B200 (profiles/r01_pdl_modes.md): an explicit early
+// trigger makes the dependent grid resident while its predecessor still runs, and those CTAs parked in
+// griddepcontrol.wait slow a small running grid down (batch-1 inference: -7 % with a trigger at kernel entry or after
+// the wait, -8 % with a trigger after the MMA main loop), while the default below -- no explicit trigger, i.e. the
+// implicit one at CTA exit; the dependent still skips the full launch latency and overlaps its set-up with the
+// predecessor's memory flush -- is +4 % at batch 1 and neutral elsewhere.  Modes 0 (entry), 1 (after the wait) and
+// 3 (after the MMA main loop of the tensor-core kernels) are kept for the A/B experiment.
+#ifndef FNST_PDL_MODE
+#define FNST_PDL_MODE 2
+#endif
+__device__ __forceinline__ void pdl_trigger_tail() {
+#if FNST_PDL_MODE == 3
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#if FNST_PDL_MODE == 0
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if FNST_PDL_MODE == 1
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface through launch_status()
 }
 
 inline size_t dtype_size(int dt) { return dt == FNST_F32 ? 4 : 2; }

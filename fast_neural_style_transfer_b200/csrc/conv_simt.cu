@@ -161,7 +161,7 @@ extern "C" int fnst_conv_simt(const fnst_conv_desc* d, int device, void* stream)
   FNST_CHECK_ARG(d->epilogue != FNST_EPI_ROWSUM9, "conv_simt: the ROWSUM9 epilogue exists on the tensor-core kernel only");
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->stats) FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
+  if (d->stats && !(d->flags & FNST_DESC_PREZEROED)) FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
   dim3 grid(((d->out_w + 7) / 8) * ((d->out_h + 7) / 8) * d->out_n, (d->n_gemm + SB_N - 1) / SB_N);
   const int odt = d->epilogue == FNST_EPI_NCHW_F32 ? FNST_F32 : d->out_dtype;
   FNST_DISPATCH_DTYPE(d->dtype, T, {

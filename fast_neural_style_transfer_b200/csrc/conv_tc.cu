@@ -121,6 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -134,6 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // set-up above overlapped the predecessor's tail; global memory is touched only from here on
 
   const int TW = 1 << p.tw_log2, TH = TC_BLOCK_M >> p.tw_log2;
 
@@ -188,6 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         umma_commit(&tmem_full[as]);
       }
+      pdl_trigger_tail();      // all MMAs of this CTA are issued: let the next kernel launch under the epilogue
     }
     __syncwarp();
   } else {
@@ -344,7 +347,7 @@ static int launch_conv_tc(const CUtensorMap& ma, const CUtensorMap& mb, const Co
   auto kern = conv_tc_kernel<BLOCK_N>;
   FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  launch_pdl(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, p);
   return launch_status("conv_tc");
 }
 
@@ -411,7 +414,7 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   else if ((int64_t)p.num_m_tiles * (d->n_gemm / 128) >= fill) block_n = 128;
   else block_n = 64;
   {
-    static const int force_n = [] { const char* e = getenv("FNST_CONV_BLOCK_N"); return e ? atoi(e) : 0; }();
+    const int force_n = tuning().conv_block_n;
     if (force_n && d->n_gemm % force_n == 0 && d->n_gemm >= 64) block_n = force_n;     // tuning override
   }
   FNST_CHECK_ARG(d->n_gemm % block_n == 0 || d->n_gemm < block_n, "conv_tc: n_gemm %d not tileable", d->n_gemm);
@@ -445,7 +448,8 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
     const uint32_t box[2] = {TC_BLOCK_K, (uint32_t)block_n};
     if (int r = encode_tensor_map_2b(&mb, d->b, 2, dims, str, box)) return r;
   }
-  if (d->stats) FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
+  if (d->stats && !(d->flags & FNST_DESC_PREZEROED))
+    FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
   switch (block_n) {
     case 16: return launch_conv_tc<16>(ma, mb, p, num_sms, st);
     case 32: return launch_conv_tc<32>(ma, mb, p, num_sms, st);

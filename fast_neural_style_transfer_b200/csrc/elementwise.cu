@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const TI* __restrict__
                                                           const float* __restrict__ drop, const T* __restrict__ res, int res_pad,
                                                           T* __restrict__ out, int H, int W, int C, int relu, float eps,
                                                           int pad, int pad_mode, int s2d, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_ab[];          // [2][C]: per-channel scale a and shift b of this image (keeps registers low)
   const int n = blockIdx.y;
   {
@@ -124,6 +126,8 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const TI* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                        int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H >> 1, Wo = W >> 1, CG = C >> 3;
   const size_t total = (size_t)N * Ho * Wo * CG;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -155,6 +159,8 @@ __device__ __forceinline__ void block_accumulate(float v, double* acc) {
 template <typename TA, typename TB>
 __global__ void __launch_bounds__(256) sse_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t count,
                                                   int64_t period, double* acc) {
+  pdl_trigger();
+  pdl_wait();
   float s = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     const float d = to_f32<TA>(a[i]) - to_f32<TB>(b[i % period]);
@@ -164,6 +170,8 @@ __global__ void __launch_bounds__(256) sse_kernel(const TA* __restrict__ a, cons
 }
 
 __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ img, int planes, int H, int W, double* acc) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)planes * H * W;
   float s = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -178,6 +186,8 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ img, 
 // [HW][C] (T) <-> [C][HW] (fp32) per image, 32x32 smem tiles.
 template <typename T, bool TO_NCHW>
 __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__ in_, void* __restrict__ out_, int HW, int C, int CP) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -214,6 +224,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
 template <typename T, int CP>
 __global__ void __launch_bounds__(256) image_to_halo_kernel(const float* __restrict__ x, T* __restrict__ out, int N, int H, int W,
                                                             int pad, int reflect, int rows, int pitch, int split) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)N * rows * pitch;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int wp = i % pitch; int64_t r = i / pitch;
@@ -242,6 +254,8 @@ __global__ void __launch_bounds__(256) image_to_halo_kernel(const float* __restr
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t count8) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count8; i += (int64_t)gridDim.x * blockDim.x) {
     float v[8];
     load8<TI>(in + i * 8, v);
@@ -254,6 +268,8 @@ __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO
 //   f32 -> u8:  u8[n,h,w,c] = round(clamp(y[n,c,h,w] * std[c] + mean[c], 0, 1) * 255)
 __global__ void __launch_bounds__(256) u8_to_nchw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t pixels,
                                                          int HW, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = i / HW, p = i - n * HW;
     const uint8_t* px = in + i * 3;
@@ -266,6 +282,8 @@ __global__ void __launch_bounds__(256) u8_to_nchw_kernel(const uint8_t* __restri
 
 __global__ void __launch_bounds__(256) nchw_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int64_t pixels,
                                                          int HW, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = i / HW, p = i - n * HW;
     const float* y = in + n * 3 * (int64_t)HW + p;
@@ -307,14 +325,14 @@ extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float
   while (rows_per_block < 4 && (int64_t)n * ((hp + 2 * rows_per_block - 1) / (2 * rows_per_block)) >= 148 * 16) rows_per_block *= 2;
   dim3 grid((hp + rows_per_block - 1) / rows_per_block, n);
   if (split) {
-    inorm_apply_kernel<float, __half, 2, true><<<grid, 256, sizeof(float) * 2 * c, (cudaStream_t)stream>>>(
+    launch_pdl(inorm_apply_kernel<float, __half, 2, true>, dim3(grid), dim3(256), sizeof(float) * 2 * c, (cudaStream_t)stream, 
         reinterpret_cast<const float*>(raw), stats, gamma, beta, drop, reinterpret_cast<const __half*>(res), res_pad,
         reinterpret_cast<__half*>(out), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
     return launch_status("inorm_apply");
   }
   FNST_DISPATCH_DTYPE(dtype, T, {
     auto kern = inorm_apply_kernel<T, T, 2, false>;   // 2 pixels (x raw + residual) in flight per thread: measured best, 77-96 % of copy peak
-    kern<<<grid, 256, sizeof(float) * 2 * c, (cudaStream_t)stream>>>(
+    launch_pdl(kern, dim3(grid), dim3(256), sizeof(float) * 2 * c, (cudaStream_t)stream,
         reinterpret_cast<const T*>(raw), stats, gamma, beta, drop, reinterpret_cast<const T*>(res), res_pad,
         reinterpret_cast<T*>(out), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
   });
@@ -327,7 +345,7 @@ extern "C" int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int
   FNST_CUDA(cudaSetDevice(device));
   const int64_t items = (int64_t)n * (h / 2) * (w / 2) * (c / 8);
   FNST_DISPATCH_DTYPE(dtype, T, {
-    maxpool2_kernel<T><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const T*>(in),
+    launch_pdl(maxpool2_kernel<T>, dim3(grid_for(items)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const T*>(in),
                                                                         reinterpret_cast<T*>(out), n, h, w, c);
   });
   return launch_status("maxpool2");
@@ -339,7 +357,7 @@ extern "C" int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_p
   FNST_CUDA(cudaSetDevice(device));
   FNST_DISPATCH_DTYPE(dtype_a, TA, {
     FNST_DISPATCH_DTYPE(dtype_b, TB, {
-      sse_kernel<TA, TB><<<grid_for(count / 4), 256, 0, (cudaStream_t)stream>>>(
+      launch_pdl(sse_kernel<TA, TB>, dim3(grid_for(count / 4)), dim3(256), 0, (cudaStream_t)stream, 
           reinterpret_cast<const TA*>(a), reinterpret_cast<const TB*>(b), count, b_period, acc);
     });
   });
@@ -349,7 +367,7 @@ extern "C" int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_p
 extern "C" int fnst_tv(const float* img, int planes, int h, int w, double* acc, int device, void* stream) {
   FNST_CHECK_ARG(img && acc && planes > 0 && h > 0 && w > 0, "tv: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
-  tv_kernel<<<grid_for((int64_t)planes * h * w / 4), 256, 0, (cudaStream_t)stream>>>(img, planes, h, w, acc);
+  launch_pdl(tv_kernel, dim3(grid_for((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w, acc);
   return launch_status("tv");
 }
 
@@ -357,7 +375,7 @@ extern "C" int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w
   FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0, "nhwc_to_nchw: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
   dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
-  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c, c); });
+  FNST_DISPATCH_DTYPE(dtype, T, { launch_pdl(transpose_kernel<T, true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, out, h * w, c, c); });
   return launch_status("nhwc_to_nchw");
 }
 
@@ -365,7 +383,7 @@ extern "C" int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w
   FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0 && c_pad >= c, "nchw_to_nhwc: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
   dim3 grid((h * w + 31) / 32, (c_pad + 31) / 32, n);
-  FNST_DISPATCH_DTYPE(dtype, T, { transpose_kernel<T, false><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, h * w, c, c_pad); });
+  FNST_DISPATCH_DTYPE(dtype, T, { launch_pdl(transpose_kernel<T, false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, out, h * w, c, c_pad); });
   return launch_status("nchw_to_nhwc");
 }
 
@@ -374,7 +392,7 @@ extern "C" int fnst_cast(const void* in, void* out, int64_t count, int in_dtype,
   FNST_CUDA(cudaSetDevice(device));
   FNST_DISPATCH_DTYPE(in_dtype, TI, {
     FNST_DISPATCH_DTYPE(out_dtype, TO, {
-      cast_kernel<TI, TO><<<grid_for(count / 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const TI*>(in),
+      launch_pdl(cast_kernel<TI, TO>, dim3(grid_for(count / 8)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const TI*>(in),
                                                                                   reinterpret_cast<TO*>(out), count / 8);
     });
   });
@@ -393,11 +411,11 @@ extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w
   const int reflect = pad_mode == FNST_PAD_REFLECT;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FNST_F16) {
-    if (c_pad == 4) image_to_halo_kernel<__half, 4><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch, split);
-    else image_to_halo_kernel<__half, 8><<<grid, 256, 0, st>>>(x, (__half*)out, n, h, w, pad, reflect, rows, pitch, split);
+    if (c_pad == 4) launch_pdl(image_to_halo_kernel<__half, 4>, dim3(grid), dim3(256), 0, st, x, (__half*)out, n, h, w, pad, reflect, rows, pitch, split);
+    else launch_pdl(image_to_halo_kernel<__half, 8>, dim3(grid), dim3(256), 0, st, x, (__half*)out, n, h, w, pad, reflect, rows, pitch, split);
   } else {
-    if (c_pad == 4) image_to_halo_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch, split);
-    else image_to_halo_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch, split);
+    if (c_pad == 4) launch_pdl(image_to_halo_kernel<__nv_bfloat16, 4>, dim3(grid), dim3(256), 0, st, x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch, split);
+    else launch_pdl(image_to_halo_kernel<__nv_bfloat16, 8>, dim3(grid), dim3(256), 0, st, x, (__nv_bfloat16*)out, n, h, w, pad, reflect, rows, pitch, split);
   }
   return launch_status("image_to_halo");
 }
@@ -407,7 +425,7 @@ extern "C" int fnst_u8_to_nchw(const void* in, float* out, int n, int h, int w, 
   FNST_CHECK_ARG(in && out && mean3 && std3 && n > 0 && h > 0 && w > 0, "u8_to_nchw: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
   const int64_t pixels = (int64_t)n * h * w;
-  u8_to_nchw_kernel<<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(in), out, pixels, h * w,
+  launch_pdl(u8_to_nchw_kernel, dim3(grid_for(pixels)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint8_t*>(in), out, pixels, h * w,
                                                                          mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
   return launch_status("u8_to_nchw");
 }
@@ -417,7 +435,7 @@ extern "C" int fnst_nchw_to_u8(const float* in, void* out, int n, int h, int w, 
   FNST_CHECK_ARG(in && out && mean3 && std3 && n > 0 && h > 0 && w > 0, "nchw_to_u8: bad arguments");
   FNST_CUDA(cudaSetDevice(device));
   const int64_t pixels = (int64_t)n * h * w;
-  nchw_to_u8_kernel<<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<uint8_t*>(out), pixels, h * w,
+  launch_pdl(nchw_to_u8_kernel, dim3(grid_for(pixels)), dim3(256), 0, (cudaStream_t)stream, in, reinterpret_cast<uint8_t*>(out), pixels, h * w,
                                                                          mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
   return launch_status("nchw_to_u8");
 }

@@ -66,6 +66,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   // task decode: tap fastest (neighbouring CTAs share the same G tiles in L2), then column block, row block, split
   int task = blockIdx.x;
@@ -96,6 +97,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const int TW = 1 << p.tw_log2, TH = WT_KPIX >> p.tw_log2;
 
   if (warp == 0) {
@@ -140,6 +142,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full);
+      pdl_trigger_tail();
     }
     __syncwarp();
   } else if (nkb > 0) {
@@ -175,7 +178,7 @@ template <int BN>
 static int launch_wgrad_tc(const CUtensorMap& mg, const CUtensorMap& ma, const WgradTcParams& p, int tasks, cudaStream_t st) {
   auto kern = wgrad_tc_kernel<BN>;
   FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WtCfg<BN>::SMEM_BYTES));
-  kern<<<tasks, WT_THREADS, WtCfg<BN>::SMEM_BYTES, st>>>(mg, ma, p);
+  launch_pdl(kern, dim3(tasks), dim3(WT_THREADS), WtCfg<BN>::SMEM_BYTES, st, mg, ma, p);
   return launch_status("wgrad_tc");
 }
 
@@ -198,15 +201,16 @@ static int run_pixel_gemm(const fnst_conv_desc* d, const void* g, int g_dtype, f
   p.tiles_h = (d->out_h + TH - 1) / TH;
   p.kblocks_per_image = p.tiles_w * p.tiles_h;
   p.kblocks_total = p.kblocks_per_image * d->out_n;
-  const int bn = d->kc % 256 == 0 ? 256 : (d->kc % 128 == 0 ? 128 : 64);
+  int bn = d->kc % 256 == 0 ? 256 : (d->kc % 128 == 0 ? 128 : 64);
+  if (const int f = tuning().wgrad_bn) { if (f <= bn && d->kc % f == 0) bn = f; }
   p.jblocks = (d->n_gemm + 127) / 128;
   p.cblocks = d->kc / bn;
   p.ntaps = d->ntaps;
   p.per_image = per_image;
   const int base_tasks = p.ntaps * p.cblocks * p.jblocks * (per_image ? d->out_n : 1);
   const int kb_avail = per_image ? p.kblocks_per_image : p.kblocks_total;
-  static const int waves_x2 = [] { const char* e = getenv("FNST_WGRAD_WAVES_X2"); return e ? atoi(e) : 4; }();
-  int splits = (waves_x2 * sms / 2 + base_tasks - 1) / base_tasks;   // aim for ~waves_x2/2 tasks per SM
+  const int waves_x2 = tuning().wgrad_waves_x2;
+  int splits = (waves_x2 * sms / 2) / base_tasks;                 // at most waves_x2/2 full waves of tasks (no ragged extra wave)
   if (splits > kb_avail / 4) splits = kb_avail / 4;               // keep >= 4 k-blocks per task
   if (splits < 1) splits = 1;
   p.splits = splits;
@@ -271,6 +275,6 @@ extern "C" int fnst_wgrad_tc(const fnst_conv_desc* d, int g_dtype, int device, v
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t ktot = (size_t)d->ntaps * d->kc;
-  FNST_CUDA(cudaMemsetAsync(d->out, 0, sizeof(float) * ktot * d->n_gemm, st));
+  if (!(d->flags & FNST_DESC_PREZEROED)) FNST_CUDA(cudaMemsetAsync(d->out, 0, sizeof(float) * ktot * d->n_gemm, st));
   return run_pixel_gemm(d, d->b, g_dtype, reinterpret_cast<float*>(d->out), (int64_t)ktot, 0, 0, device, st);
 }

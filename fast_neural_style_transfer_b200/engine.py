@@ -164,6 +164,10 @@ def pack_final_plain(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # StyleTransferNet
 # ---------------------------------------------------------------------------------------------
 
+# channels of the 14 InstanceNorm layers (models/model.py:29,32,41,44,81,83): norm1, norm2, 5 x (in1, in2), norm3, norm4
+STATS_CHANNELS = 64 + 256 + 10 * 256 + 64 + 32
+
+
 def _half_up(v: int) -> int:
     return (v + 1) // 2
 
@@ -240,7 +244,8 @@ class StyleNetPlan:
         dev, dt, tc = x.device, self.dtype, self.use_tc
         w = self.w
         new = lambda *s: torch.empty(s, dtype=dt, device=dev)
-        stats = lambda c: torch.empty((B, c, 2), dtype=torch.float32, device=dev)
+        arena = ops.ZeroArena(B * 2 * STATS_CHANNELS, dev)          # all InstanceNorm statistics: one memset per forward
+        stats = lambda c: arena.take(B, c, 2)
         if H <= 4 or W <= 4:
             raise RuntimeError("StyleTransferNet needs H, W >= 5 (ReflectionPad2d(4))")
         if tc:
@@ -252,6 +257,16 @@ class StyleNetPlan:
 
         # conv1: 9x9 stride 2, reflect 4 -> raw1 (B,H1,W1,64)
         H1, W1 = _half_up(H), _half_up(W)
+        H2, W2 = _half_up(H1), _half_up(W1)
+        H4, W4 = 4 * H2, 4 * W2
+        # every zero fill of the forward is issued here, ahead of the first kernel, so that the kernels below follow each
+        # other directly on the stream (programmatic dependent launch chains them; a fill in between would not)
+        Hp, Wp = H1 + 2, W1 + 2
+        Hs, Ws = _half_up(Hp), _half_up(Wp)
+        buf2 = torch.zeros((B, Hs, Ws, 256), dtype=dt, device=dev)
+        Hq, Wq = H4 + 8, W4 + 8
+        flat = torch.empty(B * Hq * Wq * 32 + 128, dtype=dt, device=dev)   # slack: paired / 4-pixel window views
+        flat[-128:].zero_()
         raw1, st1 = new(B, H1, W1, 64), stats(64)
         if tc:
             # tensor-core form: 4-channel reflect-halo image; kernel row kh = tap (row pair kh>>1, row parity via the
@@ -260,20 +275,16 @@ class StyleNetPlan:
             img = ops.image_to_halo(x, 4, PAD_REFLECT, 4, rows, pitch, dt)
             taps = [(kh >> 1, 0, (kh & 1) * pitch * 4) for kh in range(9)]
             ops.conv_gather(ConvSpec(taps, 64, w["conv1"], 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64),
-                            (rows * pitch * 4, 2 * pitch * 4, 8), raw1, (H1, W1), st1, True)
+                            (rows * pitch * 4, 2 * pitch * 4, 8), raw1, (H1, W1), st1, True, stats_zeroed=True)
         else:
             ops.conv_first(x, w["conv1"], None, 9, 2, 4, PAD_REFLECT, False, raw1, st1)
         # norm1 + relu -> space-to-depth halo buffer for the stride-2 conv2
-        Hp, Wp = H1 + 2, W1 + 2
-        Hs, Ws = _half_up(Hp), _half_up(Wp)
-        buf2 = torch.zeros((B, Hs, Ws, 256), dtype=dt, device=dev)
         g, b = self._affine("norm1")
         ops.inorm_apply(raw1, st1, g, b, buf2, relu=True, pad=1, pad_mode=PAD_REFLECT, s2d=True)
         # conv2: 3x3 stride 2 as a 9-tap gather over the s2d buffer
-        H2, W2 = _half_up(H1), _half_up(W1)
         raw2, st2 = new(B, H2, W2, 256), stats(256)
         spec = ConvSpec(taps_s2d_3x3(64), 64, w["conv2"], 256, 256)
-        ops.conv_gather(spec, buf2, (B, Hs, Ws, 256), _nhwc_strides(buf2), raw2, (H2, W2), st2, tc)
+        ops.conv_gather(spec, buf2, (B, Hs, Ws, 256), _nhwc_strides(buf2), raw2, (H2, W2), st2, tc, stats_zeroed=True)
         cur = new(B, H2 + 2, W2 + 2, 256)
         g, b = self._affine("norm2")
         ops.inorm_apply(raw2, st2, g, b, cur, relu=True, pad=1, pad_mode=PAD_REFLECT)
@@ -285,14 +296,14 @@ class StyleNetPlan:
         for i in range(5):
             raw_a, st_a = new(B, H2, W2, 256), stats(256)
             ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}a"], 256, 256, tag=f"res{i}a"), cur, (B, H2 + 2, W2 + 2, 256),
-                            _nhwc_strides(cur), raw_a, (H2, W2), st_a, tc)
+                            _nhwc_strides(cur), raw_a, (H2, W2), st_a, tc, stats_zeroed=True)
             mid = new(B, H2 + 2, W2 + 2, 256)
             g, b = self._affine(f"res_blocks.{i}.in1")
             drop = None if drop_scales is None else drop_scales[i].float().contiguous()
             ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop)
             raw_b, st_b = new(B, H2, W2, 256), stats(256)
             ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}b"], 256, 256, tag=f"res{i}b"), mid, (B, H2 + 2, W2 + 2, 256),
-                            _nhwc_strides(mid), raw_b, (H2, W2), st_b, tc)
+                            _nhwc_strides(mid), raw_b, (H2, W2), st_b, tc, stats_zeroed=True)
             last = i == 4
             nxt = new(B, H2, W2, 256) if last else new(B, H2 + 2, W2 + 2, 256)
             g, b = self._affine(f"res_blocks.{i}.in2")
@@ -307,19 +318,15 @@ class StyleNetPlan:
         H3, W3 = 2 * H2, 2 * W2
         raw3, st3 = new(B, H3, W3, 64), stats(64)
         ops.conv_gather(ConvSpec(TAPS_2X2, 256, w["up1"], 256, 64, epilogue=EPI_D2S), cur, (B, H2, W2, 256),
-                        _nhwc_strides(cur), raw3, (H2, W2), st3, tc)
+                        _nhwc_strides(cur), raw3, (H2, W2), st3, tc, stats_zeroed=True)
         act3 = new(B, H3, W3, 64)
         g, b = self._affine("norm3")
         ops.inorm_apply(raw3, st3, g, b, act3, relu=True)
         # up2: ConvTranspose2d(64->32)
-        H4, W4 = 2 * H3, 2 * W3
         raw4, st4 = new(B, H4, W4, 32), stats(32)
         ops.conv_gather(ConvSpec(TAPS_2X2, 64, w["up2"], 128, 32, epilogue=EPI_D2S), act3, (B, H3, W3, 64),
-                        _nhwc_strides(act3), raw4, (H3, W3), st4, tc)
+                        _nhwc_strides(act3), raw4, (H3, W3), st4, tc, stats_zeroed=True)
         # norm4 + relu -> reflect-4 halo buffer (+ slack so the paired view of the last pixel stays in bounds)
-        Hq, Wq = H4 + 8, W4 + 8
-        flat = torch.empty(B * Hq * Wq * 32 + 128, dtype=dt, device=dev)   # slack: paired / 4-pixel window views
-        flat[-128:].zero_()
         act4 = flat[:B * Hq * Wq * 32].view(B, Hq, Wq, 32)
         g, b = self._affine("norm4")
         ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT)
@@ -344,11 +351,12 @@ class StyleNetPlan:
         dev, w = x.device, self.w
         act = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)
         raw = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        stats = lambda c: torch.empty((B, c, 2), dtype=torch.float32, device=dev)
+        arena = ops.ZeroArena(B * 2 * STATS_CHANNELS, dev)          # all InstanceNorm statistics: one memset per forward
+        stats = lambda c: arena.take(B, c, 2)
 
         def conv(taps, kc, lo_off, weight, n_gemm, c_out, a, a_dims, out, out_hw, st, epilogue=EPI_NHWC, strides=None, bias=None):
             spec = ConvSpec(taps_x3(taps, lo_off), kc, weight, n_gemm, c_out, epilogue=epilogue, bias=bias)
-            ops.conv_gather(spec, a, a_dims, strides or _nhwc_strides(a), out, out_hw, st, True)
+            ops.conv_gather(spec, a, a_dims, strides or _nhwc_strides(a), out, out_hw, st, True, stats_zeroed=st is not None)
 
         # conv1: split 8-channel image (hi0..2,0,lo0..2,0); 8-pixel windows, two windows per kernel row, two weight blocks
         H1, W1 = _half_up(H), _half_up(W)
@@ -357,7 +365,7 @@ class StyleNetPlan:
         taps = [(kh >> 1, win * 4, (kh & 1) * pitch * 8) for kh in range(9) for win in (0, 1) for _blk in (0, 1)]
         raw1, st1 = raw(B, H1, W1, 64), stats(64)
         ops.conv_gather(ConvSpec(taps, 64, w["conv1"], 64, 64), img, (B, H1 + 4, W1 + 4, pitch * 8 + 64),
-                        (rows * pitch * 8, 2 * pitch * 8, 16), raw1, (H1, W1), st1, True)
+                        (rows * pitch * 8, 2 * pitch * 8, 16), raw1, (H1, W1), st1, True, stats_zeroed=True)
         Hp, Wp = H1 + 2, W1 + 2
         Hs, Ws = _half_up(Hp), _half_up(Wp)
         buf2 = torch.zeros((B, Hs, Ws, 512), dtype=torch.float16, device=dev)

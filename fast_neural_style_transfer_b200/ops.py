@@ -127,10 +127,35 @@ def _fill_desc(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, out_hw) -> Co
     return d
 
 
+class ZeroArena:
+    """One zero-filled fp32 buffer handed out in slices: accumulators (InstanceNorm statistics, reduction sums) that
+    kernels add into.  A single memset per forward / backward instead of one in front of every kernel keeps the
+    kernels adjacent on the stream, so each can be chained to its predecessor by programmatic dependent launch."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.used = 0
+
+    def take(self, *shape: int) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        n_al = (n + 3) // 4 * 4                      # keep every slice 16-byte aligned
+        if self.used + n_al > self.buf.numel():
+            raise RuntimeError("ZeroArena exhausted")
+        t = self.buf[self.used:self.used + n].view(*shape)
+        self.used += n_al
+        return t
+
+
 def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, int], a_strides: Tuple[int, int, int],
-                out: torch.Tensor, out_hw: Tuple[int, int], stats: Optional[torch.Tensor], use_tc: bool) -> None:
-    """a_dims = (n, h, w, c) logical extents of the activation view; a_strides = (n, h, w) element strides."""
+                out: torch.Tensor, out_hw: Tuple[int, int], stats: Optional[torch.Tensor], use_tc: bool,
+                stats_zeroed: bool = False) -> None:
+    """a_dims = (n, h, w, c) logical extents of the activation view; a_strides = (n, h, w) element strides.
+    stats_zeroed: `stats` is already zero (slice of a ZeroArena); the call then issues no memset."""
     d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
+    if stats_zeroed:
+        d.flags = _lib.DESC_PREZEROED
     wshape = (spec.n_gemm, len(spec.taps) * spec.kc)
     if spec.per_image_weights:
         wshape = (a_dims[0],) + wshape
@@ -155,7 +180,7 @@ def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, in
     check(fn(C.byref(d), dev, st), "conv_tc" if use_tc else "conv_simt")
     if timed:
         kernel_timer.stop(e0)
-    _count(2 if stats is not None else 1)
+    _count(2 if stats is not None and not stats_zeroed else 1)
 
 
 def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, pad: int,
@@ -241,10 +266,14 @@ def nchw_to_nhwc(x: torch.Tensor, dtype: torch.dtype, c_pad: Optional[int] = Non
 # ---- backward operators -------------------------------------------------------------------------------
 
 def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, out_hw, use_tc: bool = False,
-          g_strides: Optional[Tuple[int, int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+          g_strides: Optional[Tuple[int, int, int]] = None, out: Optional[torch.Tensor] = None,
+          out_zeroed: bool = False) -> torch.Tensor:
     """dB fp32 [n_gemm, ntaps*kc] of the gather-GEMM `spec` (weights unused); g NHWC [n, oh, ow, n_gemm], or a
-    strided view of it given by g_strides = (n, h, w) element strides."""
+    strided view of it given by g_strides = (n, h, w) element strides.  out_zeroed: `out` is already zero."""
     d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
+    if out_zeroed:
+        assert out is not None
+        d.flags = _lib.DESC_PREZEROED
     if g_strides is None:
         assert g.is_contiguous() and g.shape == (a_dims[0], out_hw[0], out_hw[1], spec.n_gemm), (g.shape, spec.n_gemm)
     else:
@@ -260,7 +289,7 @@ def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, o
     check(fn(C.byref(d), dt(g.dtype), dev, st), "wgrad_tc" if use_tc else "wgrad_simt")
     if timed:
         kernel_timer.stop(e0)
-    _count(2)
+    _count(1 if out_zeroed else 2)
     return out
 
 
@@ -276,18 +305,22 @@ def conv_first_wgrad(x: torch.Tensor, g: torch.Tensor, k: int, stride: int, pad:
 
 
 def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=_lib.PAD_NONE, s2d=False,
-                     eps: float = 1e-5):
+                     eps: float = 1e-5, arena: Optional[ZeroArena] = None):
+    """arena: take the (zeroed) reduction buffers from it instead of having the call memset fresh ones."""
     n, h, w, c = raw.shape
     gy = torch.empty((n, h, w, c), dtype=gdtype, device=raw.device)
-    sums = torch.empty((n, c, 2), dtype=torch.float32, device=raw.device)
-    dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device)          # rows: d gamma, d beta
+    if arena is not None:
+        sums, dgb = arena.take(n, c, 2), arena.take(2, c)
+    else:
+        sums = torch.empty((n, c, 2), dtype=torch.float32, device=raw.device)
+        dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device)          # rows: d gamma, d beta
     for t in (gsrc, extra):
         assert t is None or (t.dtype == gdtype and t.is_contiguous())
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_bwd_reduce(_ptr(gsrc), _ptr(extra), _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(gy),
                                     _ptr(sums), _ptr(dgb), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
-                                    dev, st), "inorm_bwd_reduce")
-    _count(3)
+                                    int(arena is not None), dev, st), "inorm_bwd_reduce")
+    _count(1 if arena is not None else 3)
     return gy, sums, dgb
 
 

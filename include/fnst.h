@@ -10,7 +10,11 @@
  *   - extern "C", POD arguments only: raw device pointers, ints, one POD descriptor struct.
  *   - All device memory is caller-owned (torch-allocated); the library never allocates, frees or
  *     retains device pointers across calls.
- *   - Every launch is asynchronous on `stream` of CUDA device `device`; no hidden sync.
+ *   - Every launch is asynchronous on `stream` of CUDA device `device`; no hidden sync.  Kernels of the tensor-core
+ *     path are launched with programmatic stream serialization (PDL): each one overlaps its set-up with the tail of
+ *     the kernel in front of it on the stream and executes griddepcontrol.wait before touching global memory, so
+ *     stream order is preserved; under stream capture these become programmatic CUDA-graph edges.  FNST_PDL=0 in
+ *     the environment turns the launch attribute off.
  *   - Return 0 on success, <0 for argument/shape/alignment errors, >0 = cudaError_t.
  *     fnst_last_error() returns a thread-local message.  There is no fallback path: an
  *     unsupported configuration is an error.
@@ -75,10 +79,19 @@ typedef struct fnst_conv_desc {
   int32_t b_image_rows;          /* 0: one weight matrix for all images; else image n uses rows [n*b_image_rows, +n_gemm) of b */
   /* wgrad only: element strides of the gradient operand g (all zero = contiguous NHWC [out_n,out_h,out_w,n_gemm]) */
   int64_t g_stride_w, g_stride_h, g_stride_n;
+  int32_t flags;                 /* FNST_DESC_* bits                                              */
 } fnst_conv_desc;
+
+/* fnst_conv_desc.flags: the accumulators the call would zero (conv: `stats`; wgrad: `out`) were already zeroed by the
+ * caller (e.g. one arena memset per forward), so the call issues no memset in front of the kernel and the kernel can
+ * be chained to its predecessor by programmatic dependent launch. */
+#define FNST_DESC_PREZEROED 1
 
 int fnst_version(void);
 const char* fnst_last_error(void);
+/* Tuning knobs of the tensor-core kernels (measurement tooling; defaults are the measured best):
+ * "conv_block_n" (0 = heuristic), "wgrad_waves_x2", "wgrad_bn" (0 = widest), "pdl" (0/1).  Returns 0, or -1 for an unknown name. */
+int fnst_set_tuning(const char* name, int value);
 /* 1 when the running device can execute the tcgen05/TMA kernels (compute capability 10.x). */
 int fnst_device_supports_tc(int device);
 
@@ -187,11 +200,12 @@ int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const void* g, in
  * fnst_inorm_apply; fold = ReflectionPad2d backward) and extra an optional plain [n,h,w,c] gradient (residual
  * branch).  Writes gy [n,h,w,c] (g_dtype) and accumulates sums[n][c] = (sum gy, sum gy*xhat) (zeroed by the call);
  * dgb (optional, fp32 [2][c], zeroed by the call) receives d gamma = sum_n sum gy*xhat and d beta = sum_n sum gy.
+ * prezeroed != 0: sums and dgb were zeroed by the caller (no memset is issued in front of the kernel).
  */
 int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
                           const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
                           float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
-                          int pad, int pad_mode, int s2d, int device, void* stream);
+                          int pad, int pad_mode, int s2d, int prezeroed, int device, void* stream);
 /* Pass 2: draw = gamma*rstd*(gy - mean(gy) - xhat*mean(gy*xhat)), written NHWC [n,h,w,c] or, if out_s2d,
  * space-to-depth [n,h/2,w/2,4c] (channel = ((h&1)*2+(w&1))*c + ch; h, w even). */
 int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, const float* sums, const float* gamma,

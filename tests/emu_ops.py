@@ -19,7 +19,7 @@ def _reflect(i: torch.Tensor, n: int) -> torch.Tensor:
     return torch.where(i >= n, 2 * (n - 1) - i, i)
 
 
-def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc):
+def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc, stats_zeroed=False):
     n, ah, aw, ac = a_dims
     sn, sh, sw = a_strides
     view = a.as_strided((n, ah, aw, ac), (sn, sh, sw, 1), a.storage_offset()).double()
@@ -55,8 +55,10 @@ def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc):
     if spec.relu:
         v = v.clamp_min(0)
     if stats is not None:
-        stats[:, :, 0] = v.sum(dim=(1, 2)).float()
-        stats[:, :, 1] = (v * v).sum(dim=(1, 2)).float()
+        if not stats_zeroed:
+            stats.zero_()                       # the call zeroes the accumulators unless the caller already did
+        stats[:, :, 0] += v.sum(dim=(1, 2)).float()
+        stats[:, :, 1] += (v * v).sum(dim=(1, 2)).float()
     if spec.epilogue == EPI_NCHW_F32:
         out.copy_(v.permute(0, 3, 1, 2).to(out.dtype))
     else:
