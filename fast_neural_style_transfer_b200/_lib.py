@@ -55,6 +55,7 @@ EXPORTS = {
     "fnst_version": (C.c_int, []),
     "fnst_last_error": (C.c_char_p, []),
     "fnst_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
+    "fnst_set_debug_buffer": (C.c_int, [C.c_void_p]),
     "fnst_device_supports_tc": (C.c_int, [C.c_int]),
     "fnst_conv_tc": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "fnst_conv_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),

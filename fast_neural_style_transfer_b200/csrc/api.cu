@@ -18,6 +18,7 @@ Tuning& tuning() {
     if (const char* e = getenv("FNST_WGRAD_WAVES_X2")) v.wgrad_waves_x2 = atoi(e);
     if (const char* e = getenv("FNST_WGRAD_BN")) v.wgrad_bn = atoi(e);
     if (const char* e = getenv("FNST_PDL")) v.pdl = atoi(e);
+    if (const char* e = getenv("FNST_CONV_PAIR")) v.conv_pair = atoi(e);
     return v;
   }();
   return t;
@@ -27,12 +28,19 @@ bool pdl_enabled() { return tuning().pdl != 0; }
 
 extern "C" int fnst_version(void) { return 101; }
 
+extern "C" int fnst_set_debug_buffer(void* device_ptr) {
+  fnst::tuning().debug_buf = reinterpret_cast<unsigned long long*>(device_ptr);
+  return 0;
+}
+
 extern "C" int fnst_set_tuning(const char* name, int value) {
   fnst::Tuning& t = fnst::tuning();
   if (!strcmp(name, "conv_block_n")) t.conv_block_n = value;
   else if (!strcmp(name, "wgrad_waves_x2")) t.wgrad_waves_x2 = value;
   else if (!strcmp(name, "wgrad_bn")) t.wgrad_bn = value;
   else if (!strcmp(name, "pdl")) t.pdl = value;
+  else if (!strcmp(name, "conv_pair")) t.conv_pair = value;
+  else if (!strcmp(name, "dbg_mode")) t.dbg_mode = value;
   else { fnst::set_error("fnst_set_tuning: unknown knob '%s'", name); return -1; }
   return 0;
 }

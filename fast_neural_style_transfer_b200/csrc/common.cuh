@@ -57,6 +57,9 @@ struct Tuning {
   int wgrad_waves_x2 = 2;      // wgrad_tc split-K target: tasks <= waves_x2/2 * SM count (one wave measured best: fewer L2 atomics)
   int wgrad_bn = 0;            // 0 = widest column block that divides kc; else force 64/128/256
   int pdl = 1;
+  int conv_pair = 1;           // 1: CTA pairs (cta_group::2) where measured faster; 0: never; 2: whenever the column tile is >= 128
+  int dbg_mode = 0;            // measurement only: bit 0 skips the per-chunk column sums, bit 1 the global statistics atomics
+  unsigned long long* debug_buf = nullptr;   // measurement only: conv_tc writes per-CTA main-loop clocks / nanoseconds here
 };
 Tuning& tuning();
 
@@ -87,16 +90,31 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// cluster_x > 1: launch as thread-block clusters of cluster_x CTAs along x (grid.x must be a multiple of it).
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline void launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                               Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface through launch_status()
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  launch_pdl_cluster(kern, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 
 inline size_t dtype_size(int dt) { return dt == FNST_F32 ? 4 : 2; }

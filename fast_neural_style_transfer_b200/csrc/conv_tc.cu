@@ -2,7 +2,7 @@
 //
 //   out[pixel, j] = sum_{tap t} sum_{c < kc} A[n, h+h0+dh[t], w+w0+dw[t], c0[t]+c] * B[j][t*kc + c]
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 192 or 320 threads, warp-specialised:
 //   warp 0      TMA producer: per k-block (one tap x 64 channels) one 4-D box load of the
 //               activation tile {64 ch, TW, TH, 1} (implicit im2col: a spatial box shifted by the
 //               tap offset; out-of-range coordinates are zero-filled by TMA = zero padding) and
@@ -11,9 +11,20 @@
 //   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 (pixels) x N=BLOCK_N x K=16,
 //               fp32 accumulators in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue
 //               of tile i overlaps the main loop of tile i+1.
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns), bias / ReLU, per-(image,channel)
-//               sum and sum-of-squares for InstanceNorm (butterfly shuffles -> smem -> one global
-//               atomic per column per tile), vector stores as NHWC / depth-to-space / NCHW fp32.
+//   warps 2..   epilogue: tcgen05.ld (32 lanes x 32 columns), bias / ReLU, per-(image,channel)
+//               sum and sum-of-squares for InstanceNorm (smem transposition -> per-warp partials ->
+//               one global atomic per column per tile), vector stores as NHWC / depth-to-space /
+//               NCHW fp32.  Four warps (one per TMEM lane quarter) for column tiles < 128, eight
+//               (two per quarter, half of the columns each) for the wide tiles: with one tile per
+//               CTA (batch <= 4) the epilogue is exposed, and it is latency-bound per warp.
+//
+// PAIR = true: the same kernel as a CTA pair (cluster of 2 on the two SMs of a TPC, tcgen05 cta_group::2): one
+// M=256 x N=BLOCK_N MMA spans two adjacent pixel tiles; each CTA stages its own 128 A rows and only HALF of the B
+// (weight) rows, so per SM the MMA reads 4 KB (A) + BLOCK_N/2 x 32 B (B) of shared memory per K=16 step instead of
+// 4 KB + BLOCK_N x 32 B, and TMA writes a third less -- the single-CTA N=256 form is shared-memory-bandwidth bound
+// (96 B/clk of operand reads + 96 B/clk of TMA writes against 128 B/clk).  The even CTA issues all MMAs; TMA bytes of
+// both CTAs are credited to its full barrier; tcgen05.commit multicasts the "slot free" / "accumulator ready" arrivals
+// to both CTAs; each CTA runs the epilogue of its own 128 TMEM lanes.
 #include "tc_common.cuh"
 
 #include <cstdlib>
@@ -66,6 +77,8 @@ struct ConvTcParams {
   float* stats;
   const void* addend;
   const void* mask;
+  unsigned long long* dbg;       // measurement only (fnst_set_debug_buffer)
+  int32_t dbg_mode;
   int8_t tap_dh[FNST_MAX_TAPS];
   int8_t tap_dw[FNST_MAX_TAPS];
   int16_t tap_c0[FNST_MAX_TAPS];
@@ -74,15 +87,19 @@ struct ConvTcParams {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;                       // 64 two-byte elements = one 128-byte swizzle row
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;
-constexpr int TC_THREADS = 192;
 
-template <int BLOCK_N> struct TcCfg {
-  static constexpr int B_BYTES = BLOCK_N * TC_BLOCK_K * 2;
+template <int BLOCK_N, bool PAIR = false> struct TcCfg {
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // weight rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int CHUNK = BLOCK_N < 32 ? BLOCK_N : 32;     // epilogue column chunk
+  static constexpr int EPI_WARPS = BLOCK_N >= 128 ? 8 : 4;      // epilogue warps: 1 or 2 per TMEM lane quarter
+  static constexpr int EPI_THREADS = 32 * EPI_WARPS;
+  static constexpr int THREADS = 64 + EPI_THREADS;              // + TMA producer warp + MMA warp
+  static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -100,11 +117,12 @@ __device__ __forceinline__ void store_chunk(TOut* p, const float (&v)[32], int c
   }
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BLOCK_N, bool PAIR>
+__global__ void __launch_bounds__((TcCfg<BLOCK_N, PAIR>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, PAIR>;
+  static_assert(!PAIR || BLOCK_N >= 64, "CTA pairs need at least 32 weight rows per CTA");
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CHUNK = Cfg::CHUNK;
 
@@ -116,48 +134,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  __shared__ float s_sum[BLOCK_N], s_sq[BLOCK_N];
-  __shared__ float s_rows[BLOCK_N == 32 ? TC_BLOCK_M * 33 : 1];   // ROWSUM9 staging: 128 T-pixels x 27 partials
+  __shared__ float s_sum[4 * BLOCK_N], s_sq[4 * BLOCK_N];     // per epilogue warp: column sums of its 32 rows (plain stores, no atomics)
+  // 128 x 33 floats of scratch: ROWSUM9 staging (128 T-pixels x 27 partials), or four per-warp 32 x 33 transposition
+  // tiles for the InstanceNorm column sums (the two uses never occur in the same launch)
+  __shared__ float s_rows[TC_BLOCK_M * 33];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PAIR: rank of this CTA inside its pair, work-unit stride and first unit (unit = pair of adjacent pixel tiles x column tile)
+  const int rank = PAIR ? (int)cluster_cta_rank() : 0;
+  const bool leader = rank == 0;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_units = PAIR ? ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles : p.num_tiles;
 
   pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    // tmem_empty: 4 epilogue warps per CTA; in a pair both CTAs' warps arrive on the leader's barrier
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], (PAIR ? 2 : 1) * Cfg::EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < BLOCK_N; i += TC_THREADS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  if (warp == 1) { if (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot); else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot); }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: the partner's barriers must exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();          // set-up above overlapped the predecessor's tail; global memory is touched only from here on
 
   const int TW = 1 << p.tw_log2, TH = TC_BLOCK_M >> p.tw_log2;
+  // unit -> (column tile, pixel tile of this CTA); a pair's phantom second tile (odd tile count) has m_tile == num_m_tiles:
+  // its image index is out of range, so TMA zero-fills the loads and the epilogue stores nothing
+  auto decode = [&](int unit, int& n_tile, int& m_tile) {
+    n_tile = unit % p.num_n_tiles;
+    m_tile = unit / p.num_n_tiles;
+    if (PAIR) m_tile = 2 * m_tile + rank;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        int m_tile = tile / p.num_n_tiles;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        int n_tile, m_tile;
+        decode(unit, n_tile, m_tile);
         const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
         const int th = m_tile % p.tiles_h;
         const int n = m_tile / p.tiles_h;
         const int hb = th * p.h_step + p.h0, wb = tw * TW + p.w0;
+        // weight rows of this CTA: the whole column tile, or its half of it in a pair
+        const int brow = n * p.b_image_rows + n_tile * BLOCK_N + rank * Cfg::B_ROWS;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           const int t = kb / p.chunks_per_tap, ch = kb - t * p.chunks_per_tap;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_4d(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, wb + p.tap_dw[t], hb + p.tap_dh[t], n);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, n * p.b_image_rows + n_tile * BLOCK_N);
+          if (PAIR) {
+            // one arrival + the bytes of BOTH CTAs on the leader's barrier (the partner's loads are credited to it)
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_4d_pair(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, wb + p.tap_dw[t], hb + p.tap_dh[t], n);
+            tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, brow);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_4d(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, wb + p.tap_dw[t], hb + p.tap_dh[t], n);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, brow);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -165,10 +207,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      long long dbg_c0 = 0; unsigned long long dbg_t0 = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -177,36 +220,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (p.dbg && it == 0 && kb == 0) {
+            dbg_c0 = clock64();
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+          }
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = umma_smem_desc(sa, 16, 1024);
           const uint64_t db = umma_smem_desc(sa + TC_A_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
             // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        if (PAIR) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+      }
+      if (p.dbg && it > 0) {
+        const int as = (it - 1) & 1;
+        mbar_wait(&tmem_full[as], ((it - 1) >> 1) & 1);           // last accumulator complete
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        unsigned long long* o = p.dbg + 4 * (PAIR ? (blockIdx.x >> 1) : blockIdx.x);
+        o[0] = (unsigned long long)(clock64() - dbg_c0); o[1] = t1 - dbg_t0;
+        o[2] = (unsigned long long)it * p.num_kblocks; o[3] = (unsigned long long)it;
       }
       pdl_trigger_tail();      // all MMAs of this CTA are issued: let the next kernel launch under the epilogue
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5 = 128 threads) =====================
+    // ===================== epilogue (warps 2.. = EPI_THREADS threads) =====================
+    constexpr int EPI_THREADS = Cfg::EPI_THREADS;
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;            // 0..127
+    const int ew = warp - 2;                    // epilogue warp index; ew >> 2 selects the column half (wide tiles)
+    const int et = threadIdx.x - 64;            // 0..EPI_THREADS-1
+    const int col_begin = (ew >> 2) * Cfg::COLS_PER_WARP, col_end = col_begin + Cfg::COLS_PER_WARP;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % p.num_n_tiles;
-      int m_tile = tile / p.num_n_tiles;
+    for (int unit = unit0; unit < num_units; unit += unit_step, ++it) {
+      int n_tile, m_tile;
+      decode(unit, n_tile, m_tile);
+      const bool tile_live = m_tile < p.num_m_tiles;          // false only for a pair's phantom second tile
       const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
       const int n = m_tile / p.tiles_h;
       const int r = q * 32 + lane;
       const int h = th * p.h_step + (r >> p.tw_log2), w = tw * TW + (r & (TW - 1));
-      const bool valid = h < p.out_h && w < p.out_w;
+      const bool valid = tile_live && h < p.out_h && w < p.out_w;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
@@ -214,18 +275,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 
 #pragma unroll 1
-      for (int cb = 0; cb < BLOCK_N; cb += CHUNK) {
+      for (int cb = col_begin; cb < col_end; cb += CHUNK) {
         uint32_t raw[32];
         if (CHUNK == 32) tmem_ld_x32(t_row + cb, raw); else tmem_ld_x16(t_row + cb, raw);
         tmem_ld_wait();
-        if (cb + CHUNK >= BLOCK_N) {
+        if (cb + CHUNK >= col_end) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]); }
         }
         const int col0 = n_tile * BLOCK_N + cb;           // first GEMM column of this chunk
-        if (col0 >= p.n_gemm) continue;
+        if (col0 >= p.n_gemm || !tile_live) continue;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = i < CHUNK ? __uint_as_float(raw[i]) : 0.f;
@@ -234,10 +295,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // stage the 27 horizontal partials of this T-pixel, then sum 9 rows per output pixel
 #pragma unroll
           for (int i = 0; i < 27; ++i) s_rows[r * 33 + i] = v[i];
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
           const int co = p.c_out;
           const int npix = p.h_step * TW;                       // output pixels of this tile: h_step rows x TW columns
-          for (int idx = et; idx < npix * co; idx += 128) {
+          for (int idx = et; idx < npix * co; idx += EPI_THREADS) {
             const int o = idx / npix, pp = idx - o * npix;
             const int oh = th * p.h_step + (pp >> p.tw_log2), ow = tw * TW + (pp & (TW - 1));
             if (oh < p.out_h && ow < p.out_w) {
@@ -247,7 +308,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               reinterpret_cast<float*>(p.out)[(((size_t)n * co + o) * p.out_h + oh) * p.out_w + ow] = acc;
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
           continue;
         }
 
@@ -303,51 +364,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           else if (p.out_is_bf16) store_chunk<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off, v, CHUNK);
           else store_chunk<__half>(reinterpret_cast<__half*>(p.out) + off, v, CHUNK);
         }
-        if (p.stats) {
-          float sq[32];
+        if (p.stats && !(p.dbg_mode & 1)) {
+          // column sums over this warp's 32 rows through a padded 16-column smem transposition (conflict-free both
+          // ways): lane l sums column (l & 15) over rows 16*(l >> 4) .. +15 with four independent partial sums, one
+          // shuffle joins the two row halves
+          float* tr = s_rows + ew * (16 * 33);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
-          const float cs = warp_column_sums(v, lane);
-          const float cq = warp_column_sums(sq, lane);
-          if (lane < CHUNK) { atomicAdd(&s_sum[cb + lane], cs); atomicAdd(&s_sq[cb + lane], cq); }
+          for (int hh = 0; hh < CHUNK; hh += 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tr[i * 33 + lane] = valid ? v[hh + i] : 0.f;
+            __syncwarp();
+            const float* col = tr + (lane & 15) * 33 + (lane >> 4) * 16;
+            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float x = col[j]; cs[j & 3] += x; cq[j & 3] = fmaf(x, x, cq[j & 3]); }
+            float s1 = (cs[0] + cs[1]) + (cs[2] + cs[3]), s2 = (cq[0] + cq[1]) + (cq[2] + cq[3]);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+            if (lane < 16) { s_sum[q * BLOCK_N + cb + hh + lane] = s1; s_sq[q * BLOCK_N + cb + hh + lane] = s2; }
+            __syncwarp();
+          }
         }
       }
 
       if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int c = et; c < BLOCK_N; c += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        for (int c = et; c < BLOCK_N; c += EPI_THREADS) {
           const int col = n_tile * BLOCK_N + c;
-          if (col < p.n_gemm) {
+          if (col < p.n_gemm && tile_live && !(p.dbg_mode & 2)) {
             const int ch = p.epilogue == FNST_EPI_D2S ? col % p.c_out : col;
             if (ch < p.c_out) {
-              atomicAdd(&p.stats[((size_t)n * p.c_out + ch) * 2 + 0], s_sum[c]);
-              atomicAdd(&p.stats[((size_t)n * p.c_out + ch) * 2 + 1], s_sq[c]);
+              atomicAdd(&p.stats[((size_t)n * p.c_out + ch) * 2 + 0], s_sum[c] + s_sum[BLOCK_N + c] + s_sum[2 * BLOCK_N + c] + s_sum[3 * BLOCK_N + c]);
+              atomicAdd(&p.stats[((size_t)n * p.c_out + ch) * 2 + 1], s_sq[c] + s_sq[BLOCK_N + c] + s_sq[2 * BLOCK_N + c] + s_sq[3 * BLOCK_N + c]);
             }
           }
-          s_sum[c] = 0.f; s_sq[c] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();     // pair: neither CTA may leave while the other still signals / reads it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
 int validate_conv_desc(const fnst_conv_desc* d);
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 static int launch_conv_tc(const CUtensorMap& ma, const CUtensorMap& mb, const ConvTcParams& p, int num_sms, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N>;
-  auto kern = conv_tc_kernel<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, PAIR>;
+  auto kern = conv_tc_kernel<BLOCK_N, PAIR>;
   FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  if (PAIR) {
+    // persistent CTA pairs: one cluster of 2 per TPC; a unit = two adjacent pixel tiles x one column tile
+    const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int pairs = units < num_sms / 2 ? units : num_sms / 2;
+    launch_pdl_cluster(kern, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 2, ma, mb, p);
+    return launch_status("conv_tc (CTA pair)");
+  }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  launch_pdl(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, p);
+  launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, ma, mb, p);
   return launch_status("conv_tc");
 }
 
@@ -425,7 +505,14 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   p.h0 = d->h0; p.w0 = d->w0;
   p.epilogue = d->epilogue; p.c_out = d->c_out; p.n_gemm = d->n_gemm; p.relu = d->relu;
   p.out_is_bf16 = d->out_dtype == FNST_BF16; p.out_is_f32 = d->out_dtype == FNST_F32;
-  p.idesc = umma_idesc_f16(d->dtype == FNST_BF16 ? 1 : 0, block_n, 0, 0);
+  // CTA pairs (M = 256 MMAs across two SMs) for the wide column tiles.  Measured (tools/exp_conv_fixed_cost.py): ~7 % less
+  // time per k-block but ~1 us more fixed cost per launch, so only when every pair gets at least two units of work.
+  const int pair_mode = tuning().conv_pair;
+  const int64_t units_pair = (int64_t)((p.num_m_tiles + 1) / 2) * ((d->n_gemm + block_n - 1) / block_n);   // 74 pairs on 148 SMs
+  const bool pair = block_n >= 128 && p.num_m_tiles >= 2 && (pair_mode == 2 || (pair_mode == 1 && units_pair >= num_sms));
+  p.dbg = tuning().debug_buf;
+  p.dbg_mode = tuning().dbg_mode;
+  p.idesc = umma_idesc_f16(d->dtype == FNST_BF16 ? 1 : 0, block_n, 0, 0, pair ? 256 : 128);
   p.out = d->out; p.bias = d->bias; p.stats = d->stats;
   p.out_dtype = d->out_dtype; p.mask_dtype = d->mask_dtype; p.b_image_rows = d->b_image_rows;
   p.addend = d->epilogue == FNST_EPI_NHWC ? d->addend : nullptr;
@@ -445,16 +532,16 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
     const uint64_t ktot = (uint64_t)d->ntaps * d->kc;
     const uint64_t dims[2] = {ktot, (uint64_t)(d->b_image_rows ? (int64_t)d->b_image_rows * d->out_n : d->n_gemm)};
     const uint64_t str[1] = {ktot * 2};
-    const uint32_t box[2] = {TC_BLOCK_K, (uint32_t)block_n};
+    const uint32_t box[2] = {TC_BLOCK_K, (uint32_t)(pair ? block_n / 2 : block_n)};     // a pair's CTAs load half the rows each
     if (int r = encode_tensor_map_2b(&mb, d->b, 2, dims, str, box)) return r;
   }
   if (d->stats && !(d->flags & FNST_DESC_PREZEROED))
     FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
   switch (block_n) {
-    case 16: return launch_conv_tc<16>(ma, mb, p, num_sms, st);
-    case 32: return launch_conv_tc<32>(ma, mb, p, num_sms, st);
-    case 64: return launch_conv_tc<64>(ma, mb, p, num_sms, st);
-    case 128: return launch_conv_tc<128>(ma, mb, p, num_sms, st);
-    default: return launch_conv_tc<256>(ma, mb, p, num_sms, st);
+    case 16: return launch_conv_tc<16, false>(ma, mb, p, num_sms, st);
+    case 32: return launch_conv_tc<32, false>(ma, mb, p, num_sms, st);
+    case 64: return launch_conv_tc<64, false>(ma, mb, p, num_sms, st);
+    case 128: return pair ? launch_conv_tc<128, true>(ma, mb, p, num_sms, st) : launch_conv_tc<128, false>(ma, mb, p, num_sms, st);
+    default: return pair ? launch_conv_tc<256, true>(ma, mb, p, num_sms, st) : launch_conv_tc<256, false>(ma, mb, p, num_sms, st);
   }
 }
