@@ -78,7 +78,7 @@ EXPORTS = {
     "fnst_conv_first_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "fnst_inorm_bwd_reduce": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "fnst_inorm_bwd_apply": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_inorm_bwd_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "fnst_maxpool2_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "fnst_sse_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
@@ -87,6 +87,7 @@ EXPORTS = {
     "fnst_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fnst_gram_diff_sym": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_float, C.c_void_p,
                                      C.c_int, C.c_int, C.c_void_p]),
+    "fnst_gather_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "fnst_channel_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
 }
 

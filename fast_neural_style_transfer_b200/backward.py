@@ -128,10 +128,12 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         keep_alive.extend(tensors)
         return _Side()
 
-    def dgrad(g, g_dims, fwd_packed, fwd_taps, fwd_kc, out_shape, out_hw, h0=0, w0=0):
-        """Data gradient of a forward gather-GEMM with plain taps (c0 == 0)."""
-        n_gemm_f = fwd_packed.shape[0]
-        wd = pack_dgrad(fwd_packed, len(fwd_taps), fwd_kc, gdt)
+    gp, f64 = ops.gather_pack, torch.float64
+
+    def dgrad(g, g_dims, wd, fwd_taps, fwd_kc, out_shape, out_hw, h0=0, w0=0):
+        """Data gradient of a forward gather-GEMM with plain taps (c0 == 0); wd = its data-gradient operand
+        [fwd_kc, ntaps * n_gemm_fwd] (pack_dgrad of the forward operand)."""
+        n_gemm_f = wd.shape[1] // len(fwd_taps)
         spec = ConvSpec(_neg(fwd_taps), n_gemm_f, wd, fwd_kc, fwd_kc, h0=-h0, w0=-w0)
         out = torch.empty(out_shape, dtype=gdt, device=dev)
         ops.conv_gather(spec, g, g_dims, _nhwc_strides(g), out, out_hw, None, _tc_ok(tc, n_gemm_f, fwd_kc))
@@ -153,59 +155,65 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         g_str = (rows_g * pitch_g * 8, pitch_g * 8, 8)
         flat = tape["act4_flat"]
         taps9 = [(kh - 8, 0, 0) for kh in range(9)]
-        idx = torch.arange(8, -1, -1, device=dev)                             # kw -> i = 8 - kw (jj = 0 entries)
+        idx = torch.arange(8, -1, -1)                                         # kw -> i = 8 - kw (jj = 0 entries); layout maps run on the CPU
         with on_side(g8, flat):
             a_g = flat if flat.dtype == gdt else ops.cast(flat, gdt)
             db = ops.wgrad(ConvSpec(taps9, 64, None, 128, 128), a_g, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), g8,
                            (rows_g, pitch_g), use_tc=True, g_strides=g_str)
-            d5 = db.view(16, 8, 9, 2, 32)                                     # (i, j, kh, jj, c)
-            grads["final_conv.conv.weight"] = d5[idx, :3, :, 0, :].permute(1, 3, 2, 0).contiguous()  # (j, c, kh, kw)
+            # (i, j, kh, jj, c) -> (j, c, kh, kw), kw = 8 - i from the jj = 0 entries
+            grads["final_conv.conv.weight"] = gp("final_wgrad_unpack", lambda t: t.view(16, 8, 9, 2, 32)[idx, :3, :, 0, :]
+                                                 .permute(1, 3, 2, 0).contiguous(), db, torch.float32)
             keep_alive.extend([a_g, db])
-        wd = torch.zeros((32, 9, 2, 8, 8), dtype=torch.float32, device=dev)   # (c, kh, a, i, j)
-        wperm = wfin.detach().float().permute(1, 2, 3, 0)                     # (c, kh, kw, j)
-        wd[:, :, 0, :, :3] = wperm[:, :, idx[:8], :]                          # a = 0: pixel i <-> kw = 8 - i
-        wd[:, :, 1, 0, :3] = wperm[:, :, 0, :]                                # a = 1: pixel 0 <-> kw = 0
+
+        def final_dgrad_layout(wt):                                           # (3, 32, 9, 9) -> (32, 18*64)
+            wd = torch.zeros((32, 9, 2, 8, 8), dtype=wt.dtype)                # (c, kh, a, i, j)
+            wperm = wt.permute(1, 2, 3, 0)                                    # (c, kh, kw, j)
+            wd[:, :, 0, :, :3] = wperm[:, :, idx[:8], :]                # a = 0: pixel i <-> kw = 8 - i
+            wd[:, :, 1, 0, :3] = wperm[:, :, 0, :]                            # a = 1: pixel 0 <-> kw = 0
+            return wd.reshape(32, 18 * 64)
+
         taps18 = [(8 - kh, a * 8, 0) for kh in range(9) for a in (0, 1)]
         d_act4 = torch.empty((B, Hq, Wq, 32), dtype=gdt, device=dev)
-        ops.conv_gather(ConvSpec(taps18, 64, wd.reshape(32, 18 * 64).to(gdt), 32, 32), g8, (B, rows_g, pitch_g, 64), g_str,
-                        d_act4, (Hq, Wq), None, True)
+        ops.conv_gather(ConvSpec(taps18, 64, gp("final_dgrad", final_dgrad_layout, wfin, gdt), 32, 32), g8,
+                        (B, rows_g, pitch_g, 64), g_str, d_act4, (Hq, Wq), None, True)
     else:
         g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
         db = _wgrad(tc, ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), g16, (H4, W4))
         grads["final_conv.conv.weight"] = unpack_conv(db, 3, 32, 9)
-        wf_plain = engine.pack_final_plain(wfin, gdt)
-        d_act4 = dgrad(g16, (B, H4, W4, 16), wf_plain, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
+        wd_fin = gp("final_plain_dgrad", lambda t: pack_dgrad(engine.pack_final_plain(t, f64), 81, 32, f64), wfin, gdt)
+        d_act4 = dgrad(g16, (B, H4, W4, 16), wd_fin, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
 
     # ---- norm4 + up2 ------------------------------------------------------------------------------------
     g4, b4 = plan._affine("norm4")
-    gy, sums, dgb = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT, arena=arena)
+    gy, sums = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT, arena=arena)
+    d_raw4, dgb = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
     grads["norm4.weight"], grads["norm4.bias"] = _affine_grads(dgb)
-    d_raw4 = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
     act3 = tape["act3"]
     H3, W3 = act3.shape[1], act3.shape[2]
     with on_side(act3, d_raw4):
         db = _wgrad(tc, ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, (B, H3, W3, 64), d_raw4, (H3, W3))
-        grads["up2.upsample_conv.weight"] = unpack_conv_transpose(db, 64, 32)
+        grads["up2.upsample_conv.weight"] = gp("convT_unpack", lambda t: unpack_conv_transpose(t, 64, 32), db, torch.float32)
         keep_alive.append(db)
     grads["up2.upsample_conv.bias"] = zeros_like_param("up2.upsample_conv.bias")
-    wup2 = plan.w["up2"] if plan.w["up2"].dtype == gdt else engine.pack_conv_transpose(p["up2.upsample_conv.weight"], gdt)
-    d_act3 = dgrad(d_raw4, (B, H3, W3, 128), wup2, TAPS_2X2, 64, (B, H3, W3, 64), (H3, W3))
+    convT_dgrad = lambda kc: (lambda t: pack_dgrad(engine.pack_conv_transpose(t, f64), 4, kc, f64))
+    wd_up2 = gp("convT_dgrad", convT_dgrad(64), p["up2.upsample_conv.weight"], gdt)
+    d_act3 = dgrad(d_raw4, (B, H3, W3, 128), wd_up2, TAPS_2X2, 64, (B, H3, W3, 64), (H3, W3))
 
     # ---- norm3 + up1 ------------------------------------------------------------------------------------
     g3, b3 = plan._affine("norm3")
-    gy, sums, dgb = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True, arena=arena)
+    gy, sums = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True, arena=arena)
+    d_raw3, dgb = ops.inorm_bwd_apply(gy, tape["raw3"], tape["st3"], sums, g3, out_s2d=True)     # (B,H2,W2,256)
     grads["norm3.weight"], grads["norm3.bias"] = _affine_grads(dgb)
-    d_raw3 = ops.inorm_bwd_apply(gy, tape["raw3"], tape["st3"], sums, g3, out_s2d=True)     # (B,H2,W2,256)
     trunk = tape["trunk"]
     last = trunk[5]
     H2, W2 = last.shape[1], last.shape[2]
     with on_side(last, d_raw3):
         db = _wgrad(tc, ConvSpec(TAPS_2X2, 256, None, 256, 64), last, (B, H2, W2, 256), d_raw3, (H2, W2))
-        grads["up1.upsample_conv.weight"] = unpack_conv_transpose(db, 256, 64)
+        grads["up1.upsample_conv.weight"] = gp("convT_unpack", lambda t: unpack_conv_transpose(t, 256, 64), db, torch.float32)
         keep_alive.append(db)
     grads["up1.upsample_conv.bias"] = zeros_like_param("up1.upsample_conv.bias")
-    wup1 = plan.w["up1"] if plan.w["up1"].dtype == gdt else engine.pack_conv_transpose(p["up1.upsample_conv.weight"], gdt)
-    g_plain = dgrad(d_raw3, (B, H2, W2, 256), wup1, TAPS_2X2, 256, (B, H2, W2, 256), (H2, W2))
+    wd_up1 = gp("convT_dgrad", convT_dgrad(256), p["up1.upsample_conv.weight"], gdt)
+    g_plain = dgrad(d_raw3, (B, H2, W2, 256), wd_up1, TAPS_2X2, 256, (B, H2, W2, 256), (H2, W2))
 
     # ---- residual trunk -----------------------------------------------------------------------------------
     taps9 = taps_kxk(3)
@@ -229,10 +237,10 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         pre = f"res_blocks.{i}"
         # in2 (no ReLU); the total output gradient also feeds the skip connection
         ga, ba = plan._affine(pre + ".in2")
-        g_out, sums, dgb = ops.inorm_bwd_reduce(gsrc, extra, blk["raw_b"], blk["st_b"], ga, ba, None, gdt, False,
+        g_out, sums = ops.inorm_bwd_reduce(gsrc, extra, blk["raw_b"], blk["st_b"], ga, ba, None, gdt, False,
                                            1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE, arena=arena)
+        d_raw_b, dgb = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
         grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(dgb)
-        d_raw_b = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
         mid = blk["mid"]
         with on_side(mid, d_raw_b):
             _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2), out=res_db[2 * i + 1], out_zeroed=True)
@@ -240,9 +248,9 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         d_mid = res_dgrad(d_raw_b, 2 * i + 1)
         # in1 + ReLU + Dropout2d
         ga, ba = plan._affine(pre + ".in1")
-        gy, sums, dgb = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT, arena=arena)
+        gy, sums = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT, arena=arena)
+        d_raw_a, dgb = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
         grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(dgb)
-        d_raw_a = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
         cur = trunk[i]
         with on_side(cur, d_raw_a):
             _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2), out=res_db[2 * i], out_zeroed=True)
@@ -258,17 +266,17 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 
     # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
     g2, b2 = plan._affine("norm2")
-    gy, sums, dgb = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT, arena=arena)
+    gy, sums = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT, arena=arena)
+    d_raw2, dgb = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
     grads["norm2.weight"], grads["norm2.bias"] = _affine_grads(dgb)
-    d_raw2 = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
     buf2 = tape["buf2"]
     Hs, Ws = buf2.shape[1], buf2.shape[2]
     with on_side(buf2, d_raw2):
         db = _wgrad(tc, ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, (B, Hs, Ws, 256), d_raw2, (H2, W2))
-        grads["conv2.conv.weight"] = unpack_conv(db, 256, 64, 3)
+        grads["conv2.conv.weight"] = gp("conv_unpack_3x3", lambda t: unpack_conv(t, 256, 64, 3), db, torch.float32)
         keep_alive.append(db)
     grads["conv2.conv.bias"] = zeros_like_param("conv2.conv.bias")
-    wd2 = pack_dgrad_s2d(p["conv2.conv.weight"], gdt)
+    wd2 = gp("s2d_dgrad", lambda t: pack_dgrad_s2d(t, f64), p["conv2.conv.weight"], gdt)
     d_buf2 = torch.empty((B, Hs, Ws, 256), dtype=gdt, device=dev)
     ops.conv_gather(ConvSpec(_neg(TAPS_2X2), 256, wd2, 256, 256), d_raw2, (B, H2, W2, 256), _nhwc_strides(d_raw2), d_buf2,
                     (Hs, Ws), None, tc)
@@ -276,9 +284,9 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     # ---- norm1 + conv1 -----------------------------------------------------------------------------------------
     g1, b1 = plan._affine("norm1")
     raw1 = tape["raw1"]
-    gy, sums, dgb = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True, arena=arena)
+    gy, sums = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True, arena=arena)
+    d_raw1, dgb = ops.inorm_bwd_apply(gy, raw1, tape["st1"], sums, g1)
     grads["norm1.weight"], grads["norm1.bias"] = _affine_grads(dgb)
-    d_raw1 = ops.inorm_bwd_apply(gy, raw1, tape["st1"], sums, g1)
     if tc:
         # same window view as the forward (engine.StyleNetPlan.forward): taps = kernel rows, 16-pixel x 4-channel windows
         x = tape["x"]
@@ -288,7 +296,8 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         taps = [(kh >> 1, 0, (kh & 1) * pitch * 4) for kh in range(9)]
         db = ops.wgrad(ConvSpec(taps, 64, None, 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64), (rows * pitch * 4, 2 * pitch * 4, 8),
                        d_raw1, (H1, W1), use_tc=True)
-        grads["conv1.conv.weight"] = db.view(64, 9, 16, 4)[:, :, :9, :3].permute(0, 3, 1, 2).contiguous()
+        grads["conv1.conv.weight"] = gp("conv1_wgrad_unpack", lambda t: t.view(64, 9, 16, 4)[:, :, :9, :3].permute(0, 3, 1, 2).contiguous(),
+                                        db, torch.float32)
     else:
         dw1 = ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT)             # tap-major (243, 64)
         grads["conv1.conv.weight"] = dw1.view(3, 9, 9, 64).permute(3, 0, 1, 2).contiguous()
@@ -317,7 +326,9 @@ def vgg_backward(plan: "engine.VGGPlan", tape: dict, dfeats: Sequence[Optional[t
         a, _ = tape[name]
         B, H, W, cin = a.shape
         cout = g.shape[-1]
-        wd = pack_dgrad(plan.w[name], 9, cin, gdt)                      # [cin, 9*cout]
+        wd = plan.derived.get("dgrad." + name)                         # [cin, 9*cout]; the weights are frozen: packed once
+        if wd is None:
+            wd = plan.derived["dgrad." + name] = pack_dgrad(plan.w[name], 9, cin, gdt)
         out = torch.empty((B, H, W, cin), dtype=gdt, device=g.device)
         spec = ConvSpec(_neg(taps9), cout, wd, cin, cin, addend=addend, mask=a if masked else None)
         ops.conv_gather(spec, g, (B, H, W, cout), _nhwc_strides(g), out, (H, W), None, _tc_ok(tc, cout, cin))
@@ -359,10 +370,12 @@ def vgg_backward(plan: "engine.VGGPlan", tape: dict, dfeats: Sequence[Optional[t
     # conv1_1: 64 -> 3 image channels, NCHW fp32 output
     x = tape["x"]
     B, _, H, W = x.shape
-    w0 = plan.params["slice1.0.weight"]                                   # (64, 3, 3, 3)
-    wd = torch.zeros((16, 9, 64), dtype=torch.float32, device=x.device)
-    wd[:3] = w0.permute(1, 2, 3, 0).reshape(3, 9, 64)
-    wd = wd.reshape(16, 576).to(gdt).contiguous()
+    wd = plan.derived.get("dgrad.slice1.0")
+    if wd is None:
+        w0 = plan.params["slice1.0.weight"]                               # (64, 3, 3, 3)
+        wd = torch.zeros((16, 9, 64), dtype=torch.float32, device=x.device)
+        wd[:3] = w0.permute(1, 2, 3, 0).reshape(3, 9, 64)
+        wd = plan.derived["dgrad.slice1.0"] = wd.reshape(16, 576).to(gdt).contiguous()
     dx = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
     spec = ConvSpec(_neg(taps9), 64, wd, 16, 3, epilogue=EPI_NCHW_F32)
     ops.conv_gather(spec, g, (B, H, W, 64), _nhwc_strides(g), dx, (H, W), None, tc)

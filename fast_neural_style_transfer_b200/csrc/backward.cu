@@ -177,82 +177,116 @@ struct HaloLayout {
   }
 };
 
+// Pass 1.  Block = (row group, image); thread = (8-channel group cg, pixel lane pl).  Per-channel constants are
+// computed once per block into shared memory (one channel per thread) instead of 8 channels x 5 scalars per thread;
+// the per-(n,c) partial sums go lane -> smem table -> one global atomic per channel per block.
 template <typename TA, typename TG>
 __global__ void __launch_bounds__(256) inorm_bwd_reduce_kernel(const TG* __restrict__ gsrc, const TG* __restrict__ extra,
                                                                const TA* __restrict__ raw, const float* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                const float* __restrict__ drop, TG* __restrict__ gy,
                                                                float* __restrict__ sums, float* __restrict__ dgb, HaloLayout L,
-                                                               int relu, float eps) {
+                                                               int relu, float eps, int rows_per_block) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float s_acc[];   // [2][C]
-  const int n = blockIdx.y, h = blockIdx.x;
+  extern __shared__ float sm[];      // par[5][C] (a, b, mean, rstd, dropout scale) | part[PL][2C]
+  const int n = blockIdx.y;
   const int C = L.C, CG = C >> 3, PL = 256 / CG;
   const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, c0 = cg * 8;
-  for (int i = threadIdx.x; i < 2 * C; i += 256) s_acc[i] = 0.f;
+  float* par = sm;
+  float* part = sm + 5 * C;
+  {
+    const float inv_cnt = 1.f / (float)(L.H * L.W);
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const float* st = stats + ((size_t)n * C + c) * 2;
+      const float mean = st[0] * inv_cnt;
+      const float rstd = rsqrtf(fmaxf(st[1] * inv_cnt - mean * mean, 0.f) + eps);
+      const float ai = gamma[c] * rstd;
+      par[c] = ai; par[C + c] = beta[c] - mean * ai; par[2 * C + c] = mean; par[3 * C + c] = rstd;
+      par[4 * C + c] = drop ? drop[(size_t)n * C + c] : 1.f;
+    }
+  }
   __syncthreads();
-
   float a[8], b[8], mean[8], rstd[8], ds[8];
-  const float inv_cnt = 1.f / (float)(L.H * L.W);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float* st = stats + ((size_t)n * C + c0 + i) * 2;
-    mean[i] = st[0] * inv_cnt;
-    rstd[i] = rsqrtf(fmaxf(st[1] * inv_cnt - mean[i] * mean[i], 0.f) + eps);
-    a[i] = gamma[c0 + i] * rstd[i];
-    b[i] = beta[c0 + i] - mean[i] * a[i];
-    ds[i] = drop ? drop[(size_t)n * C + c0 + i] : 1.f;
+    a[i] = par[c0 + i]; b[i] = par[C + c0 + i]; mean[i] = par[2 * C + c0 + i]; rstd[i] = par[3 * C + c0 + i]; ds[i] = par[4 * C + c0 + i];
   }
-  int hs[3]; const int nh = L.sources(h, L.H, hs);
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
 
-  for (int w = pl; w < L.W; w += PL) {
-    int wsrc[3]; const int nw = L.sources(w, L.W, wsrc);
-    float g[8];
+  constexpr int U = 2;               // pixels in flight per thread: all loads of a group are issued before the arithmetic
+  for (int rr = 0; rr < rows_per_block; ++rr) {
+    const int h = blockIdx.x * rows_per_block + rr;
+    if (h >= L.H) break;
+    int hs[3]; const int nh = L.sources(h, L.H, hs);
+    for (int w0 = pl; w0 < L.W; w0 += U * PL) {
+      Raw8<TG> gc[U], ge[U];
+      Raw8<TA> xr[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = 0.f;
-    if (gsrc) {
-      for (int ih = 0; ih < nh; ++ih)
-        for (int iw = 0; iw < nw; ++iw) {
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * PL;
+        if (w < L.W) {
+          const size_t idx = (((size_t)n * L.H + h) * L.W + w) * C + c0;
+          if (gsrc) gc[u] = load_raw8<TG>(gsrc + L.index(n, h + L.pad, w + L.pad, c0));      // the unreflected source
+          if (extra) ge[u] = load_raw8<TG>(extra + idx);
+          xr[u] = load_raw8<TA>(raw + idx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * PL;
+        if (w >= L.W) continue;
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = 0.f;
+        if (gsrc) {
           float t[8];
-          load8<TG>(gsrc + L.index(n, hs[ih], wsrc[iw], c0), t);
+          raw8_to_f32<TG>(gc[u], t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = t[i];
+          int wsrc[3]; const int nw = L.sources(w, L.W, wsrc);
+          if (nh > 1 || nw > 1) {          // ReflectionPad2d fold: halo positions that were copied from (h, w) (border pixels only)
+            for (int ih = 0; ih < nh; ++ih)
+              for (int iw = (ih == 0 ? 1 : 0); iw < nw; ++iw) {
+                load8<TG>(gsrc + L.index(n, hs[ih], wsrc[iw], c0), t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] += t[i];
+              }
+          }
+        }
+        const size_t idx = (((size_t)n * L.H + h) * L.W + w) * C + c0;
+        if (extra) {
+          float t[8];
+          raw8_to_f32<TG>(ge[u], t);
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] += t[i];
         }
-    }
-    const size_t idx = (((size_t)n * L.H + h) * L.W + w) * C + c0;
-    if (extra) {
-      float t[8];
-      load8<TG>(extra + idx, t);
+        float x[8];
+        raw8_to_f32<TA>(xr[u], x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] += t[i];
+        for (int i = 0; i < 8; ++i) {
+          const float y = fmaf(x[i], a[i], b[i]);
+          float gv = g[i] * ds[i];
+          if (relu && !(y > 0.f)) gv = 0.f;
+          g[i] = gv;
+          s1[i] += gv;
+          s2[i] = fmaf(gv, (x[i] - mean[i]) * rstd[i], s2[i]);
+        }
+        store8<TG>(gy + idx, g);
+      }
     }
-    float x[8];
-    load8<TA>(raw + idx, x);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float y = fmaf(x[i], a[i], b[i]);
-      float gv = g[i] * ds[i];
-      if (relu && !(y > 0.f)) gv = 0.f;
-      g[i] = gv;
-      s1[i] += gv;
-      s2[i] = fmaf(gv, (x[i] - mean[i]) * rstd[i], s2[i]);
-    }
-    store8<TG>(gy + idx, g);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { atomicAdd(&s_acc[c0 + i], s1[i]); atomicAdd(&s_acc[C + c0 + i], s2[i]); }
+  for (int i = 0; i < 8; ++i) { part[pl * 2 * C + c0 + i] = s1[i]; part[pl * 2 * C + C + c0 + i] = s2[i]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 256) {
-    atomicAdd(&sums[((size_t)n * C + i) * 2 + 0], s_acc[i]);
-    atomicAdd(&sums[((size_t)n * C + i) * 2 + 1], s_acc[C + i]);
-    if (dgb) {                       // d gamma = sum_n sum gy*xhat ; d beta = sum_n sum gy
-      atomicAdd(&dgb[i], s_acc[C + i]);
-      atomicAdd(&dgb[C + i], s_acc[i]);
-    }
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float t = 0.f;
+    for (int q = 0; q < PL; ++q) t += part[q * 2 * C + i];
+    const int c = i < C ? i : i - C, which = i < C ? 0 : 1;
+    atomicAdd(&sums[((size_t)n * C + c) * 2 + which], t);
+    if (dgb) atomicAdd(&dgb[which ? c : C + c], t);      // d gamma = sum gy*xhat (row 0), d beta = sum gy (row 1)
   }
 }
 
@@ -260,34 +294,72 @@ template <typename TA, typename TG>
 __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restrict__ gy, const TA* __restrict__ raw,
                                                               const float* __restrict__ stats, const float* __restrict__ sums,
                                                               const float* __restrict__ gamma, TG* __restrict__ draw,
-                                                              int H, int W, int C, float eps, int out_s2d) {
+                                                              int H, int W, int C, float eps, int out_s2d, float* __restrict__ dgb,
+                                                              int rows_per_block) {
   pdl_trigger();
   pdl_wait();
-  const int n = blockIdx.y, h = blockIdx.x;
+  extern __shared__ float par[];     // [5][C]: k0 = gamma*rstd, mean(gy), mean(gy*xhat), mean, rstd
+  const int n = blockIdx.y;
+  if (dgb && blockIdx.x == 0 && blockIdx.y == 0) {
+    // d gamma = sum_n sum gy*xhat, d beta = sum_n sum gy: from the per-(n,c) sums of pass 1 (one block, plain stores --
+    // accumulating them with atomics in pass 1 would put every block of the grid on the same 2C addresses)
+    const int N = gridDim.y;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float dg = 0.f, db = 0.f;
+      for (int i = 0; i < N; ++i) { db += sums[((size_t)i * C + c) * 2 + 0]; dg += sums[((size_t)i * C + c) * 2 + 1]; }
+      dgb[c] = dg; dgb[C + c] = db;
+    }
+  }
+  {
+    const float inv_cnt = 1.f / (float)(H * W);
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const float* st = stats + ((size_t)n * C + c) * 2;
+      const float* smv = sums + ((size_t)n * C + c) * 2;
+      const float mean = st[0] * inv_cnt;
+      const float rstd = rsqrtf(fmaxf(st[1] * inv_cnt - mean * mean, 0.f) + eps);
+      par[c] = gamma[c] * rstd; par[C + c] = smv[0] * inv_cnt; par[2 * C + c] = smv[1] * inv_cnt;
+      par[3 * C + c] = mean; par[4 * C + c] = rstd;
+    }
+  }
+  __syncthreads();
   const int CG = C >> 3, PL = 256 / CG;
   const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, c0 = cg * 8;
   float mean[8], rstd[8], k0[8], m1[8], m2[8];
-  const float inv_cnt = 1.f / (float)(H * W);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float* st = stats + ((size_t)n * C + c0 + i) * 2;
-    const float* sm = sums + ((size_t)n * C + c0 + i) * 2;
-    mean[i] = st[0] * inv_cnt;
-    rstd[i] = rsqrtf(fmaxf(st[1] * inv_cnt - mean[i] * mean[i], 0.f) + eps);
-    k0[i] = gamma[c0 + i] * rstd[i];
-    m1[i] = sm[0] * inv_cnt;
-    m2[i] = sm[1] * inv_cnt;
+    k0[i] = par[c0 + i]; m1[i] = par[C + c0 + i]; m2[i] = par[2 * C + c0 + i]; mean[i] = par[3 * C + c0 + i]; rstd[i] = par[4 * C + c0 + i];
   }
-  for (int w = pl; w < W; w += PL) {
-    const size_t idx = (((size_t)n * H + h) * W + w) * C + c0;
-    float g[8], x[8];
-    load8<TG>(gy + idx, g);
-    load8<TA>(raw + idx, x);
+  constexpr int U = 2;
+  for (int rr = 0; rr < rows_per_block; ++rr) {
+    const int h = blockIdx.x * rows_per_block + rr;
+    if (h >= H) break;
+    for (int w0 = pl; w0 < W; w0 += U * PL) {
+      Raw8<TG> gr[U];
+      Raw8<TA> xr[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = k0[i] * (g[i] - m1[i] - (x[i] - mean[i]) * rstd[i] * m2[i]);
-    TG* dst = out_s2d ? draw + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c0
-                      : draw + idx;
-    store8<TG>(dst, g);
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * PL;
+        if (w < W) {
+          const size_t idx = (((size_t)n * H + h) * W + w) * C + c0;
+          gr[u] = load_raw8<TG>(gy + idx);
+          xr[u] = load_raw8<TA>(raw + idx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * PL;
+        if (w >= W) continue;
+        const size_t idx = (((size_t)n * H + h) * W + w) * C + c0;
+        float g[8], x[8];
+        raw8_to_f32<TG>(gr[u], g);
+        raw8_to_f32<TA>(xr[u], x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = k0[i] * (g[i] - m1[i] - (x[i] - mean[i]) * rstd[i] * m2[i]);
+        TG* dst = out_s2d ? draw + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c0
+                          : draw + idx;
+        store8<TG>(dst, g);
+      }
+    }
   }
 }
 
@@ -441,6 +513,14 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restric
   }
 }
 
+// Rows per block of the InstanceNorm backward kernels: the per-block set-up (channel constants, partial-sum flush) is
+// amortised over several rows once the grid is large enough to fill the GPU; single rows for small problems.
+static int rows_per_block(int h, int n) {
+  int r = 1;
+  while (r < 8 && (int64_t)n * ((h + 2 * r - 1) / (2 * r)) >= 148 * 8) r *= 2;
+  return r;
+}
+
 static int grid_cap(int64_t items) {
   int64_t b = (items + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -491,7 +571,7 @@ extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const 
                                      float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
                                      int pad, int pad_mode, int s2d, int prezeroed, int device, void* stream) {
   FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && gy && sums, "inorm_bwd_reduce: null pointer");
-  FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_reduce: unsupported channel count %d", c);
+  FNST_CHECK_ARG(c % 8 == 0 && c <= 1024 && 256 % (c / 8) == 0, "inorm_bwd_reduce: unsupported channel count %d", c);
   FNST_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
   if (!prezeroed) {
@@ -499,30 +579,33 @@ extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const 
     if (dgb) FNST_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * 2 * (size_t)c, st));
   }
   HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d};
-  dim3 grid(h, n);
+  const int rpb = rows_per_block(h, n);
+  dim3 grid((h + rpb - 1) / rpb, n);
+  const size_t smem = sizeof(float) * (5 * (size_t)c + (size_t)(256 / (c / 8)) * 2 * c);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
-      launch_pdl(inorm_bwd_reduce_kernel<TA, TG>, dim3(grid), dim3(256), sizeof(float) * 2 * c, st, 
+      launch_pdl(inorm_bwd_reduce_kernel<TA, TG>, dim3(grid), dim3(256), smem, st,
           reinterpret_cast<const TG*>(gsrc), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(raw), stats, gamma,
-          beta, drop, reinterpret_cast<TG*>(gy), sums, dgb, L, relu, eps);
+          beta, drop, reinterpret_cast<TG*>(gy), sums, dgb, L, relu, eps, rpb);
     });
   });
   return launch_status("inorm_bwd_reduce");
 }
 
 extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, const float* sums, const float* gamma,
-                                    void* draw, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps, int out_s2d,
-                                    int device, void* stream) {
+                                    void* draw, float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps,
+                                    int out_s2d, int device, void* stream) {
   FNST_CHECK_ARG(gy && raw && stats && sums && gamma && draw, "inorm_bwd_apply: null pointer");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_apply: unsupported channel count %d", c);
   FNST_CHECK_ARG(!out_s2d || (h % 2 == 0 && w % 2 == 0), "inorm_bwd_apply: space-to-depth output needs even h, w");
   FNST_CUDA(cudaSetDevice(device));
-  dim3 grid(h, n);
+  const int rpb = rows_per_block(h, n);
+  dim3 grid((h + rpb - 1) / rpb, n);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
-      launch_pdl(inorm_bwd_apply_kernel<TA, TG>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
+      launch_pdl(inorm_bwd_apply_kernel<TA, TG>, dim3(grid), dim3(256), sizeof(float) * 5 * c, (cudaStream_t)stream,
           reinterpret_cast<const TG*>(gy), reinterpret_cast<const TA*>(raw), stats, sums, gamma, reinterpret_cast<TG*>(draw),
-          h, w, c, eps, out_s2d);
+          h, w, c, eps, out_s2d, dgb, rpb);
     });
   });
   return launch_status("inorm_bwd_apply");

@@ -263,6 +263,20 @@ __global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO
   }
 }
 
+// out[i] = idx[i] < 0 ? 0 : src[idx[i]], converted to the output element type: every weight re-layout of the path
+// (parameter layout <-> packed gather-GEMM operand, sub-pixel / space-to-depth / window forms, and their inverses for
+// the gradients) is one launch of this kernel with a cached index map (engine.gather_pack).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) gather_cast_kernel(const TI* __restrict__ src, const int32_t* __restrict__ idx,
+                                                          TO* __restrict__ out, int64_t count) {
+  pdl_trigger();
+  pdl_wait();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t j = idx[i];
+    out[i] = from_f32<TO>(j < 0 ? 0.f : to_f32<TI>(src[j]));
+  }
+}
+
 // uint8 HWC images <-> NCHW fp32 (inference pre/post-processing on the device, inference.py:28-31,52-60):
 //   u8 -> f32:  x[n,c,h,w] = (u8[n,h,w,c] / 255 - mean[c]) / std[c]        (mean = 0, std = 1: plain ToTensor)
 //   f32 -> u8:  u8[n,h,w,c] = round(clamp(y[n,c,h,w] * std[c] + mean[c], 0, 1) * 255)
@@ -397,6 +411,19 @@ extern "C" int fnst_cast(const void* in, void* out, int64_t count, int in_dtype,
     });
   });
   return launch_status("cast");
+}
+
+extern "C" int fnst_gather_cast(const void* src, int src_dtype, const int32_t* idx, void* out, int out_dtype, int64_t count,
+                                int device, void* stream) {
+  FNST_CHECK_ARG(src && idx && out && count > 0, "gather_cast: bad arguments");
+  FNST_CUDA(cudaSetDevice(device));
+  FNST_DISPATCH_DTYPE(src_dtype, TI, {
+    FNST_DISPATCH_DTYPE(out_dtype, TO, {
+      launch_pdl(gather_cast_kernel<TI, TO>, dim3(grid_for(count)), dim3(256), 0, (cudaStream_t)stream,
+                 reinterpret_cast<const TI*>(src), idx, reinterpret_cast<TO*>(out), count);
+    });
+  });
+  return launch_status("gather_cast");
 }
 
 extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w, int pad, int pad_mode, int c_pad, int rows,

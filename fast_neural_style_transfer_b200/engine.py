@@ -211,8 +211,11 @@ class StyleNetPlan:
             self.final_bias = torch.zeros(16, dtype=torch.float32, device=self.w["final"].device)
             self.final_bias[:3] = p["final_conv.conv.bias"].float()
             return self
-        w = {"conv1": pack_first_tc(p["conv1.conv.weight"], 4, dt) if self.use_tc else pack_first(p["conv1.conv.weight"]),
-             "conv2": pack_conv(p["conv2.conv.weight"], dt)}
+        # irregular re-layouts run as one gather kernel each (ops.gather_pack: cached index map of the layout function)
+        gp, f64 = ops.gather_pack, torch.float64
+        w = {"conv1": gp("first_tc4", lambda t: pack_first_tc(t, 4, f64), p["conv1.conv.weight"], dt) if self.use_tc
+             else pack_first(p["conv1.conv.weight"]),
+             "conv2": gp("conv", lambda t: pack_conv(t, f64), p["conv2.conv.weight"], dt)}
         # the ten 3x3 256->256 weights are packed by two kernels (stack, permute+cast) into one (10, 256, 2304) tensor
         names = [f"res_blocks.{i}.{c}.conv.weight" for i in range(5) for c in ("conv1", "conv2")]
         stacked = torch.stack([p[n] for n in names])                              # (10, O, C, 3, 3)
@@ -221,9 +224,10 @@ class StyleNetPlan:
         w["res_all"] = res_all
         for i in range(5):
             w[f"res{i}a"], w[f"res{i}b"] = res_all[2 * i], res_all[2 * i + 1]
-        w["up1"] = pack_conv_transpose(p["up1.upsample_conv.weight"], dt)
-        w["up2"] = pack_conv_transpose(p["up2.upsample_conv.weight"], dt)
-        w["final"] = (pack_final_rowsum if self.use_tc else pack_final_plain)(p["final_conv.conv.weight"], dt)
+        w["up1"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up1.upsample_conv.weight"], dt)
+        w["up2"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up2.upsample_conv.weight"], dt)
+        w["final"] = (gp("final_rowsum", lambda t: pack_final_rowsum(t, f64), p["final_conv.conv.weight"], dt) if self.use_tc
+                      else gp("final_plain", lambda t: pack_final_plain(t, f64), p["final_conv.conv.weight"], dt))
         self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
         self.final_bias[:3] = p["final_conv.conv.bias"].float()
         self.w = w
@@ -435,6 +439,7 @@ class VGGPlan:
 
     def pack(self, params: Dict[str, torch.Tensor]) -> "VGGPlan":
         self.params = {k: v.detach() for k, v in params.items()}
+        self.derived: Dict[str, torch.Tensor] = {}      # operands derived from the (frozen) weights, e.g. data-gradient forms
         for name in VGG_LAYERS:
             wt = params[name + ".weight"].detach()
             self.b[name] = params[name + ".bias"].detach().float().contiguous()

@@ -309,30 +309,32 @@ def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, p
     """arena: take the (zeroed) reduction buffers from it instead of having the call memset fresh ones."""
     n, h, w, c = raw.shape
     gy = torch.empty((n, h, w, c), dtype=gdtype, device=raw.device)
+    dgb = None                   # d gamma / d beta come out of pass 2 (inorm_bwd_apply): no same-address atomics in pass 1
     if arena is not None:
-        sums, dgb = arena.take(n, c, 2), arena.take(2, c)
+        sums = arena.take(n, c, 2)
     else:
         sums = torch.empty((n, c, 2), dtype=torch.float32, device=raw.device)
-        dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device)          # rows: d gamma, d beta
     for t in (gsrc, extra):
         assert t is None or (t.dtype == gdtype and t.is_contiguous())
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_bwd_reduce(_ptr(gsrc), _ptr(extra), _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(gy),
                                     _ptr(sums), _ptr(dgb), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
                                     int(arena is not None), dev, st), "inorm_bwd_reduce")
-    _count(1 if arena is not None else 3)
-    return gy, sums, dgb
+    _count(1 if arena is not None else 2)
+    return gy, sums
 
 
 def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-5):
+    """Returns (d_raw, dgb) with dgb = [d gamma; d beta] (2, c) fp32."""
     n, h, w, c = raw.shape
     shape = (n, h // 2, w // 2, 4 * c) if out_s2d else (n, h, w, c)
     draw = torch.empty(shape, dtype=gy.dtype, device=raw.device)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device)
     dev, st = _ctx(raw)
-    check(lib.fnst_inorm_bwd_apply(_ptr(gy), _ptr(raw), _ptr(stats), _ptr(sums), _ptr(gamma), _ptr(draw), n, h, w, c,
+    check(lib.fnst_inorm_bwd_apply(_ptr(gy), _ptr(raw), _ptr(stats), _ptr(sums), _ptr(gamma), _ptr(draw), _ptr(dgb), n, h, w, c,
                                    dt(raw.dtype), dt(gy.dtype), eps, int(out_s2d), dev, st), "inorm_bwd_apply")
     _count()
-    return draw
+    return draw, dgb
 
 
 def maxpool2_bwd(inp, gout, extra):
@@ -418,6 +420,31 @@ def gram_diff_sym(g: torch.Tensor, gt: torch.Tensor, scale: torch.Tensor, coef: 
     dev, st = _ctx(g)
     check(lib.fnst_gram_diff_sym(_ptr(g), _ptr(gt), n, c, gt.numel(), _ptr(scale), float(coef), _ptr(out), dt(dtype), dev, st),
           "gram_diff_sym")
+    _count()
+    return out
+
+
+_GATHER_MAPS = {}
+
+
+def gather_pack(key: str, layout_fn, src: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """out = layout_fn(src).to(out_dtype) as ONE kernel.  `layout_fn` must be a pure re-layout (every output element is
+    one input element or zero); its index map is derived once per (key, shape, device) by running it on a CPU tensor of
+    element numbers and cached on the device.  (First use does host work: warm up before CUDA-graph capture.)"""
+    ck = (key, tuple(src.shape), src.device)
+    ent = _GATHER_MAPS.get(ck)
+    if ent is None:
+        probe = torch.arange(1, src.numel() + 1, dtype=torch.float64).reshape(src.shape)
+        res = layout_fn(probe)
+        idx = (res.reshape(-1).round().to(torch.int64) - 1).to(torch.int32)
+        ent = _GATHER_MAPS[ck] = (idx.to(src.device), tuple(res.shape))
+    idx, shape = ent
+    s = src.detach()
+    if not s.is_contiguous():
+        s = s.contiguous()
+    out = torch.empty(shape, dtype=out_dtype, device=src.device)
+    dev, st = _ctx(s)
+    check(lib.fnst_gather_cast(_ptr(s), dt(s.dtype), _ptr(idx), _ptr(out), dt(out_dtype), idx.numel(), dev, st), "gather_cast")
     _count()
     return out
 

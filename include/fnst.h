@@ -203,7 +203,8 @@ int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const void* g, in
  * where gsrc is the gradient of the consumer's halo buffer (layout pad / pad_mode / s2d exactly as written by
  * fnst_inorm_apply; fold = ReflectionPad2d backward) and extra an optional plain [n,h,w,c] gradient (residual
  * branch).  Writes gy [n,h,w,c] (g_dtype) and accumulates sums[n][c] = (sum gy, sum gy*xhat) (zeroed by the call);
- * dgb (optional, fp32 [2][c], zeroed by the call) receives d gamma = sum_n sum gy*xhat and d beta = sum_n sum gy.
+ * dgb (optional, fp32 [2][c], zeroed by the call) receives d gamma = sum_n sum gy*xhat and d beta = sum_n sum gy
+ * (every block of the grid then adds to the same 2c addresses: prefer passing NULL here and dgb to pass 2).
  * prezeroed != 0: sums and dgb were zeroed by the caller (no memset is issued in front of the kernel).
  */
 int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
@@ -211,10 +212,11 @@ int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, 
                           float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
                           int pad, int pad_mode, int s2d, int prezeroed, int device, void* stream);
 /* Pass 2: draw = gamma*rstd*(gy - mean(gy) - xhat*mean(gy*xhat)), written NHWC [n,h,w,c] or, if out_s2d,
- * space-to-depth [n,h/2,w/2,4c] (channel = ((h&1)*2+(w&1))*c + ch; h, w even). */
+ * space-to-depth [n,h/2,w/2,4c] (channel = ((h&1)*2+(w&1))*c + ch; h, w even).
+ * dgb (optional, fp32 [2][c], written, not accumulated): d gamma = sum_n sums[n][c][1], d beta = sum_n sums[n][c][0]. */
 int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, const float* sums, const float* gamma,
-                         void* draw, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps, int out_s2d,
-                         int device, void* stream);
+                         void* draw, float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps,
+                         int out_s2d, int device, void* stream);
 
 /* MaxPool2d(2,2) backward fused with the ReLU mask of its input: gin = (extra + route(gout)) * (in > 0);
  * the first maximal element of each window receives the gradient (PyTorch tie rule). */
@@ -240,6 +242,12 @@ int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, 
 /* Element-type conversion of a contiguous tensor (count % 8 == 0).  tcgen05 kind::f16 needs both operands in the
  * same 16-bit format, so saved fp16 activations are converted to the bf16 gradient format for fnst_wgrad_tc. */
 int fnst_cast(const void* in, void* out, int64_t count, int in_dtype, int out_dtype, int device, void* stream);
+
+/* Weight re-layout: out[i] = idx[i] < 0 ? 0 : src[idx[i]] converted to out_dtype (count elements; idx int32 on the device).
+ * One launch per packed operand: PyTorch OIHW / IOHW parameters -> gather-GEMM operands of include/fnst.h's conv
+ * descriptor (and packed fp32 weight gradients -> parameter layout), with index maps cached by the host layer. */
+int fnst_gather_cast(const void* src, int src_dtype, const int32_t* idx, void* out, int out_dtype, int64_t count,
+                     int device, void* stream);
 
 /* out[c] = sum over n,h,w of x[n,c,h,w] (fp32 NCHW); final_conv bias gradient. */
 int fnst_channel_sum(const float* x, int n, int c, int hw, float* out, int device, void* stream);

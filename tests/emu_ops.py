@@ -156,11 +156,15 @@ def nchw_to_nhwc(x, dtype):
     return x.permute(0, 2, 3, 1).to(dtype).contiguous()
 
 
+def gather_pack(key, layout_fn, src, out_dtype):
+    return layout_fn(src.detach().double()).to(out_dtype)
+
+
 def require_tensor_cores(device):
     return None
 
 
 def install(monkeypatch, ops_module):
     """Substitute every operator of `ops_module` by its emulation."""
-    for name in ("require_tensor_cores", "conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc"):
+    for name in ("require_tensor_cores", "conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc", "gather_pack"):
         monkeypatch.setattr(ops_module, name, globals()[name])

@@ -159,10 +159,10 @@ def test_inorm_backward(cfg, gdtype):
         gs = F.pad(gs.float(), (0, 0, 0, wp % 2, 0, hp % 2)).to(gdtype)
         gs = gs.view(n, gs.shape[1] // 2, 2, gs.shape[2] // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, gs.shape[1] // 2, gs.shape[2] // 2, 4 * c).contiguous()
     st = torch.stack([raw.double().sum((1, 2)), (raw.double() ** 2).sum((1, 2))], dim=-1).float()
-    gy, sums, dgb = ops.inorm_bwd_reduce(gs.to(DEV), None if extra is None else extra.to(DEV), raw.to(DEV), st.to(DEV), gamma.to(DEV),
+    gy, sums = ops.inorm_bwd_reduce(gs.to(DEV), None if extra is None else extra.to(DEV), raw.to(DEV), st.to(DEV), gamma.to(DEV),
                                     beta.to(DEV), None if drop is None else drop.to(DEV), gdtype, cfg["relu"], pad,
                                     _lib.PAD_REFLECT if pad else _lib.PAD_NONE, cfg["s2d"])
-    draw = ops.inorm_bwd_apply(gy, raw.to(DEV), st.to(DEV), sums, gamma.to(DEV), out_s2d=cfg["out_s2d"])
+    draw, dgb = ops.inorm_bwd_apply(gy, raw.to(DEV), st.to(DEV), sums, gamma.to(DEV), out_s2d=cfg["out_s2d"])
     ref = r64.grad
     if cfg["out_s2d"]:
         ref = ref.view(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c)

@@ -106,7 +106,7 @@ def case_inorm_bwd(B, sets, which, hw=64, c=256):
     if which == "reduce":
         return run_reduce, sets, B * hw * hw * c * (2 + 2 + 2 + 2)
     run_reduce()
-    gy, sums, _ = res["last"]
+    gy, sums = res["last"]
 
     def run_apply():
         for r in raws:
@@ -118,11 +118,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bench_kernels.json"))
+    ap.add_argument("--only", default="", help="substring filter on the case name")
     args = ap.parse_args()
     B = args.batch
     results = []
 
     def rec(name, maker, **knobs):
+        if args.only and args.only not in name:
+            return
         for k, v in knobs.items():
             knob(k, v)
         for sets in (2, 24):
@@ -147,8 +150,8 @@ def main():
     knob("wgrad_bn", 0)
     for pdl in (0, 1):
         rec("inorm_apply_256", lambda s: case_inorm_apply(B, s), pdl=pdl)
-        rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=pdl)
-        rec("inorm_bwd_apply_256", lambda s: case_inorm_bwd(B, s, "apply"), pdl=pdl)
+    rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=1)
+    rec("inorm_bwd_apply_256", lambda s: case_inorm_bwd(B, s, "apply"), pdl=1)
     rec("vgg_conv1_2_64", lambda s: case_conv3x3(B, s, dt=torch.bfloat16, hw=256, cin=64, cout=64), pdl=1)
     rec("vgg_conv2_2_128", lambda s: case_conv3x3(B, s, dt=torch.bfloat16, hw=128, cin=128, cout=128), pdl=1)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest -q --timeout 300 --timeout-method thread -p no:cacheprovider tests -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python tools/bench_kernels.py --only inorm > gpurun_out/bench_kernels_inorm.log 2>&1; grep inorm gpurun_out/bench_kernels_inorm.log | grep '"pdl": 1'
+for WL in train infer256_b1; do
+  FNST_BENCH_NO_ROOFLINE=1 timeout 600 python bench.py --workload $WL --no-cpu-baseline --steps 30 > gpurun_out/q_$WL.json 2> gpurun_out/q_$WL.err
+  python -c "
+import json; d=json.load(open('gpurun_out/q_$WL.json')); print('$WL', round(d['ms_per_step'],4), 'ms  e2e', round(d['e2e']['value'],1), d['gpu_launches'])"
+done
