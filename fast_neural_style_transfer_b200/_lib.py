@@ -58,6 +58,7 @@ EXPORTS = {
     "fnst_set_debug_buffer": (C.c_int, [C.c_void_p]),
     "fnst_device_supports_tc": (C.c_int, [C.c_int]),
     "fnst_conv_tc": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
+    "fnst_finalconv_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fnst_conv_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_void_p]),
     "fnst_conv_first": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

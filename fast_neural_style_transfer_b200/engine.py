@@ -11,6 +11,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from . import ops
@@ -153,6 +155,17 @@ def pack_final_rowsum(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return out.to(dtype).contiguous()
 
 
+def pack_final_stream(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """final_conv weight (3, 32, 9, 9) -> operand image of fnst_finalconv_tc: [kw][channel half][k-chunk][row][8 channels],
+    row = kh*3 + o (27 used of 32), channel = half*16 + chunk*8 + e  (K-major core matrices of 8 rows x 16 bytes)."""
+    o, c, k, _ = w.shape
+    assert (o, c, k) == (3, 32, 9)
+    b = torch.zeros((9, 2, 2, 32, 8), dtype=w.dtype, device=w.device)        # (kw, half, chunk, row, e)
+    src = w.permute(3, 2, 0, 1).reshape(9, 27, 2, 2, 8)                        # (kw, kh*3+o, half, chunk, e)
+    b[:, :, :, :27, :] = src.permute(0, 2, 3, 1, 4)
+    return b.reshape(-1).to(dtype).contiguous()
+
+
 def pack_final_plain(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     o = w.shape[0]
     b = torch.zeros((16, w.shape[2] * w.shape[3] * w.shape[1]), dtype=w.dtype, device=w.device)
@@ -163,6 +176,12 @@ def pack_final_plain(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 # StyleTransferNet
 # ---------------------------------------------------------------------------------------------
+
+# final_conv forward through the row-streaming kernel (fnst_finalconv_tc); FNST_FINAL_STREAM=0 keeps the gather-GEMM ROWSUM9 form
+FINAL_STREAM = os.environ.get("FNST_FINAL_STREAM", "1") != "0"
+# measured (tools/check_finalconv.py): 808 vs 2078 us at 256 x 256x256, 924 vs 1993 us at 8 x 1080x1920, 25 vs 40 us at batch 4,
+# 25 vs 21 us for a single 256x256 image -> the streaming kernel from two 256x256 images' worth of pixels upwards
+FINAL_STREAM_MIN_PIXELS = 2 * 256 * 256
 
 # channels of the 14 InstanceNorm layers (models/model.py:29,32,41,44,81,83): norm1, norm2, 5 x (in1, in2), norm3, norm4
 STATS_CHANNELS = 64 + 256 + 10 * 256 + 64 + 32
@@ -226,6 +245,8 @@ class StyleNetPlan:
             w[f"res{i}a"], w[f"res{i}b"] = res_all[2 * i], res_all[2 * i + 1]
         w["up1"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up1.upsample_conv.weight"], dt)
         w["up2"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up2.upsample_conv.weight"], dt)
+        if self.use_tc and FINAL_STREAM:
+            w["final_stream"] = gp("final_stream", lambda t: pack_final_stream(t, f64), p["final_conv.conv.weight"], dt)
         w["final"] = (gp("final_rowsum", lambda t: pack_final_rowsum(t, f64), p["final_conv.conv.weight"], dt) if self.use_tc
                       else gp("final_plain", lambda t: pack_final_plain(t, f64), p["final_conv.conv.weight"], dt))
         self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
@@ -336,7 +357,10 @@ class StyleNetPlan:
         ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT)
         # final_conv 9x9 -> NCHW fp32
         y = torch.empty((B, 3, H4, W4), dtype=torch.float32, device=dev)
-        if tc:
+        if tc and FINAL_STREAM and B * H4 * W4 >= FINAL_STREAM_MIN_PIXELS:
+            # row-streaming kernel: every input row is staged in shared memory once, the 9 horizontal taps are address shifts
+            ops.finalconv_stream(flat, B, H4, W4, w["final_stream"], self.final_bias, y)
+        elif tc:
             # separable form: 5 pixel-pair taps along w, the 9 kernel rows live in the GEMM columns (ROWSUM9 epilogue)
             spec = ConvSpec(TAPS_ROWSUM, 64, w["final"], 32, 3, epilogue=EPI_ROWSUM9, bias=self.final_bias)
             ops.conv_gather(spec, act4, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), y, (H4, W4), None, True)

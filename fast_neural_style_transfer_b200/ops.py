@@ -183,6 +183,18 @@ def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, in
     _count(2 if stats is not None and not stats_zeroed else 1)
 
 
+def finalconv_stream(act_flat: torch.Tensor, n: int, h: int, w: int, wpacked: torch.Tensor, bias: torch.Tensor,
+                     out: torch.Tensor) -> None:
+    """final_conv forward (32 -> 3, 9x9) as the row-streaming tensor-core kernel.  act_flat: the (n, h+8, w+8, 32) reflect-halo
+    buffer (flat or shaped); wpacked: engine.pack_final_stream; bias: >= 3 fp32 values on the device; out (n,3,h,w) fp32."""
+    assert act_flat.numel() >= n * (h + 8) * (w + 8) * 32 and act_flat.dtype == wpacked.dtype and wpacked.numel() == 9 * 2 * 2 * 32 * 8
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, 3, h, w) and bias.dtype == torch.float32
+    dev, st = _ctx(act_flat)
+    check(lib.fnst_finalconv_tc(_ptr(act_flat), _ptr(wpacked), _ptr(bias), _ptr(out), n, h, w, dt(act_flat.dtype), dev, st),
+          "finalconv_tc")
+    _count()
+
+
 def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, pad: int,
                pad_mode: int, relu: bool, out: torch.Tensor, stats: Optional[torch.Tensor]) -> None:
     n, c, h, w = x.shape

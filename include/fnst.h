@@ -107,6 +107,18 @@ int fnst_device_supports_tc(int device);
  */
 int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream);
 
+/*
+ * final_conv forward on tensor cores as a row-streaming kernel: ConvLayer(32, 3, kernel=9) (models/model.py:47,64-65).
+ *   act      [n][h+8][w+8][32] fp16/bf16 NHWC halo buffer (reflected border written by fnst_inorm_apply, pad 4)
+ *   wpacked  [9 kw][2 channel halves][2 k-chunks][32 rows = kh*3+o, 27 used][8 channels] of the same element type
+ *            (18 KB; engine.pack_final_stream)
+ *   bias3    the three biases (device, fp32);  out [n][3][h][w] fp32 NCHW.
+ * Each input row is loaded into shared memory once (un-swizzled core-matrix layout) and the nine horizontal taps are
+ * the same buffer at start addresses 16 bytes apart; the nine-row sum runs over a TMEM ring in the epilogue.
+ */
+int fnst_finalconv_tc(const void* act, const void* wpacked, const float* bias3, float* out, int n, int h, int w,
+                      int dtype, int device, void* stream);
+
 /* Same operator on CUDA cores with fp32 accumulation (any dtype); the fp32-accurate path. */
 int fnst_conv_simt(const fnst_conv_desc* d, int device, void* stream);
 

@@ -156,6 +156,14 @@ def nchw_to_nhwc(x, dtype):
     return x.permute(0, 2, 3, 1).to(dtype).contiguous()
 
 
+def finalconv_stream(act_flat, n, h, w, wpacked, bias, out):
+    """fnst_finalconv_tc: decode the operand image back to OIHW and convolve the halo buffer (valid 9x9)."""
+    act = act_flat.reshape(-1)[: n * (h + 8) * (w + 8) * 32].view(n, h + 8, w + 8, 32).double()
+    b = wpacked.view(9, 2, 2, 32, 8).double()                                   # (kw, half, chunk, row, e)
+    wt = b[:, :, :, :27, :].permute(3, 1, 2, 4, 0).reshape(9, 3, 32, 9).permute(1, 2, 0, 3)   # (o, c, kh, kw)
+    out.copy_(F.conv2d(act.permute(0, 3, 1, 2), wt, bias[:3].double()))
+
+
 def gather_pack(key, layout_fn, src, out_dtype):
     return layout_fn(src.detach().double()).to(out_dtype)
 
@@ -166,5 +174,5 @@ def require_tensor_cores(device):
 
 def install(monkeypatch, ops_module):
     """Substitute every operator of `ops_module` by its emulation."""
-    for name in ("require_tensor_cores", "conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc", "gather_pack"):
+    for name in ("require_tensor_cores", "conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc", "gather_pack", "finalconv_stream"):
         monkeypatch.setattr(ops_module, name, globals()[name])

@@ -1,0 +1,111 @@
+"""GPU tests of the B200-specific execution features added on top of the operator set: CTA-pair (cta_group::2)
+gather-GEMM, the row-streaming final_conv kernel, single-kernel weight re-layouts, programmatic dependent launch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import stylenet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from fast_neural_style_transfer_b200 import engine, ops, _lib, backward
+    from fast_neural_style_transfer_b200.ops import ConvSpec
+
+DEV = "cuda"
+
+
+def knob(name, value):
+    _lib.check(_lib.lib.fnst_set_tuning(name.encode(), int(value)), "set_tuning")
+
+
+@pytest.fixture
+def restore_knobs():
+    yield
+    for k, v in (("conv_block_n", 0), ("conv_pair", 1), ("pdl", 1), ("dbg_mode", 0)):
+        knob(k, v)
+
+
+def _conv(B, hw, cin, cout, block_n, pair, epilogue=0, taps=None, n_gemm=None, dt=torch.float16):
+    torch.manual_seed(0)
+    taps = taps or engine.taps_kxk(3)
+    n_gemm = n_gemm or cout
+    pad = 2 if len(taps) == 9 else 1
+    a = torch.randn((B, hw + pad, hw + pad, cin), device=DEV).to(dt)
+    wt = (torch.randn((n_gemm, len(taps) * cin), device=DEV) * 0.05).to(dt)
+    shape = (B, 2 * hw, 2 * hw, cout) if epilogue == _lib.EPI_D2S else (B, hw, hw, cout)
+    out = torch.zeros(shape, dtype=dt, device=DEV)
+    st = torch.zeros((B, cout, 2), dtype=torch.float32, device=DEV)
+    knob("conv_block_n", block_n)
+    knob("conv_pair", pair)
+    ops.conv_gather(ConvSpec(taps, cin, wt, n_gemm, cout, epilogue=epilogue), a, tuple(a.shape), engine._nhwc_strides(a), out, (hw, hw), st, True)
+    torch.cuda.synchronize()
+    return out, st
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=4, hw=64, cin=256, cout=256, block_n=256),
+    dict(B=3, hw=24, cin=64, cout=128, block_n=128),                       # odd tile count: the pair's phantom tile, ragged edges
+    dict(B=2, hw=32, cin=256, cout=64, block_n=256, epilogue=1, n_gemm=256),   # depth-to-space epilogue (ConvTranspose2d)
+    dict(B=5, hw=17, cin=64, cout=256, block_n=256, dt=torch.bfloat16),
+])
+def test_cta_pair_matches_single_cta(cfg, restore_knobs):
+    """cta_group::2 (two SMs, M = 256) and cta_group::1 run the same K order per output element: outputs agree bit for bit;
+    the InstanceNorm statistics differ only by the order of their fp32 atomics."""
+    cfg = dict(cfg)
+    if cfg.get("epilogue") == 1:
+        cfg["taps"] = engine.TAPS_2X2
+    o0, s0 = _conv(pair=0, **cfg)
+    o1, s1 = _conv(pair=2, **cfg)
+    assert torch.equal(o0, o1)
+    assert float(((s0 - s1).abs() / (s0.abs() + 1)).max()) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 256), (3, 100, 131), (5, 17, 9), (1, 270, 480)])
+def test_finalconv_stream_matches_conv2d(shape):
+    """fnst_finalconv_tc (models/model.py:47 final_conv on the reflect-halo buffer) vs torch conv2d on the same fp16 operands."""
+    B, H, W = shape
+    torch.manual_seed(1)
+    act = torch.randn((B, H + 8, W + 8, 32), device=DEV).half()
+    w = torch.randn((3, 32, 9, 9), device=DEV) * 0.05
+    bias = torch.zeros(16, device=DEV)
+    bias[:3] = torch.tensor([0.1, -0.2, 0.3], device=DEV)
+    y = torch.full((B, 3, H, W), float("nan"), device=DEV)
+    ops.finalconv_stream(act, B, H, W, engine.pack_final_stream(w, torch.float16), bias, y)
+    ref = F.conv2d(act.float().permute(0, 3, 1, 2), w.half().float(), bias[:3])
+    assert float((y - ref).norm() / ref.norm()) < 5e-5          # fp32 accumulation of identical fp16 products
+
+
+def test_gather_pack_equals_layout_function():
+    """ops.gather_pack runs a pure re-layout as one gather kernel: must equal the layout function applied directly."""
+    torch.manual_seed(2)
+    w = torch.randn((256, 64, 3, 3), device=DEV)
+    got = ops.gather_pack("convT", lambda t: engine.pack_conv_transpose(t, torch.float64), w, torch.bfloat16)
+    assert torch.equal(got, engine.pack_conv_transpose(w, torch.bfloat16))
+    got = ops.gather_pack("s2d_dgrad", lambda t: backward.pack_dgrad_s2d(t, torch.float64), w, torch.float32)
+    assert torch.equal(got, backward.pack_dgrad_s2d(w, torch.float32))
+    wf = torch.randn((3, 32, 9, 9), device=DEV)
+    got = ops.gather_pack("final_stream", lambda t: engine.pack_final_stream(t, torch.float64), wf, torch.float16)
+    assert torch.equal(got, engine.pack_final_stream(wf, torch.float16))
+
+
+def test_forward_identical_with_and_without_pdl(restore_knobs):
+    """Programmatic dependent launch only changes when kernels start, never what they read: bit-identical network output."""
+    p = {k: v.to(DEV) for k, v in O.make_net_params(seed=0).items()}
+    x = O.make_image(2, 64, 96, seed=5).to(DEV)
+    plan = engine.StyleNetPlan("fp16").pack(p)
+    outs = []
+    for pdl in (0, 1):
+        knob("pdl", pdl)
+        outs.append(plan.forward(x).clone())
+        torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) or float((outs[0] - outs[1]).abs().max()) < 1e-3   # statistics atomics reorder
+
+
+def test_zero_arena_semantics():
+    a = ops.ZeroArena(64, DEV)
+    t1, t2 = a.take(2, 3, 2), a.take(5)
+    assert t1.shape == (2, 3, 2) and t2.shape == (5,) and float(t1.abs().sum() + t2.abs().sum()) == 0.0
+    assert t1.data_ptr() % 16 == 0 and t2.data_ptr() % 16 == 0
+    with pytest.raises(RuntimeError):
+        a.take(64)
