@@ -288,7 +288,9 @@ class StyleNetPlan:
         # other directly on the stream (programmatic dependent launch chains them; a fill in between would not)
         Hp, Wp = H1 + 2, W1 + 2
         Hs, Ws = _half_up(Hp), _half_up(Wp)
-        buf2 = torch.zeros((B, Hs, Ws, 256), dtype=dt, device=dev)
+        # (the space-to-depth buffer is written completely by inorm_apply when the padded extent is even; with an odd
+        # extent the last half-filled row / column of phases must read as zero)
+        buf2 = (torch.empty if Hp % 2 == 0 and Wp % 2 == 0 else torch.zeros)((B, Hs, Ws, 256), dtype=dt, device=dev)
         Hq, Wq = H4 + 8, W4 + 8
         flat = torch.empty(B * Hq * Wq * 32 + 128, dtype=dt, device=dev)   # slack: paired / 4-pixel window views
         flat[-128:].zero_()

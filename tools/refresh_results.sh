@@ -6,9 +6,4 @@ for WL in infer256 infer1080 infer1080_b1 infer256_b1; do python bench.py --work
 python bench.py --workload infer256_b1 --precision fp16x3 --steps 20 --no-cpu-baseline > gpurun_out/bench_infer256_b1_fp16x3.json 2>/dev/null; echo "x3 rc=$?"
 python bench.py --workload infer256_b1 --precision fp32 --steps 20 --no-cpu-baseline > gpurun_out/bench_infer256_b1_fp32.json 2>/dev/null; echo "fp32 rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_train.json; echo "ref rc=$?"
-CMD="python bench.py --workload train --steps 2 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/plain_train.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 1400 --csv --log-file gpurun_out/launches_train.csv $CMD > gpurun_out/ncu_train.log 2>&1; echo "ncu train rc=$?"
-CMD="python bench.py --workload infer256 --steps 2 --warmup 3 --no-cpu-baseline"
-$CMD > gpurun_out/plain_infer.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_infer256.csv $CMD > gpurun_out/ncu_infer.log 2>&1; echo "ncu infer rc=$?"
+bash tools/launch_lists.sh
