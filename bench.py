@@ -249,6 +249,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("FNST_BENCH_WORKLOAD", "train"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32", "fp16x3"])
+    ap.add_argument("--optimizer", default="fnst", choices=["fnst", "torch"],
+                    help="train workload: clip_grad_norm_ + Adam on libfnst's multi-tensor kernels (default) or torch's foreach "
+                         "implementations (A/B only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2-flush", action="store_true", help="write a 256 MB buffer between timed iterations (small workloads)")
     args = ap.parse_args()
@@ -263,14 +266,14 @@ def main():
     torch.cuda.set_device(dev)
     args.warmup = max(args.warmup, 3)
 
-    from oracle import stylenet_oracle as O
+    import bench_data
     from fast_neural_style_transfer_b200 import ops
     sys.path.insert(0, os.path.join(ROOT, "fast_neural_style_transfer_b200", "dropin"))
     from models.model import StyleTransferNet
 
     peaks = load_peaks()
     net = StyleTransferNet()
-    net.load_state_dict(O.make_net_params(seed=0))
+    net.load_state_dict(bench_data.net_state_dict(seed=0))
     net = net.to(dev).eval()
     net.precision = args.precision
 

@@ -16,29 +16,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
 def run(args, wl, net, rank, world, dev, peaks):
-    from oracle import stylenet_oracle as O
+    import bench_data
     from fast_neural_style_transfer_b200 import ops, parallel
+    from fast_neural_style_transfer_b200 import optim as fnst_optim
     from models.vgg19_net import VGG19
     from losses import losses as L
 
     bsz, h, w = wl["batch"], wl["h"], wl["w"]
     vgg = VGG19()
-    vgg.load_state_dict(O.make_vgg_params(seed=1))
+    vgg.load_state_dict(bench_data.vgg_state_dict(seed=1))
     vgg = vgg.to(dev).eval()
     vgg.precision = "fp32" if args.precision == "fp32" else "bf16"
     for p in vgg.parameters():
         p.requires_grad = False
     net.train()
-    style = O.make_image(1, h, w, seed=4321, normalized=True).to(dev)
+    style = bench_data.image_batch(1, h, w, seed=4321, normalized=True).to(dev)
     with torch.no_grad():
         targets = [L.gram_matrix(f).squeeze(0).detach() for f in vgg(style)]           # train.py:25-37
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    # train.py:135-139 / :203: same names and arguments, libfnst multi-tensor kernels unless --optimizer torch
+    adam_cls, clip_fn = ((fnst_optim.Adam, fnst_optim.clip_grad_norm_) if args.optimizer == "fnst"
+                         else (torch.optim.Adam, torch.nn.utils.clip_grad_norm_))
+    opt = adam_cls(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=80000, eta_min=1e-7)
     dp = parallel.GradientAllReduce(net, world) if world > 1 else None
     torch.manual_seed(1000 + rank)                                                      # per-rank dropout streams
     g = torch.Generator().manual_seed(1234 + rank)
     n_host = 4
-    host_batches = [O.make_image(bsz, h, w, seed=1234 + 17 * rank + i, normalized=True).pin_memory() for i in range(n_host)]
+    host_batches = [bench_data.image_batch(bsz, h, w, seed=1234 + 17 * rank + i, normalized=True).pin_memory() for i in range(n_host)]
     dev_batches = [b.to(dev) for b in host_batches]
     tv_scale = 1.0 / world          # TV is a batch mean, content/style are batch sums: SUM all-reduce
 
@@ -57,7 +61,7 @@ def run(args, wl, net, rank, world, dev, peaks):
         total.backward()
         if dp is not None:
             dp.all_reduce()
-        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
+        clip_fn(net.parameters(), max_norm=1.0)
         opt.step()
         sched.step()
         if read_losses:
@@ -103,6 +107,7 @@ def run(args, wl, net, rank, world, dev, peaks):
             "dtype": {"fp16": "f16 fwd / bf16 grads", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": "train", "desc": wl["desc"], "per_gpu_batch": bsz, "image": [h, w],
                        "optimizer": "clip_grad_norm_(1.0) + Adam(lr 1e-3, wd 1e-5) + CosineAnnealingLR",
+                       "optimizer_impl": "libfnst multi-tensor kernels" if args.optimizer == "fnst" else "torch foreach",
                        "loss_weights": [1000.0, 1, 10], "parallelism": f"dp{world}" if world > 1 else "single",
                        "value_note": "global steps/s x n_gpus = per-GPU-batch steps processed per second (weak scaling)",
                        "l2": "per-step activations (>1 GB) exceed the 126 MB L2; 4 rotating input batches"},

@@ -180,8 +180,10 @@ struct HaloLayout {
 // Pass 1.  Block = (row group, image); thread = (8-channel group cg, pixel lane pl).  Per-channel constants are
 // computed once per block into shared memory (one channel per thread) instead of 8 channels x 5 scalars per thread;
 // the per-(n,c) partial sums go lane -> smem table -> one global atomic per channel per block.
-template <typename TA, typename TG>
-__global__ void __launch_bounds__(256) inorm_bwd_reduce_kernel(const TG* __restrict__ gsrc, const TG* __restrict__ extra,
+// Two blocks per SM for the 16-bit variants (128 registers; 140 unconstrained = one block per SM = 8 warps, which ncu
+// showed latency-bound on long-scoreboard stalls with the 256-block batch-4 grid running as 1.73 waves).
+template <typename TA, typename TG, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS) inorm_bwd_reduce_kernel(const TG* __restrict__ gsrc, const TG* __restrict__ extra,
                                                                const TA* __restrict__ raw, const float* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                const float* __restrict__ drop, TG* __restrict__ gy,
@@ -584,7 +586,10 @@ extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const 
   const size_t smem = sizeof(float) * (5 * (size_t)c + (size_t)(256 / (c / 8)) * 2 * c);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
-      launch_pdl(inorm_bwd_reduce_kernel<TA, TG>, dim3(grid), dim3(256), smem, st,
+      // two resident blocks per SM for the 16-bit variants (tuning knob inorm_bwd_blocks = 1 restores the unconstrained build)
+      auto kern = (sizeof(TA) + sizeof(TG) <= 4 && tuning().inorm_bwd_blocks >= 2) ? inorm_bwd_reduce_kernel<TA, TG, 2>
+                                                                                    : inorm_bwd_reduce_kernel<TA, TG, 1>;
+      launch_pdl(kern, dim3(grid), dim3(256), smem, st,
           reinterpret_cast<const TG*>(gsrc), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(raw), stats, gamma,
           beta, drop, reinterpret_cast<TG*>(gy), sums, dgb, L, relu, eps, rpb);
     });

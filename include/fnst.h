@@ -264,6 +264,34 @@ int fnst_gather_cast(const void* src, int src_dtype, const int32_t* idx, void* o
 /* out[c] = sum over n,h,w of x[n,c,h,w] (fp32 NCHW); final_conv bias gradient. */
 int fnst_channel_sum(const float* x, int n, int c, int hw, float* out, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer tail of the training step (train.py:203-205): torch.nn.utils.clip_grad_norm_ and
+ * torch.optim.Adam(betas, eps, weight_decay = coupled L2, amsgrad=False) as multi-tensor kernels over the 58
+ * parameter tensors.  Tensor lists are HOST arrays of n device pointers to contiguous fp32 tensors of numels[i]
+ * elements (1 <= numels[i] < 2^31); any n (64 tensors per launch).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Bytes of the device workspace of fnst_grad_norm (8-byte aligned; zeroed ONCE by the caller at allocation: the kernel
+ * leaves it zeroed again at the end of every call). */
+int64_t fnst_grad_norm_workspace_bytes(void);
+
+/* clip_grad_norm_ (train.py:203), part 1: norm_coef[0] = total 2-norm of all gradients (fp64 accumulation),
+ * norm_coef[1] = min(1, max_norm / (norm + 1e-6)) -- torch's clip coefficient.  No host synchronisation. */
+int fnst_grad_norm(void* const* grads, const int64_t* numels, int n, void* workspace, float max_norm, float* norm_coef,
+                   int device, void* stream);
+
+/* clip_grad_norm_, part 2: g *= coef[0] in place for every gradient (coef on the device, e.g. norm_coef + 1). */
+int fnst_grad_scale(void* const* grads, const int64_t* numels, int n, const float* coef, int device, void* stream);
+
+/* One Adam step (train.py:205 with the optimizer of train.py:135-139), the arithmetic of torch.optim.Adam:
+ *   g = grad_scale[0] * g (if grad_scale != NULL: clip fused into the update);   g += weight_decay * p;
+ *   m += (1 - beta1) * (g - m);   v = beta2 * v + (1 - beta2) * g * g;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).
+ * step counts from 1.  params / exp_avg / exp_avg_sq are updated in place; grads are only read. */
+int fnst_adam_step(void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                   const int64_t* numels, int n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                   int64_t step, const float* grad_scale, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,7 +72,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     from fast_neural_style_transfer_b200 import _lib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     header = open(os.path.join(root, "include", "fnst.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(fnst_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(fnst_\w+)\s*\(", header, flags=re.M))
     assert len(declared) >= 25
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:

@@ -153,7 +153,16 @@ def test_loss_functions_backward_standalone(dropin):
     assert rel_l2(x.grad, xr.grad) < 1e-5
 
 
-def test_training_loop_reduces_loss_and_survives_checkpoint_reload(dropin):
+def _optimizer_tail(impl):
+    """(Adam class, clip_grad_norm_) of train.py:135-139 / :203 -- torch's, or the drop-in's multi-tensor kernels."""
+    if impl == "torch":
+        return torch.optim.Adam, torch.nn.utils.clip_grad_norm_
+    from fast_neural_style_transfer_b200 import optim as fo
+    return fo.Adam, fo.clip_grad_norm_
+
+
+@pytest.mark.parametrize("opt_impl", ["torch", "fnst"])
+def test_training_loop_reduces_loss_and_survives_checkpoint_reload(dropin, opt_impl):
     """60 optimizer steps of the reference's loop body on the drop-in (CUDA-graph path: forward incl. weight re-pack,
     backward, Adam in place): the loss must fall, stay finite, and a state_dict round trip in the middle (the
     reference's checkpoint resume, train.py:39-66) must be picked up by the captured graphs."""
@@ -164,7 +173,8 @@ def test_training_loop_reduces_loss_and_survives_checkpoint_reload(dropin):
     content = O.make_image(2, 64, 64, seed=5, normalized=True).to(DEV)
     with torch.no_grad():
         targets = [ll.gram_matrix(f).squeeze(0) for f in vgg(O.make_image(1, 64, 64, seed=6, normalized=True).to(DEV))]
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    adam, clip = _optimizer_tail(opt_impl)
+    opt = adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
     losses = []
     for it in range(60):
         y = torch.clamp(net(content), -3, 3)
@@ -174,7 +184,7 @@ def test_training_loop_reduces_loss_and_survives_checkpoint_reload(dropin):
         total = 1000.0 * ll.content_loss(sf, cf) + ll.style_loss(sf, targets) + 10 * ll.total_variation_loss(y)
         assert torch.isfinite(total)
         opt.zero_grad(); total.backward()
-        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
+        clip(net.parameters(), max_norm=1.0)
         opt.step()
         losses.append(float(total))
         if it == 30:                                  # checkpoint round trip (in-place load: graphs must see it)
@@ -187,7 +197,8 @@ def test_training_loop_reduces_loss_and_survives_checkpoint_reload(dropin):
     assert min(losses[35:]) < min(losses[:25])        # keeps improving after the reload
 
 
-def test_first_optimizer_steps_follow_the_oracle(dropin):
+@pytest.mark.parametrize("opt_impl", ["torch", "fnst"])
+def test_first_optimizer_steps_follow_the_oracle(dropin, opt_impl):
     """Three full steps (loss -> backward -> clip -> Adam) on the fp32 path vs the oracle's own loop, eval mode
     (no dropout) so both see identical arithmetic; trajectories are chaotic later, so only three."""
     mm, mv, ll = dropin
@@ -200,7 +211,8 @@ def test_first_optimizer_steps_follow_the_oracle(dropin):
     with torch.no_grad():
         targets = [ll.gram_matrix(f).squeeze(0) for f in vgg(sty.to(DEV))]
     ref_targets = O.style_targets(vp, sty)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    adam, clip = _optimizer_tail(opt_impl)
+    opt = adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
     ref_params, ref_state = {k: v.clone() for k, v in p.items()}, {}
     x = content.to(DEV)
     for step in range(1, 4):
@@ -210,7 +222,7 @@ def test_first_optimizer_steps_follow_the_oracle(dropin):
         sf = vgg(y)
         total = 1000.0 * ll.content_loss(sf, cf) + ll.style_loss(sf, targets) + 10 * ll.total_variation_loss(y)
         opt.zero_grad(); total.backward()
-        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
+        clip(net.parameters(), max_norm=1.0)
         opt.step()
         rl, rg = O.loss_and_grads(ref_params, vp, content, ref_targets, None)
         O.clip_and_adam(ref_params, rg, ref_state, step=step)

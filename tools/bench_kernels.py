@@ -114,6 +114,28 @@ def case_inorm_bwd(B, sets, which, hw=64, c=256):
     return run_apply, sets, B * hw * hw * c * (2 + 2 + 2)
 
 
+def case_optimizer_tail(sets, impl):
+    """clip_grad_norm_(1.0) + Adam.step over the 58 StyleTransferNet parameter tensors (train.py:203-205): libfnst's three
+    multi-tensor kernels vs torch's foreach implementations.  GPU time per whole tail; bytes = 4 + 8 + 28 per element."""
+    from fast_neural_style_transfer_b200 import optim as fo
+    sys.path.insert(0, os.path.join(ROOT, "fast_neural_style_transfer_b200", "dropin"))
+    from models.model import StyleTransferNet
+    nets = [StyleTransferNet().to(DEV) for _ in range(min(sets, 4))]
+    for net in nets:
+        for p in net.parameters():
+            p.grad = torch.randn_like(p) * 0.01
+    adam, clip = (fo.Adam, fo.clip_grad_norm_) if impl == "fnst" else (torch.optim.Adam, torch.nn.utils.clip_grad_norm_)
+    kw = dict(capturable=True) if impl == "torch" else {}
+    opts = [adam(net.parameters(), lr=1e-3, weight_decay=1e-5, **kw) for net in nets]
+    numel = sum(p.numel() for p in nets[0].parameters())
+
+    def run():
+        for net, opt in zip(nets, opts):
+            clip(net.parameters(), 1.0)
+            opt.step()
+    return run, len(nets), numel * 40.0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4)
@@ -150,10 +172,17 @@ def main():
     knob("wgrad_bn", 0)
     for pdl in (0, 1):
         rec("inorm_apply_256", lambda s: case_inorm_apply(B, s), pdl=pdl)
-    rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=1)
+    for blocks in (1, 2):
+        rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=1, inorm_bwd_blocks=blocks)
     rec("inorm_bwd_apply_256", lambda s: case_inorm_bwd(B, s, "apply"), pdl=1)
     rec("vgg_conv1_2_64", lambda s: case_conv3x3(B, s, dt=torch.bfloat16, hw=256, cin=64, cout=64), pdl=1)
     rec("vgg_conv2_2_128", lambda s: case_conv3x3(B, s, dt=torch.bfloat16, hw=128, cin=128, cout=128), pdl=1)
+    for impl in ("fnst", "torch"):
+        try:
+            rec("optimizer_tail_" + impl, lambda s, impl=impl: case_optimizer_tail(s, impl), pdl=1)
+        except Exception as e:                       # torch's foreach path may refuse stream capture: keep the other rows
+            print(json.dumps({"name": "optimizer_tail_" + impl, "error": repr(e)[:300]}), flush=True)
+            torch.cuda.synchronize()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(results, f, indent=1)
