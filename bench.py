@@ -240,6 +240,41 @@ def cpu_baseline(workload, wl):
     return {"value": units * reps / dt, "unit": wl["unit"], "cores": cores, "kind": "port", "sample": sample}
 
 
+def time_optimizer_tail(net, dev):
+    """Device time of the optimizer tail (clip_grad_norm_ + Adam.step, train.py:203-205) on libfnst's three multi-tensor
+    kernels: a twin of the network's 58 parameter tensors (the benchmark's own weights are not touched), captured as a
+    CUDA graph, replayed back to back, CUDA events on the launching stream.  The working set (p, g, m, v = 100 MB) fits
+    the 126 MB L2, so 256 MB are written between replays.  Returns (microseconds per tail, algorithmic bytes per tail:
+    4 + 8 + 28 bytes per parameter element)."""
+    from fast_neural_style_transfer_b200 import optim as fnst_optim
+    if os.environ.get("FNST_BENCH_NO_ROOFLINE"):
+        return float("nan"), 0.0
+    twins = [torch.nn.Parameter(p.detach().clone()) for p in net.parameters()]
+    for p in twins:
+        p.grad = torch.randn_like(p) * 1e-2
+    opt = fnst_optim.Adam(twins, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
+    def tail():
+        fnst_optim.clip_grad_norm_(twins, max_norm=1.0)
+        opt.step()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        tail()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        tail()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total, reps = 0.0, 20
+    for _ in range(reps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    return 1e3 * total / reps, 40.0 * sum(p.numel() for p in twins)
+
+
 # -------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()

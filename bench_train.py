@@ -98,6 +98,7 @@ def run(args, wl, net, rank, world, dev, peaks):
     ms_e2e = B.max_over_ranks(e0.elapsed_time(e1), world, dev)
 
     k_ms, flops, k_launches = B.time_dominant_kernel(net, bsz, h, w, dev)
+    tail_us, tail_bytes = B.time_optimizer_tail(net, dev) if args.optimizer == "fnst" else (float("nan"), 0.0)
     achieved = flops / (k_ms * 1e-3) / 1e12
     if rank != 0:
         return
@@ -123,6 +124,13 @@ def run(args, wl, net, rank, world, dev, peaks):
             "e2e": {"value": world * args.steps / (ms_e2e / 1e3), "unit": wl["unit"],
                     "h2d_bytes_per_step": host_batches[0].numel() * 4, "d2h_bytes_per_step": 16},
             "gpu_launches": launches, "clocks": clocks, "last_losses": losses}
+    if tail_bytes:
+        gbs = tail_bytes / (tail_us * 1e-6) / 1e9
+        line["roofline_optimizer_tail"] = {
+            "bound": "hbm", "kernel": "mt_sqnorm_kernel + mt_scale_kernel + mt_adam_kernel (clip_grad_norm_ + Adam.step, 58 tensors)",
+            "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None,
+            "peak_source": peaks["src"] + " (copy bandwidth)", "us_per_tail": tail_us, "tail_share_of_step": tail_us / 1e3 / (ms / args.steps),
+            "method": "three launches captured as one CUDA graph, replayed 20x with a 256 MB L2 flush in between, CUDA events"}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = B.cpu_baseline("train", wl)
     print(json.dumps(line), flush=True)

@@ -90,16 +90,27 @@ def test_gather_pack_equals_layout_function():
 
 
 def test_forward_identical_with_and_without_pdl(restore_knobs):
-    """Programmatic dependent launch only changes when kernels start, never what they read: bit-identical network output."""
+    """Programmatic dependent launch only changes when kernels start, never what they read.  The per-(n,c) InstanceNorm
+    statistics are fp32 atomics whose order differs from run to run; a last-bit change of a mean flips single fp16 roundings
+    that the following 3x3 convolutions spread, so two runs of the SAME configuration already differ in the low bits.  The
+    PDL-on / PDL-off difference must stay within that run-to-run noise class (a read-before-write race produces O(1) errors
+    in whole tiles)."""
     p = {k: v.to(DEV) for k, v in O.make_net_params(seed=0).items()}
     x = O.make_image(2, 64, 96, seed=5).to(DEV)
     plan = engine.StyleNetPlan("fp16").pack(p)
-    outs = []
-    for pdl in (0, 1):
+    outs = {}
+    for pdl in (0, 1, 0, 1):
         knob("pdl", pdl)
-        outs.append(plan.forward(x).clone())
+        outs.setdefault(pdl, []).append(plan.forward(x).clone())
         torch.cuda.synchronize()
-    assert torch.equal(outs[0], outs[1]) or float((outs[0] - outs[1]).abs().max()) < 1e-3   # statistics atomics reorder
+
+    def dist(a, b):
+        return float((a - b).abs().max()), float((a - b).norm() / b.norm())
+
+    noise_max = max(dist(outs[0][0], outs[0][1])[0], dist(outs[1][0], outs[1][1])[0])
+    d_max, d_rel = dist(outs[0][0], outs[1][0])
+    print(f"pdl on/off: max abs {d_max:.2e}, rel l2 {d_rel:.2e}; same-setting run-to-run max abs {noise_max:.2e}")
+    assert d_rel < 2e-3 and d_max < max(1e-2, 4 * noise_max)
 
 
 def test_zero_arena_semantics():
