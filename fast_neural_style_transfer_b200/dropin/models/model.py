@@ -154,8 +154,9 @@ class StyleTransferNet(nn.Module):
             if graphs.enabled() and not torch.cuda.is_current_stream_capturing():
                 # training step as two CUDA-graph replays (forward incl. weight re-pack, backward) per input shape
                 cache = self.__dict__.setdefault("_train_graphs", {})
-                # (the parameter addresses are part of the key: the captured graphs read the weights in place)
-                key = (self.precision, tuple(x.shape), x.device.index, self.training, params[0].data_ptr(), params[-1].data_ptr())
+                # (every parameter address is part of the key: the captured graphs read the weights in place, so a parameter
+                #  whose storage was replaced -- `.to()`, `p.data = ...` -- must not hit a stale capture)
+                key = (self.precision, tuple(x.shape), x.device.index, self.training, tuple(p.data_ptr() for p in params))
                 state = cache.get(key)
                 if state is None:
                     if len(cache) >= 4:

@@ -54,6 +54,10 @@ def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc, stats_ze
         v = v + spec.bias.double()[:c]
     if spec.relu:
         v = v.clamp_min(0)
+    if getattr(spec, "addend", None) is not None:          # dgrad epilogue extras: out = (acc + addend) * (mask > 0)
+        v = v + spec.addend.double()
+    if getattr(spec, "mask", None) is not None:
+        v = v * (spec.mask.double() > 0)
     if stats is not None:
         if not stats_zeroed:
             stats.zero_()                       # the call zeroes the accumulators unless the caller already did
@@ -152,8 +156,11 @@ def nhwc_to_nchw(x):
     return x.permute(0, 3, 1, 2).float().contiguous()
 
 
-def nchw_to_nhwc(x, dtype):
-    return x.permute(0, 2, 3, 1).to(dtype).contiguous()
+def nchw_to_nhwc(x, dtype, c_pad=None):
+    v = x.permute(0, 2, 3, 1)
+    if c_pad is not None and c_pad > v.shape[-1]:          # zero channels up to c_pad
+        v = F.pad(v, (0, c_pad - v.shape[-1]))
+    return v.to(dtype).contiguous()
 
 
 def finalconv_stream(act_flat, n, h, w, wpacked, bias, out):
@@ -176,3 +183,158 @@ def install(monkeypatch, ops_module):
     """Substitute every operator of `ops_module` by its emulation."""
     for name in ("require_tensor_cores", "conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc", "gather_pack", "finalconv_stream"):
         monkeypatch.setattr(ops_module, name, globals()[name])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Backward operators (include/fnst.h, "Backward operators" section)
+# ---------------------------------------------------------------------------------------------------------
+
+def wgrad(spec, a, a_dims, a_strides, g, out_hw, use_tc=False, g_strides=None, out=None, out_zeroed=False):
+    """dB[j][t*kc+c] = sum_{n,h,w} g[n,h,w,j] * A[n, h+h0+dh[t], w+w0+dw[t], c0[t]+c] (A reads as zero out of range)."""
+    n, ah, aw, ac = a_dims
+    sn, sh, sw = a_strides
+    oh, ow = out_hw
+    view = a.as_strided((n, ah, aw, ac), (sn, sh, sw, 1), a.storage_offset()).double()
+    if g_strides is None:
+        gv = g.double()
+    else:
+        gv = g.as_strided((n, oh, ow, spec.n_gemm), (g_strides[0], g_strides[1], g_strides[2], 1), g.storage_offset()).double()
+    blocks = []
+    for dh, dw, c0 in spec.taps:
+        hs = torch.arange(oh) + spec.h0 + dh
+        ws = torch.arange(ow) + spec.w0 + dw
+        hm = ((hs >= 0) & (hs < ah)).double().view(1, -1, 1, 1)
+        wm = ((ws >= 0) & (ws < aw)).double().view(1, 1, -1, 1)
+        patch = view[:, hs.clamp(0, ah - 1)][:, :, ws.clamp(0, aw - 1)][..., c0:c0 + spec.kc] * hm * wm
+        blocks.append(torch.einsum("nhwj,nhwc->jc", gv, patch))
+    db = torch.cat(blocks, dim=1).float()
+    if out is None:
+        return db
+    if out_zeroed:
+        out += db.view_as(out)
+    else:
+        out.copy_(db.view_as(out))
+    return out
+
+
+def conv_first_wgrad(x, g, k, stride, pad, pad_mode):
+    xp = F.pad(x.double(), (pad,) * 4, mode="reflect" if pad_mode == PAD_REFLECT else "constant")
+    n, c, _, _ = x.shape
+    _, ho, wo, co = g.shape
+    cols = F.unfold(xp, k, stride=stride).view(n, c * k * k, ho * wo)            # rows ordered (c, kh, kw) = tap-major
+    return torch.einsum("nkp,npo->ko", cols, g.double().reshape(n, ho * wo, co)).float()
+
+
+def _norm_consts(raw, stats, eps):
+    n, h, w, c = raw.shape
+    cnt = h * w
+    mean = stats[:, :, 0].double() / cnt
+    var = (stats[:, :, 1].double() / cnt - mean * mean).clamp_min(0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    xhat = (raw.double() - mean.view(n, 1, 1, c)) * rstd.view(n, 1, 1, c)
+    return mean, rstd, xhat
+
+
+def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=PAD_NONE, s2d=False, eps=1e-5,
+                     arena=None):
+    n, h, w, c = raw.shape
+    g = torch.zeros((n, h, w, c), dtype=torch.float64)
+    if gsrc is not None:
+        hp, wp = h + 2 * pad, w + 2 * pad
+        gs = gsrc.double()
+        if s2d:                                      # undo the space-to-depth layout written by inorm_apply
+            hs, ws = (hp + 1) // 2, (wp + 1) // 2
+            gs = gs.view(n, hs, ws, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * hs, 2 * ws, c)[:, :hp, :wp]
+        else:
+            gs = gs.view(n, hp, wp, c)
+        if pad and pad_mode == PAD_REFLECT:          # ReflectionPad2d backward: every halo position adds into its source
+            hi = _reflect(torch.arange(-pad, h + pad), h)
+            wi = _reflect(torch.arange(-pad, w + pad), w)
+            tmp = torch.zeros((n, h, wp, c), dtype=torch.float64).index_add_(1, hi, gs)
+            g = torch.zeros((n, h, w, c), dtype=torch.float64).index_add_(2, wi, tmp)
+        else:
+            g = gs[:, pad:pad + h, pad:pad + w].clone()
+    if extra is not None:
+        g = g + extra.double()
+    _, _, xhat = _norm_consts(raw, stats, eps)
+    if drop is not None:
+        g = g * drop.double().view(n, 1, 1, c)
+    if relu:
+        y = xhat * gamma.double() + beta.double()
+        g = g * (y > 0)
+    sums = arena.take(n, c, 2) if arena is not None else torch.zeros((n, c, 2), dtype=torch.float32)
+    gy = g.to(gdtype)
+    sums[:, :, 0] += g.sum(dim=(1, 2)).float()
+    sums[:, :, 1] += (g * xhat).sum(dim=(1, 2)).float()
+    return gy, sums
+
+
+def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps=1e-5):
+    n, h, w, c = raw.shape
+    cnt = h * w
+    _, rstd, xhat = _norm_consts(raw, stats, eps)
+    m1 = (sums[:, :, 0].double() / cnt).view(n, 1, 1, c)
+    m2 = (sums[:, :, 1].double() / cnt).view(n, 1, 1, c)
+    d = gamma.double() * rstd.view(n, 1, 1, c) * (gy.double() - m1 - xhat * m2)
+    if out_s2d:
+        d = d.view(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c)
+    dgb = torch.stack([sums[:, :, 1].sum(0), sums[:, :, 0].sum(0)]).float()
+    return d.to(gy.dtype), dgb
+
+
+def maxpool2_bwd(inp, gout, extra):
+    n, h, w, c = inp.shape
+    x = inp.double().permute(0, 3, 1, 2)
+    _, idx = F.max_pool2d(x, 2, 2, return_indices=True)                         # first maximal element (PyTorch tie rule)
+    route = F.max_unpool2d(gout.double().permute(0, 3, 1, 2), idx, 2, 2, output_size=(h, w)).permute(0, 2, 3, 1)
+    if extra is not None:
+        route = route + extra.double()
+    return (route * (inp.double() > 0)).to(gout.dtype)
+
+
+def relu_mask(g, extra, act):
+    v = g.double() if extra is None else g.double() + extra.double()
+    return (v * (act.double() > 0)).to(g.dtype)
+
+
+def sse_bwd(a, b, scale, gdtype, relu_mask=False):
+    d = 2.0 * scale.double()[0] * (a.double().reshape(-1, b.numel()) - b.double().reshape(1, -1))
+    d = d.view(a.shape)
+    if relu_mask:
+        d = d * (a.double() > 0)
+    return d.to(gdtype)
+
+
+def tv_bwd(img, scale):
+    x = img.double()
+    d = torch.zeros_like(x)
+    dh = x[:, :, 1:] - x[:, :, :-1]
+    dw = x[:, :, :, 1:] - x[:, :, :, :-1]
+    d[:, :, 1:] += 2 * dh
+    d[:, :, :-1] -= 2 * dh
+    d[:, :, :, 1:] += 2 * dw
+    d[:, :, :, :-1] -= 2 * dw
+    return (scale.double()[0] * d).float()
+
+
+def channel_sum(x):
+    return x.double().sum(dim=(0, 2, 3)).float()
+
+
+def cast(x, dtype):
+    return x.to(dtype)
+
+
+def gram_diff_sym(g, gt, scale, coef, dtype):
+    d = g.double() - gt.double().reshape(-1, g.shape[1], g.shape[2])
+    return (scale.double()[0] * coef * (d + d.transpose(1, 2))).to(dtype)
+
+
+def install_backward(monkeypatch, ops_module):
+    """Substitute the backward operators too, and make the stream plumbing of backward.py a no-op on CPU."""
+    install(monkeypatch, ops_module)
+    for name in ("wgrad", "conv_first_wgrad", "inorm_bwd_reduce", "inorm_bwd_apply", "maxpool2_bwd", "relu_mask", "sse_bwd",
+                 "tv_bwd", "channel_sum", "cast", "gram_diff_sym"):
+        monkeypatch.setattr(ops_module, name, globals()[name])
+    monkeypatch.setenv("FNST_WGRAD_STREAM", "0")                   # no side stream for the weight-gradient branch
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: None)
