@@ -87,3 +87,21 @@ def test_vgg_contract(dropin):
     vgg.load_state_dict(ref)
     assert all(not p.requires_grad for p in vgg.parameters())
     assert hasattr(vgg, "slice5")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present on this machine")
+def test_same_seed_gives_the_reference_weights(dropin):
+    """All 58 tensors: the drop-in constructed under a seed equals the unmodified reference module constructed under the
+    same seed (same nn modules in the same construction order, models/model.py:25-47) -- SURVEY 8b 'same default init'."""
+    import importlib.util
+    mm, _, _ = dropin
+    spec = importlib.util.spec_from_file_location("_reference_model", "/root/reference/models/model.py")
+    ref_mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_mod)
+    torch.manual_seed(123)
+    ref = ref_mod.StyleTransferNet().state_dict()
+    torch.manual_seed(123)
+    got = mm.StyleTransferNet().state_dict()
+    assert list(ref) == list(got) and len(ref) == 58
+    for k in ref:
+        assert torch.equal(ref[k], got[k]), k
