@@ -292,6 +292,23 @@ int fnst_adam_step(void* const* params, void* const* grads, void* const* exp_avg
                    const int64_t* numels, int n, double lr, double beta1, double beta2, double eps, double weight_decay,
                    int64_t step, const float* grad_scale, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input pre-processing (device side): the per-image transform of the reference's data pipeline,
+ *   transforms.Resize((out_h, out_w)) -> transforms.ToTensor() [-> transforms.Normalize(mean, std)]
+ * (train.py:92-102, inference.py:28-31, data/dataset.py:21-27).  On a PIL image, Resize is Pillow's
+ * Image.resize(BILINEAR): two-pass 8-bit resampling with 22-bit fixed-point weights; reproduced bit for bit.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* img_hwc: decoded RGB image, uint8 [in_h][in_w][3] with in_pitch_bytes per row, on the device.
+ * out_chw (optional): float32 [3][out_h][out_w] = u8/255, then (x-mean)/std if mean3/std3 (HOST float[3]) are given.
+ * out_u8_hwc (optional): the resized uint8 image [out_h][out_w][3].  Down-scaling factors up to 35 per axis. */
+int fnst_resize_to_tensor(const void* img_hwc, int in_h, int in_w, int64_t in_pitch_bytes, int out_h, int out_w,
+                          float* out_chw, void* out_u8_hwc, const float* mean3, const float* std3, int device, void* stream);
+
+/* Test hook (no device work): the resampling window of output index `index` along one axis, computed on the HOST by the
+ * same functions the kernel runs on the device.  Returns the window capacity ksize (> 0), or < 0 on bad arguments. */
+int fnst_resize_window_host(int in_size, int out_size, int index, int* first, int* len, int* kk, int kk_capacity);
+
 #ifdef __cplusplus
 }
 #endif
