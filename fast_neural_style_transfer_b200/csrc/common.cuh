@@ -59,6 +59,7 @@ struct Tuning {
   int pdl = 1;
   int conv_pair = 1;           // 1: CTA pairs (cta_group::2) where measured faster; 0: never; 2: whenever the column tile is >= 128
   int inorm_bwd_blocks = 2;    // resident blocks per SM the InstanceNorm-backward reduce kernel is compiled for (16-bit types): 1 or 2
+  int resize_staged = 0;       // fnst_resize_to_tensor: 1 = stage the tile's input span in shared memory with 32-bit loads
   int dbg_mode = 0;            // measurement only: bit 0 skips the per-chunk column sums, bit 1 the global statistics atomics
   unsigned long long* debug_buf = nullptr;   // measurement only: conv_tc writes per-CTA main-loop clocks / nanoseconds here
 };

@@ -22,6 +22,9 @@ int main() {
                           {8000, 31, 256, 256}, {1, 1, 256, 256}, {500, 333, 224, 320}, {64, 64, 1080, 1920}, {777, 1234, 40, 48}};
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   int failures = 0;
+  for (int staged = 0; staged <= 1; ++staged) {
+  fnst_set_tuning("resize_staged", staged);
+  printf("---- resize_staged = %d ----\n", staged);
   uint32_t seed = 12345u;
   for (const auto& c : cases) {
     const int ih = c[0], iw = c[1], oh = c[2], ow = c[3];
@@ -52,6 +55,7 @@ int main() {
     failures += (bad_u8 != 0) + bad_f + bad_f0;
     cudaFree(d_img); cudaFree(d_u8); cudaFree(d_f); cudaFree(d_f0);
   }
+  }
   // timing of the training-pipeline case (decoded 1080p frame -> normalised 256x256 tensor), device time per image
   {
     const int ih = 1080, iw = 1920, n = 64;
@@ -59,6 +63,8 @@ int main() {
     CK(cudaMalloc(&d_img, (size_t)n * ih * iw * 3)); CK(cudaMalloc(&d_f, (size_t)n * 3 * 256 * 256 * 4));
     CK(cudaMemset(d_img, 77, (size_t)n * ih * iw * 3));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int staged = 0; staged <= 1; ++staged) {
+    fnst_set_tuning("resize_staged", staged);
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(e0);
       for (int i = 0; i < n; ++i)
@@ -67,8 +73,9 @@ int main() {
     }
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     const double bytes = (double)ih * iw * 3 + 3.0 * 256 * 256 * 4;
-    printf("timing: 1080x1920 -> 256x256 normalised tensor: %.2f us/image, %.0f GB/s of algorithmic bytes (%d images, 398 MB > L2)\n",
-           1e3 * ms / n, bytes * n / (ms * 1e-3) / 1e9, n);
+    printf("timing (resize_staged = %d): 1080x1920 -> 256x256 normalised tensor: %.2f us/image, %.0f GB/s of algorithmic bytes (%d images, 398 MB > L2)\n",
+           staged, 1e3 * ms / n, bytes * n / (ms * 1e-3) / 1e9, n);
+    }
   }
   printf(failures ? "FAILED (%d)\n" : "ALL OK\n", failures);
   return failures ? 1 : 0;
