@@ -19,6 +19,8 @@
 // Algorithmic bytes per image: read in_h*in_w*3 once, write out_h*out_w*3*4 (float) -- HBM-bound by the input image.
 #include "common.cuh"
 
+#include <atomic>
+
 namespace fnst {
 
 constexpr int RS_TILE = 16;
@@ -99,9 +101,11 @@ struct ResizeParams {
 
 // STAGED: the input span of the tile is first copied to shared memory with coalesced 32-bit loads (chunks of stage_rows rows),
 // and the horizontal taps read shared memory; otherwise every tap is a byte load from global memory through L1.
-// Measured on B200 (profiles/r01_resize_selftest.log, 1080x1920 -> 256x256, both bit-exact): byte loads 13.7 us per image,
-// staged 26.3 us -- the extra 31 KB of shared memory per block and two more block-wide barriers cost more than the
-// uncoalesced L1 traffic they remove, so the un-staged form is the default (tuning knob resize_staged = 1 selects this one).
+// Measured on B200 (profiles/r01_resize_selftest.log, 1080x1920 -> 256x256, both bit-exact, 64 single-image launches back to
+// back): byte loads 13.7 us per image, staged 26.3 us.  Caveat: those are per-LAUNCH times of one-image kernels and include
+// the host's launch cost -- in that run the staged form also paid a cudaFuncSetAttribute call per launch (since made
+// once per device) -- so they bound the kernel times from above rather than rank the two forms; until both are re-measured
+// from a CUDA graph the verified un-staged form stays the default (tuning knob resize_staged = 1 selects this one).
 template <bool STAGED>
 __global__ void __launch_bounds__(RS_TILE * RS_TILE) resize_to_tensor_kernel(const ResizeParams p) {
   pdl_trigger();
@@ -284,7 +288,15 @@ extern "C" int fnst_resize_to_tensor(const void* img_hwc, int in_h, int in_w, in
   FNST_CHECK_ARG(smem <= 160 * 1024, "resize_to_tensor: strip of %d rows does not fit shared memory", p.strip_rows);
   FNST_CUDA(cudaSetDevice(device));
   auto kern = staged ? resize_to_tensor_kernel<true> : resize_to_tensor_kernel<false>;
-  if (smem > 32 * 1024) FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 32 * 1024) {
+    // opt in to > 48 KB once per (device, variant) with the largest size this entry point can ask for, not on every launch
+    static std::atomic<unsigned long long> opted[2] = {{0ull}, {0ull}};
+    const unsigned long long bit = 1ull << (device & 63);
+    if (!(opted[staged ? 1 : 0].load(std::memory_order_acquire) & bit)) {
+      FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      opted[staged ? 1 : 0].fetch_or(bit, std::memory_order_release);
+    }
+  }
   dim3 grid((out_w + RS_TILE - 1) / RS_TILE, (out_h + RS_TILE - 1) / RS_TILE);
   launch_pdl(kern, grid, dim3(RS_TILE * RS_TILE), smem, (cudaStream_t)stream, p);
   return launch_status("resize_to_tensor");
