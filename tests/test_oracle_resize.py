@@ -121,3 +121,21 @@ def test_preprocess_python_layer_with_emulated_abi(monkeypatch):
         P.resize_to_tensor(torch.zeros((8, 8, 4), dtype=torch.uint8))
     with pytest.raises(ValueError):
         P.resize_to_tensor(torch.zeros((8, 8, 3), dtype=torch.uint8), mean=MEAN)
+
+
+def test_oracle_matches_committed_pillow_digests(golden_dir):
+    """Same pin without needing Pillow at test time: digests generated by tests/golden/make_resize_golden.py."""
+    import hashlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_resize_golden import image
+    with open(os.path.join(golden_dir, "resize_pillow.json")) as f:
+        gold = json.load(f)
+    assert len(gold["cases"]) >= 8
+    for case in gold["cases"]:
+        (h, w), (oh, ow) = case["in"], case["out"]
+        small = R.resize_bilinear_u8(image(h, w), oh, ow)
+        assert hashlib.sha256(small.tobytes()).hexdigest() == case["u8_sha256"], case
+        assert hashlib.sha256(R.to_tensor(small, MEAN, STD).tobytes()).hexdigest() == case["tensor_sha256"], case
