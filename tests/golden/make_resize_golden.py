@@ -7,11 +7,6 @@ import json
 import os
 
 import numpy as np
-import PIL
-import torch
-import torchvision
-from PIL import Image
-from torchvision import transforms
 
 CASES = [(444, 444, 256, 256), (609, 800, 256, 256), (1080, 1920, 256, 256), (256, 300, 256, 256), (100, 120, 256, 256),
          (17, 23, 256, 256), (500, 333, 224, 320), (64, 64, 300, 500)]
@@ -23,6 +18,11 @@ def image(h, w):
 
 
 def main():
+    import PIL
+    import torch
+    import torchvision
+    from PIL import Image
+    from torchvision import transforms
     out = {"pillow": PIL.__version__, "torchvision": torchvision.__version__, "torch": torch.__version__, "cases": []}
     for h, w, oh, ow in CASES:
         img = image(h, w)
