@@ -1,0 +1,43 @@
+"""Every prototype of include/fnst.h against its ctypes binding in _lib.EXPORTS: same arity, same scalar widths, pointers where
+the header has pointers.  A mismatch here is a silent stack / register corruption at call time, so it is checked on CPU."""
+import ctypes as C
+import os
+import re
+
+from fast_neural_style_transfer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _prototypes():
+    text = open(os.path.join(ROOT, "include", "fnst.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)                       # drop comments
+    for m in re.finditer(r"^(int64_t|int|const char\*)\s+(fnst_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M | re.S):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        yield name, ret, params
+
+
+def _kind(param: str) -> str:
+    if "*" in param:
+        return "ptr"
+    base = param.rsplit(" ", 1)[0].replace("const ", "").strip() if " " in param else param
+    return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "float": "f32", "double": "f64"}[base]
+
+
+def _ckind(t) -> str:
+    if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+        return "ptr"
+    return {C.c_int: "i32", C.c_int32: "i32", C.c_int64: "i64", C.c_float: "f32", C.c_double: "f64"}[t]
+
+
+def test_header_prototypes_match_ctypes_bindings():
+    protos = {name: (ret, params) for name, ret, params in _prototypes()}
+    assert set(protos) == set(_lib.EXPORTS), set(protos) ^ set(_lib.EXPORTS)
+    for name, (ret, params) in protos.items():
+        restype, argtypes = _lib.EXPORTS[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for i, (p, t) in enumerate(zip(params, argtypes)):
+            assert _kind(p) == _ckind(t), (name, i, p, t)
+        want = {"int": C.c_int, "int64_t": C.c_int64, "const char*": C.c_char_p}[ret]
+        assert restype is want, (name, ret, restype)
