@@ -41,3 +41,20 @@ def test_header_prototypes_match_ctypes_bindings():
             assert _kind(p) == _ckind(t), (name, i, p, t)
         want = {"int": C.c_int, "int64_t": C.c_int64, "const char*": C.c_char_p}[ret]
         assert restype is want, (name, ret, restype)
+
+
+def test_conv_descriptor_layout_matches_the_c_struct(tmp_path):
+    """sizeof / offsetof of fnst_conv_desc as the C compiler lays it out == the ctypes.Structure mirror in _lib.ConvDesc."""
+    import subprocess
+    fields = [f[0] for f in _lib.ConvDesc._fields_]
+    src = tmp_path / "layout.c"
+    lines = "\n".join(f'  printf("{f} %zu\\n", offsetof(fnst_conv_desc, {f}));' for f in fields)
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "fnst.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(fnst_conv_desc));\n' + lines + "\n  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["sizeof"]) == C.sizeof(_lib.ConvDesc)
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.ConvDesc, f).offset, f
+    assert _lib.MAX_TAPS == 96 and "#define FNST_MAX_TAPS 96" in open(os.path.join(ROOT, "include", "fnst.h")).read()
