@@ -21,6 +21,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("FNST_VGG19_RANDOM_INIT", "1")     # BASELINE.json: no network, VGG-19 weights are random (seeded below)
 
 WORKLOADS = {
     # name: (global batch, H, W, metric, unit, algorithmic GFLOP per image of the dominant kernel launch (one 3x3 256->256 conv))

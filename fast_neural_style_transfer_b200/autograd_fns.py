@@ -3,6 +3,7 @@ whole-network functions for StyleTransferNet and the VGG-19 feature stack, and t
 reductions (Gram, squared error, total variation)."""
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -122,7 +123,7 @@ class _StyleLoss(torch.autograd.Function):
         scale = g.reshape(1).float()
         outs = []
         for f, gram_, t, coef in zip(ctx.fs, ctx.grams, ctx.targets, ctx.coefs):
-            s = ops.gram_diff_sym(gram_, t, scale, 2.0 * coef, f.dtype)     # d/dG of coef*sum(G-T)^2 is 2*coef*(G-T); dF = F (dG + dG^T)
+            s = ops.gram_diff_sym(gram_, t, scale, 2.0 * coef, backward.grad_dtype_of(f.dtype))     # d/dG of coef*sum(G-T)^2 is 2*coef*(G-T); dF = F (dG + dG^T)
             outs.append(backward.gram_apply(f, s).permute(0, 3, 1, 2))
         ctx.fs = ctx.grams = None
         return (None, None, None) + tuple(outs)
@@ -213,6 +214,38 @@ def vgg_apply(plan, x: torch.Tensor) -> List[torch.Tensor]:
 
 
 # ---- CUDA-graph variants (training): one replay for the forward, one for the backward ----------------------------
+#
+# A captured forward keeps its saved-for-backward tape in ONE set of static buffers, so only one forward of a given
+# graph can be "in flight" (forward done, backward still to come) at a time.  Every graphed forward therefore hands a
+# token to its autograd node and bumps the graph's generation: `busy()` tells the module that an earlier forward of
+# this graph is still waiting for its backward (gradient accumulation over micro-batches, vgg(a) + vgg(b), ...) -- the
+# module then runs the new forward through the eager per-call-tape Functions above -- and backward() refuses to run on
+# a tape that a later forward has overwritten.
+
+class _Token:
+    pass
+
+
+class _InFlight:
+    def __init__(self):
+        self.generation = 0
+        self._live = None
+
+    def busy(self) -> bool:
+        return self._live is not None and self._live() is not None
+
+    def begin(self, ctx) -> None:
+        self.generation += 1
+        ctx.generation = self.generation
+        ctx.token = _Token()
+        self._live = weakref.ref(ctx.token)
+
+    def check(self, ctx, what: str) -> None:
+        if ctx.generation != self.generation:
+            raise RuntimeError(f"{what}: the saved activations of this forward were overwritten by a later forward of the same "
+                               "CUDA graph before backward() ran (set FNST_CUDA_GRAPH=0 for unrestricted autograd semantics)")
+        ctx.token = None
+
 
 class StyleNetTrainGraph:
     """Forward (incl. weight re-pack) and backward of StyleTransferNet captured as two CUDA graphs for one input shape."""
@@ -225,6 +258,7 @@ class StyleNetTrainGraph:
         self.tape: dict = {}
         self.plan = None
         self.has_drop = drops is not None
+        self.in_flight = _InFlight()
 
         def fwd(x_, *drops_):
             self.tape.clear()
@@ -252,10 +286,12 @@ class _StyleNetGraphed(torch.autograd.Function):
     @staticmethod
     def forward(ctx, state, x, drops, *params):
         ctx.state = state
+        state.in_flight.begin(ctx)
         return state.forward(x.detach(), drops).clone()
 
     @staticmethod
     def backward(ctx, dy):
+        ctx.state.in_flight.check(ctx, "StyleTransferNet backward")
         return (None, None, None) + tuple(ctx.state.backward(dy.contiguous()))
 
 
@@ -271,6 +307,7 @@ class VGGGraph:
         self.plan = plan
         self.tape: dict = {}
         self.with_tape = with_tape
+        self.in_flight = _InFlight()
 
         def fwd(x_):
             self.tape.clear()
@@ -299,10 +336,12 @@ class _VGGGraphed(torch.autograd.Function):
     @staticmethod
     def forward(ctx, state, x):
         ctx.state = state
+        state.in_flight.begin(ctx)
         return state.forward(x.detach())
 
     @staticmethod
     def backward(ctx, *dfeats):
+        ctx.state.in_flight.check(ctx, "VGG19 backward")
         return None, ctx.state.backward(dfeats)
 
 

@@ -26,6 +26,12 @@ def grad_dtype(precision: str) -> torch.dtype:
     return torch.float32 if precision == "fp32" else torch.bfloat16
 
 
+def grad_dtype_of(act: torch.dtype) -> torch.dtype:
+    """Gradient element type for activations of type `act`: fp32 stays fp32; both 16-bit activation types carry bf16
+    gradients (fp16's range is too small for the un-normalised Gram / style gradients)."""
+    return torch.float32 if act == torch.float32 else torch.bfloat16
+
+
 def _neg(taps):
     return [(-dh, -dw, 0) for dh, dw, _ in taps]
 
@@ -314,8 +320,10 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 # -------------------------------------------------------------------------------------------------------
 
 def vgg_backward(plan: "engine.VGGPlan", tape: dict, dfeats: Sequence[Optional[torch.Tensor]]) -> torch.Tensor:
-    """dfeats: gradients of the five NHWC feature maps (None where unused).  Returns dx (B,3,H,W) fp32."""
-    gdt = plan.dtype
+    """dfeats: gradients of the five NHWC feature maps (None where unused).  Returns dx (B,3,H,W) fp32.
+    The gradient element type is independent of the activation type: bf16 on both tensor-core precisions, so the
+    drop-in's default pair (fp16 net + fp16 VGG) back-propagates without overflow."""
+    gdt = grad_dtype(plan.precision)
     tc = plan.use_tc
     taps9 = taps_kxk(3, origin=-1)
     dfe = [None if g is None else g.contiguous().to(gdt) for g in dfeats]
@@ -388,12 +396,15 @@ def vgg_backward(plan: "engine.VGGPlan", tape: dict, dfeats: Sequence[Optional[t
 
 def gram_backward(f: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
     """f NHWC (B,H,W,C); dg (B,C,C) fp32.  dF[p,i] = sum_j F[p,j] * (dG + dG^T)[i,j]: a 1x1 gather-GEMM with per-image weights."""
-    return gram_apply(f, (dg + dg.transpose(1, 2)).to(f.dtype).contiguous())
+    return gram_apply(f, (dg + dg.transpose(1, 2)).to(grad_dtype_of(f.dtype)).contiguous())
 
 
 def gram_apply(f: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
-    """dF[n] = F[n] S[n] for per-image symmetric factors S (B,C,C) in the feature dtype."""
+    """dF[n] = F[n] S[n] for per-image symmetric factors S (B,C,C) in the gradient dtype of the features (fp16
+    features are multiplied as bf16: kind::f16 MMAs take one 16-bit format, and the products exceed fp16's range)."""
     B, H, W, C = f.shape
+    if f.dtype != s.dtype:
+        f = ops.cast(f, s.dtype)
     out = torch.empty_like(f)
     use_tc = f.dtype != torch.float32 and C % 64 == 0
     spec = ConvSpec([(0, 0, 0)], C, s, C, C, per_image_weights=True)      # one launch, image n multiplies by s[n]
@@ -402,7 +413,7 @@ def gram_apply(f: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
 
 
 def sse_backward(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
-    return ops.sse_bwd(a, b, g.reshape(1).float(), a.dtype)
+    return ops.sse_bwd(a, b, g.reshape(1).float(), grad_dtype_of(a.dtype))
 
 
 def tv_backward(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:

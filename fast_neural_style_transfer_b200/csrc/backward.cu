@@ -535,7 +535,7 @@ using namespace fnst;
 
 extern "C" int fnst_wgrad_simt(const fnst_conv_desc* d, int g_dtype, int device, void* stream) {
   if (int r = validate_conv_desc(d)) return r;
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t ktot = (size_t)d->ntaps * d->kc;
   if (!(d->flags & FNST_DESC_PREZEROED)) FNST_CUDA(cudaMemsetAsync(d->out, 0, sizeof(float) * ktot * d->n_gemm, st));
@@ -553,7 +553,7 @@ extern "C" int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const 
   FNST_CHECK_ARG(x && g && dw, "conv_first_wgrad: null pointer");
   FNST_CHECK_ARG(c_out == 64 && k % 2 == 1 && k <= 9 && (stride == 1 || stride == 2), "conv_first_wgrad: unsupported configuration");
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   FNST_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * 3 * k * k * c_out, st));
   const int pdim = 7 * stride + k;
@@ -574,7 +574,7 @@ extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const 
                                      int pad, int pad_mode, int s2d, int prezeroed, int device, void* stream) {
   FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && gy && sums, "inorm_bwd_reduce: null pointer");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 1024 && 256 % (c / 8) == 0, "inorm_bwd_reduce: unsupported channel count %d", c);
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!prezeroed) {
     FNST_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, st));
@@ -603,7 +603,7 @@ extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float
   FNST_CHECK_ARG(gy && raw && stats && sums && gamma && draw, "inorm_bwd_apply: null pointer");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_apply: unsupported channel count %d", c);
   FNST_CHECK_ARG(!out_s2d || (h % 2 == 0 && w % 2 == 0), "inorm_bwd_apply: space-to-depth output needs even h, w");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   const int rpb = rows_per_block(h, n);
   dim3 grid((h + rpb - 1) / rpb, n);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
@@ -619,7 +619,7 @@ extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float
 extern "C" int fnst_maxpool2_bwd(const void* in, const void* gout, const void* extra, void* gin, int n, int h, int w, int c,
                                  int act_dtype, int g_dtype, int device, void* stream) {
   FNST_CHECK_ARG(in && gout && gin && c % 8 == 0 && h >= 2 && w >= 2, "maxpool2_bwd: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   const int64_t items = (int64_t)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
@@ -634,7 +634,7 @@ extern "C" int fnst_maxpool2_bwd(const void* in, const void* gout, const void* e
 extern "C" int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
                             const float* scale, void* da, int g_dtype, int relu_mask, int device, void* stream) {
   FNST_CHECK_ARG(a && b && scale && da && count > 0 && b_period > 0, "sse_bwd: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   FNST_DISPATCH_DTYPE(dtype_a, TA, {
     FNST_DISPATCH_DTYPE(dtype_b, TB, {
       FNST_DISPATCH_DTYPE(g_dtype, TG, {
@@ -649,7 +649,7 @@ extern "C" int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t
 extern "C" int fnst_relu_mask(const void* g, const void* extra, const void* act, void* out, int64_t count, int act_dtype,
                               int g_dtype, int device, void* stream) {
   FNST_CHECK_ARG(g && act && out && count > 0 && count % 8 == 0, "relu_mask: bad arguments (count must be a multiple of 8)");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
       launch_pdl(relu_mask_kernel<TA, TG>, dim3(grid_cap(count / 8)), dim3(256), 0, (cudaStream_t)stream, 
@@ -663,7 +663,7 @@ extern "C" int fnst_relu_mask(const void* g, const void* extra, const void* act,
 extern "C" int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c, int64_t gt_numel, const float* scale, float coef,
                                   void* s_out, int out_dtype, int device, void* stream) {
   FNST_CHECK_ARG(g && gt && scale && s_out && n > 0 && c > 0 && gt_numel > 0, "gram_diff_sym: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   const int64_t total = (int64_t)n * c * c;
   FNST_DISPATCH_DTYPE(out_dtype, TG, {
     launch_pdl(gram_diff_sym_kernel<TG>, dim3(grid_cap(total)), dim3(256), 0, (cudaStream_t)stream, g, gt, gt_numel, c, total, scale, coef,
@@ -674,14 +674,14 @@ extern "C" int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c,
 
 extern "C" int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream) {
   FNST_CHECK_ARG(img && scale && dimg && planes > 0 && h > 0 && w > 0, "tv_bwd: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   launch_pdl(tv_bwd_kernel, dim3(grid_cap((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w, scale, dimg);
   return launch_status("tv_bwd");
 }
 
 extern "C" int fnst_channel_sum(const float* x, int n, int c, int hw, float* out, int device, void* stream) {
   FNST_CHECK_ARG(x && out && n > 0 && c > 0 && hw > 0, "channel_sum: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   FNST_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * c, st));
   int chunks = (int)(((int64_t)n * hw + 256 * 16 - 1) / (256 * 16));

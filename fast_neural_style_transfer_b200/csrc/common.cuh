@@ -32,6 +32,25 @@ void set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+// Every entry point runs on the device the caller names (it may be called from autograd's backward thread, whose current
+// device is not the forward thread's); the caller's current device is restored when the entry point returns.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t enter(int device) {
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return e;
+    if (cur == device) return cudaSuccess;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) prev = cur;
+    return e;
+  }
+  ~DeviceGuard() { if (prev >= 0) (void)cudaSetDevice(prev); }
+};
+#define FNST_DEVICE(device)              \
+  ::fnst::DeviceGuard fnst_device_guard__; \
+  FNST_CUDA(fnst_device_guard__.enter(device))
+
 inline int launch_status(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

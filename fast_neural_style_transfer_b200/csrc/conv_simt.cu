@@ -159,7 +159,7 @@ using namespace fnst;
 extern "C" int fnst_conv_simt(const fnst_conv_desc* d, int device, void* stream) {
   if (int r = validate_conv_desc(d)) return r;
   FNST_CHECK_ARG(d->epilogue != FNST_EPI_ROWSUM9, "conv_simt: the ROWSUM9 epilogue exists on the tensor-core kernel only");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   if (d->stats && !(d->flags & FNST_DESC_PREZEROED)) FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
   dim3 grid(((d->out_w + 7) / 8) * ((d->out_h + 7) / 8) * d->out_n, (d->n_gemm + SB_N - 1) / SB_N);
@@ -282,7 +282,7 @@ extern "C" int fnst_conv_first(const float* x, int n, int h, int w, const float*
   if (pad_mode == FNST_PAD_REFLECT) FNST_CHECK_ARG(h > pad && w > pad, "conv_first: reflect pad %d needs h,w > pad", pad);
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   FNST_CHECK_ARG(ho > 0 && wo > 0, "conv_first: empty output");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   if (stats) FNST_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)n * c_out, st));
   const int pdim = 7 * stride + k;

@@ -148,6 +148,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_units = PAIR ? ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles : p.num_tiles;
 
   pdl_trigger();
+  // measurement only (fnst_set_debug_buffer): per-CTA timeline in globaltimer nanoseconds behind the 4 x 148 main-loop slots:
+  // [0] kernel entry, [1] set-up done (after griddepcontrol.wait), [2] first operand stage landed, [3] last MMA complete,
+  // [4] epilogue done (first epilogue warp), [5] after the final CTA barrier
+  unsigned long long* tl = p.dbg ? p.dbg + 4 * 148 + 8 * (PAIR ? (blockIdx.x >> 1) : blockIdx.x) : nullptr;
+  auto stamp = [&](int slot) {
+    if (tl) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[slot] = t; }
+  };
+  if (threadIdx.x == 0) stamp(0);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -162,6 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();          // set-up above overlapped the predecessor's tail; global memory is touched only from here on
+  if (threadIdx.x == 0) stamp(1);
 
   const int TW = 1 << p.tw_log2, TH = TC_BLOCK_M >> p.tw_log2;
   // unit -> (column tile, pixel tile of this CTA); a pair's phantom second tile (odd tile count) has m_tile == num_m_tiles:
@@ -246,6 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         unsigned long long* o = p.dbg + 4 * (PAIR ? (blockIdx.x >> 1) : blockIdx.x);
         o[0] = (unsigned long long)(clock64() - dbg_c0); o[1] = t1 - dbg_t0;
         o[2] = (unsigned long long)it * p.num_kblocks; o[3] = (unsigned long long)it;
+        tl[2] = dbg_t0; tl[3] = t1;
       }
       pdl_trigger_tail();      // all MMAs of this CTA are issued: let the next kernel launch under the epilogue
     }
@@ -404,8 +414,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
 
+  if (threadIdx.x == 64) stamp(4);
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();     // pair: neither CTA may leave while the other still signals / reads it
+  if (threadIdx.x == 0) stamp(5);
   if (warp == 1) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base); else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -466,7 +478,7 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
     FNST_CHECK_ARG(d->n_gemm == 32 && 9 * d->c_out <= 27 && !d->stats && !d->relu, "conv_tc: ROWSUM9 needs n_gemm == 32, c_out <= 3, no stats/relu");
     for (int t = 0; t < d->ntaps; ++t) FNST_CHECK_ARG(d->tap_dh[t] == 0, "conv_tc: ROWSUM9 taps must have dh == 0");
   }
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
 
   ConvTcParams p;

@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(256) gather_cast_kernel(const TI* __restrict__
 
 // uint8 HWC images <-> NCHW fp32 (inference pre/post-processing on the device, inference.py:28-31,52-60):
 //   u8 -> f32:  x[n,c,h,w] = (u8[n,h,w,c] / 255 - mean[c]) / std[c]        (mean = 0, std = 1: plain ToTensor)
-//   f32 -> u8:  u8[n,h,w,c] = round(clamp(y[n,c,h,w] * std[c] + mean[c], 0, 1) * 255)
+//   f32 -> u8:  u8[n,h,w,c] = trunc(clamp(y[n,c,h,w] * std[c] + mean[c], 0, 1) * 255)   (ToPILImage on a float tensor is
+//               pic.mul(255).byte(), i.e. truncation, inference.py:57-60)
 __global__ void __launch_bounds__(256) u8_to_nchw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t pixels,
                                                          int HW, float m0, float m1, float m2, float s0, float s1, float s2) {
   pdl_trigger();
@@ -302,9 +303,9 @@ __global__ void __launch_bounds__(256) nchw_to_u8_kernel(const float* __restrict
     const int64_t n = i / HW, p = i - n * HW;
     const float* y = in + n * 3 * (int64_t)HW + p;
     uint8_t* px = out + i * 3;
-    px[0] = (uint8_t)__float2int_rn(fminf(fmaxf(y[0] * s0 + m0, 0.f), 1.f) * 255.f);
-    px[1] = (uint8_t)__float2int_rn(fminf(fmaxf(y[HW] * s1 + m1, 0.f), 1.f) * 255.f);
-    px[2] = (uint8_t)__float2int_rn(fminf(fmaxf(y[2 * (int64_t)HW] * s2 + m2, 0.f), 1.f) * 255.f);
+    px[0] = (uint8_t)__float2int_rz(fminf(fmaxf(y[0] * s0 + m0, 0.f), 1.f) * 255.f);
+    px[1] = (uint8_t)__float2int_rz(fminf(fmaxf(y[HW] * s1 + m1, 0.f), 1.f) * 255.f);
+    px[2] = (uint8_t)__float2int_rz(fminf(fmaxf(y[2 * (int64_t)HW] * s2 + m2, 0.f), 1.f) * 255.f);
   }
 }
 
@@ -331,7 +332,7 @@ extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float
   FNST_CHECK_ARG(pad >= 0 && (pad == 0 || pad_mode == FNST_PAD_REFLECT || pad_mode == FNST_PAD_ZERO), "inorm_apply: bad pad mode");
   if (pad_mode == FNST_PAD_REFLECT) FNST_CHECK_ARG(h > pad && w > pad, "inorm_apply: reflect pad %d needs h,w > pad (got %dx%d)", pad, h, w);
   FNST_CHECK_ARG(!(s2d && res), "inorm_apply: residual with space-to-depth output unsupported");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   // several output rows per block once the grid is large enough to fill the GPU (amortises the per-thread
   // scale/shift set-up); single rows for small problems
   const int hp = h + 2 * pad;
@@ -356,7 +357,7 @@ extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float
 extern "C" int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int c, int dtype, int device, void* stream) {
   FNST_CHECK_ARG(in && out, "maxpool2: null pointer");
   FNST_CHECK_ARG(c % 8 == 0 && h >= 2 && w >= 2, "maxpool2: unsupported shape");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   const int64_t items = (int64_t)n * (h / 2) * (w / 2) * (c / 8);
   FNST_DISPATCH_DTYPE(dtype, T, {
     launch_pdl(maxpool2_kernel<T>, dim3(grid_for(items)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const T*>(in),
@@ -368,7 +369,7 @@ extern "C" int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int
 extern "C" int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
                         double* acc, int device, void* stream) {
   FNST_CHECK_ARG(a && b && acc && count > 0 && b_period > 0, "sse: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   FNST_DISPATCH_DTYPE(dtype_a, TA, {
     FNST_DISPATCH_DTYPE(dtype_b, TB, {
       launch_pdl(sse_kernel<TA, TB>, dim3(grid_for(count / 4)), dim3(256), 0, (cudaStream_t)stream, 
@@ -380,14 +381,14 @@ extern "C" int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_p
 
 extern "C" int fnst_tv(const float* img, int planes, int h, int w, double* acc, int device, void* stream) {
   FNST_CHECK_ARG(img && acc && planes > 0 && h > 0 && w > 0, "tv: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   launch_pdl(tv_kernel, dim3(grid_for((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w, acc);
   return launch_status("tv");
 }
 
 extern "C" int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w, int c, int dtype, int device, void* stream) {
   FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0, "nhwc_to_nchw: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   dim3 grid((h * w + 31) / 32, (c + 31) / 32, n);
   FNST_DISPATCH_DTYPE(dtype, T, { launch_pdl(transpose_kernel<T, true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, out, h * w, c, c); });
   return launch_status("nhwc_to_nchw");
@@ -395,7 +396,7 @@ extern "C" int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w
 
 extern "C" int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int c_pad, int dtype, int device, void* stream) {
   FNST_CHECK_ARG(in && out && n > 0 && h > 0 && w > 0 && c > 0 && c_pad >= c, "nchw_to_nhwc: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   dim3 grid((h * w + 31) / 32, (c_pad + 31) / 32, n);
   FNST_DISPATCH_DTYPE(dtype, T, { launch_pdl(transpose_kernel<T, false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, out, h * w, c, c_pad); });
   return launch_status("nchw_to_nhwc");
@@ -403,7 +404,7 @@ extern "C" int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w
 
 extern "C" int fnst_cast(const void* in, void* out, int64_t count, int in_dtype, int out_dtype, int device, void* stream) {
   FNST_CHECK_ARG(in && out && count > 0 && count % 8 == 0, "cast: bad arguments (count must be a multiple of 8)");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   FNST_DISPATCH_DTYPE(in_dtype, TI, {
     FNST_DISPATCH_DTYPE(out_dtype, TO, {
       launch_pdl(cast_kernel<TI, TO>, dim3(grid_for(count / 8)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const TI*>(in),
@@ -416,7 +417,7 @@ extern "C" int fnst_cast(const void* in, void* out, int64_t count, int in_dtype,
 extern "C" int fnst_gather_cast(const void* src, int src_dtype, const int32_t* idx, void* out, int out_dtype, int64_t count,
                                 int device, void* stream) {
   FNST_CHECK_ARG(src && idx && out && count > 0, "gather_cast: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   FNST_DISPATCH_DTYPE(src_dtype, TI, {
     FNST_DISPATCH_DTYPE(out_dtype, TO, {
       launch_pdl(gather_cast_kernel<TI, TO>, dim3(grid_for(count)), dim3(256), 0, (cudaStream_t)stream,
@@ -433,7 +434,7 @@ extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w
   FNST_CHECK_ARG((c_pad == 4 || c_pad == 8) && (dtype == FNST_F16 || dtype == FNST_BF16), "image_to_halo: c_pad must be 4 or 8, dtype fp16/bf16");
   FNST_CHECK_ARG(rows >= h + 2 * pad && pitch >= w + 2 * pad, "image_to_halo: buffer smaller than the padded image");
   if (pad_mode == FNST_PAD_REFLECT) FNST_CHECK_ARG(h > pad && w > pad, "image_to_halo: reflect pad %d needs h,w > pad", pad);
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   const int grid = grid_for((int64_t)n * rows * pitch);
   const int reflect = pad_mode == FNST_PAD_REFLECT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -450,7 +451,7 @@ extern "C" int fnst_image_to_halo(const float* x, void* out, int n, int h, int w
 extern "C" int fnst_u8_to_nchw(const void* in, float* out, int n, int h, int w, const float* mean3, const float* std3,
                                int device, void* stream) {
   FNST_CHECK_ARG(in && out && mean3 && std3 && n > 0 && h > 0 && w > 0, "u8_to_nchw: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   const int64_t pixels = (int64_t)n * h * w;
   launch_pdl(u8_to_nchw_kernel, dim3(grid_for(pixels)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const uint8_t*>(in), out, pixels, h * w,
                                                                          mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
@@ -460,7 +461,7 @@ extern "C" int fnst_u8_to_nchw(const void* in, float* out, int n, int h, int w, 
 extern "C" int fnst_nchw_to_u8(const float* in, void* out, int n, int h, int w, const float* mean3, const float* std3,
                                int device, void* stream) {
   FNST_CHECK_ARG(in && out && mean3 && std3 && n > 0 && h > 0 && w > 0, "nchw_to_u8: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   const int64_t pixels = (int64_t)n * h * w;
   launch_pdl(nchw_to_u8_kernel, dim3(grid_for(pixels)), dim3(256), 0, (cudaStream_t)stream, in, reinterpret_cast<uint8_t*>(out), pixels, h * w,
                                                                          mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);

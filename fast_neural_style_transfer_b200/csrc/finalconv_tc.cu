@@ -199,7 +199,7 @@ extern "C" int fnst_finalconv_tc(const void* act, const void* wpacked, const flo
                                  int dtype, int device, void* stream) {
   FNST_CHECK_ARG(act && wpacked && bias3 && out && n > 0 && h > 0 && w > 0, "finalconv_tc: bad arguments");
   FNST_CHECK_ARG(dtype == FNST_F16 || dtype == FNST_BF16, "finalconv_tc: activations must be fp16 or bf16");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   FinalTcParams p;
   memset(&p, 0, sizeof(p));

@@ -65,7 +65,7 @@ using namespace fnst;
 
 extern "C" int fnst_gram(const void* feat, float* out, int n, int hw, int c, int dtype, int use_tc, int device, void* stream) {
   FNST_CHECK_ARG(feat && out && n > 0 && hw > 0 && c > 0, "gram: bad arguments");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   FNST_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * c * c, st));
   if (use_tc) return gram_tc(feat, out, n, hw, c, dtype, device, st);

@@ -216,7 +216,7 @@ extern "C" int fnst_grad_norm(void* const* grads, const int64_t* numels, int n, 
   FNST_CHECK_ARG(workspace && norm_coef, "grad_norm: workspace / output is NULL");
   FNST_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7u) == 0, "grad_norm: workspace must be 8-byte aligned");
   FNST_CHECK_ARG(max_norm > 0.f, "grad_norm: max_norm must be positive");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total_blocks = 0;
   for (int i = 0; i < n; ++i) total_blocks += (numels[i] + MT_CHUNK - 1) / MT_CHUNK;
@@ -237,7 +237,7 @@ extern "C" int fnst_grad_norm(void* const* grads, const int64_t* numels, int n, 
 extern "C" int fnst_grad_scale(void* const* grads, const int64_t* numels, int n, const float* coef, int device, void* stream) {
   if (int rc = mt_check(grads, numels, n, "grad_scale")) return rc;
   FNST_CHECK_ARG(coef, "grad_scale: coef is NULL");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   for (int first = 0; first < n; first += MT_MAX) {
     const int count = n - first < MT_MAX ? n - first : MT_MAX;
@@ -262,7 +262,7 @@ extern "C" int fnst_adam_step(void* const* params, void* const* grads, void* con
                  "adam_step: bad hyper-parameters");
   // torch's lerp_ switches formula at weight >= 0.5; only the small-weight form is implemented
   FNST_CHECK_ARG(1.0 - beta1 < 0.5, "adam_step: beta1 <= 0.5 is not supported");
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   // bias corrections in double, like the Python scalars of torch/optim/adam.py
   const double bc1 = 1.0 - std::pow(beta1, (double)step);

@@ -286,7 +286,7 @@ extern "C" int fnst_resize_to_tensor(const void* img_hwc, int in_h, int in_w, in
     smem = ((smem + 15) & ~size_t(15)) + (size_t)p.stage_rows * p.stage_pitch;
   }
   FNST_CHECK_ARG(smem <= 160 * 1024, "resize_to_tensor: strip of %d rows does not fit shared memory", p.strip_rows);
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   auto kern = staged ? resize_to_tensor_kernel<true> : resize_to_tensor_kernel<false>;
   if (smem > 32 * 1024) {
     // opt in to > 48 KB once per (device, variant) with the largest size this entry point can ask for, not on every launch

@@ -272,7 +272,7 @@ using namespace fnst;
 
 extern "C" int fnst_wgrad_tc(const fnst_conv_desc* d, int g_dtype, int device, void* stream) {
   if (int r = validate_conv_desc(d)) return r;
-  FNST_CUDA(cudaSetDevice(device));
+  FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t ktot = (size_t)d->ntaps * d->kc;
   if (!(d->flags & FNST_DESC_PREZEROED)) FNST_CUDA(cudaMemsetAsync(d->out, 0, sizeof(float) * ktot * d->n_gemm, st));

@@ -162,7 +162,10 @@ class StyleTransferNet(nn.Module):
                     if len(cache) >= 4:
                         cache.clear()
                     state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(self.named_parameters()), self.precision, x, drops)
-                return autograd_fns.stylenet_graphed_apply(state, x, drops, params)
+                if not state.in_flight.busy():
+                    return autograd_fns.stylenet_graphed_apply(state, x, drops, params)
+                # an earlier forward of this graph still waits for its backward (gradient accumulation, two losses on two
+                # inputs): the captured tape holds ONE forward, so this call takes the eager per-call-tape path below
             names = [n for n, _ in self.named_parameters()]
             return autograd_fns.stylenet_apply(self._plan(), names, x, drops, params)
         plan = self._plan()

@@ -3,9 +3,18 @@ feature maps [relu1_2, relu2_2, relu3_3, relu4_2, relu4_3] (models/vgg19_net.py:
 libfnst.  The returned tensors have the reference's logical (B,C,H,W) shape; their memory is the
 path's NHWC activation buffer (a permuted view, no copy) in the path's element type.
 
-Weights: torchvision's vgg19 architecture with random init (there is no network for the pretrained
-file the reference downloads, models/vgg19_net.py:27); set FNST_VGG19_WEIGHTS=/path/vgg19.pth to load a
-torchvision state dict instead.  The reference constructor's undefined `slice5` (:51) is created here.
+Weights follow the reference (models/vgg19_net.py:27 builds `vgg19(weights='DEFAULT')`, the pretrained ImageNet
+weights): in order, FNST_VGG19_WEIGHTS=/path/vgg19.pth (a torchvision state dict, the offline override), then
+FNST_VGG19_RANDOM_INIT=1 (explicit opt-in to torchvision's random init -- tests and the benchmark, which have no
+network), then torchvision's own 'DEFAULT' download.  If none of them yields weights the constructor RAISES, as the
+reference does without a network: a perceptual loss against a silently random VGG would be meaningless.
+The reference constructor's undefined `slice5` (:51) is created here.
+
+Precision: `vgg.precision` in {"bf16" (default), "fp16", "fp32"}; FNST_VGG_PRECISION overrides, FNST_PRECISION=fp32
+selects fp32 for both networks.  Gradients of the features are bf16 on the tensor-core paths; because autograd casts an
+incoming gradient to the dtype of the forward output, feature maps that need a gradient must themselves be bf16 (or
+fp32) -- asking the fp16 path for gradients raises instead of overflowing (fp16 cannot hold the un-normalised
+Gram / style gradients).
 """
 import os
 import sys
@@ -27,10 +36,21 @@ class VGG19(nn.Module):
     def __init__(self):
         super().__init__()
         from torchvision.models import vgg19
-        net = vgg19(weights=None)
         path = os.environ.get("FNST_VGG19_WEIGHTS")
         if path:
+            net = vgg19(weights=None)
             net.load_state_dict(torch.load(path, map_location="cpu"))
+        elif os.environ.get("FNST_VGG19_RANDOM_INIT", "0") not in ("", "0"):
+            net = vgg19(weights=None)
+        else:
+            try:
+                net = vgg19(weights="DEFAULT")                       # models/vgg19_net.py:27
+            except Exception as exc:                                   # no network / no cached file
+                raise RuntimeError(
+                    "VGG19: the pretrained torchvision weights (vgg19(weights='DEFAULT'), as in the reference) could not be "
+                    f"loaded ({type(exc).__name__}: {exc}).  Set FNST_VGG19_WEIGHTS=/path/to/vgg19.pth to load a torchvision "
+                    "state dict from disk, or FNST_VGG19_RANDOM_INIT=1 to opt in to random weights (tests / benchmarks only)."
+                ) from exc
         feats = net.features
         for name, lo, hi in _SLICES:
             seq = nn.Sequential()
@@ -39,7 +59,7 @@ class VGG19(nn.Module):
             setattr(self, name, seq)
         for p in self.parameters():
             p.requires_grad = False
-        self.precision = os.environ.get("FNST_PRECISION", "fp16")
+        self.precision = os.environ.get("FNST_VGG_PRECISION") or ("fp32" if os.environ.get("FNST_PRECISION") == "fp32" else "bf16")
 
     def __getstate__(self):
         state = self.__dict__.copy()
@@ -61,6 +81,9 @@ class VGG19(nn.Module):
             raise RuntimeError("VGG19 (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
         plan = self._plan()
         need_grad = torch.is_grad_enabled() and x.requires_grad
+        if need_grad and self.precision == "fp16":
+            raise RuntimeError("VGG19 (B200 drop-in): precision 'fp16' cannot back-propagate -- autograd would cast the bf16 feature "
+                               "gradients to fp16, which overflows on the un-normalised Gram / style gradients; use 'bf16' (default) or 'fp32'")
         small = x.shape[0] * x.shape[2] * x.shape[3] <= 16 * 256 * 256
         if graphs.enabled() and small and not torch.cuda.is_current_stream_capturing():
             cache = self.__dict__.setdefault("_graphs", {})
@@ -70,7 +93,12 @@ class VGG19(nn.Module):
                 for k in [k for k in cache if k[0] != id(plan)] if len(cache) < 8 else list(cache):
                     del cache[k]
                 state = cache[key] = autograd_fns.VGGGraph(plan, x, with_tape=need_grad)
-            feats = autograd_fns.vgg_graphed_apply(state, x) if need_grad else state.forward(x.detach())
+            if not need_grad:
+                feats = state.forward(x.detach())
+            elif not state.in_flight.busy():
+                feats = autograd_fns.vgg_graphed_apply(state, x)
+            else:
+                feats = autograd_fns.vgg_apply(plan, x)      # vgg(a) and vgg(b) both awaiting backward: per-call tape
         elif need_grad:
             feats = autograd_fns.vgg_apply(plan, x)
         else:

@@ -477,7 +477,7 @@ def u8_to_nchw(img_u8: torch.Tensor, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)) 
 
 
 def nchw_to_u8(y: torch.Tensor, mean, std) -> torch.Tensor:
-    """(n,3,h,w) fp32 -> (n,h,w,3) uint8: round(clamp(y*std + mean, 0, 1)*255)."""
+    """(n,3,h,w) fp32 -> (n,h,w,3) uint8: trunc(clamp(y*std + mean, 0, 1)*255), i.e. ToPILImage's mul(255).byte() (inference.py:57-60)."""
     n, c, h, w = y.shape
     assert c == 3 and y.dtype == torch.float32 and y.is_contiguous()
     out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=y.device)

@@ -38,16 +38,20 @@ def _workspace(device: torch.device) -> torch.Tensor:
 
 
 class _PtrList:
-    """ctypes view of a list of device tensors (host array of pointers + element counts), rebuilt only when an address changes."""
+    """ctypes view of a list of device tensors (host array of pointers + element counts), rebuilt (and re-validated) whenever
+    an address, element count, dtype or contiguity changes -- `zero_grad(set_to_none=True)` frees and re-allocates the
+    gradients every step, so another tensor set can reappear at the same addresses."""
 
     def __init__(self):
-        self.key: Optional[Tuple[int, ...]] = None
+        self.key: Optional[tuple] = None
         self.ptrs = None
         self.numels = None
         self.n = 0
 
     def update(self, tensors: List[torch.Tensor], what: str):
-        key = tuple(t.data_ptr() for t in tensors)
+        ptrs = tuple(t.data_ptr() for t in tensors)
+        key = (ptrs, tuple(t.numel() for t in tensors), tuple(t.dtype for t in tensors), all(t.is_contiguous() for t in tensors),
+               tensors[0].device)
         if key != self.key:
             ops._ctx(tensors[0])                     # raises for CPU tensors: there is no CPU fallback
             for t in tensors:
@@ -58,7 +62,7 @@ class _PtrList:
                 if t.numel() == 0:
                     raise RuntimeError(f"{what}: empty tensors are not supported")
             self.n = len(tensors)
-            self.ptrs = (C.c_void_p * self.n)(*key)
+            self.ptrs = (C.c_void_p * self.n)(*ptrs)
             self.numels = (C.c_int64 * self.n)(*[t.numel() for t in tensors])
             self.key = key
         return self

@@ -188,7 +188,8 @@ int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w, int c, in
 int fnst_nchw_to_nhwc(const float* in, void* out, int n, int h, int w, int c, int c_pad, int dtype, int device, void* stream);
 
 /* uint8 HWC images <-> NCHW fp32 on the device (inference.py:28-31 ToTensor, :52-60 de-normalise/clamp).
- * mean3/std3 are HOST pointers to three floats.  u8->f32: (u8/255 - mean)/std;  f32->u8: round(clamp(y*std + mean, 0, 1)*255). */
+ * mean3/std3 are HOST pointers to three floats.  u8->f32: (u8/255 - mean)/std;  f32->u8: trunc(clamp(y*std + mean, 0, 1)*255)
+ * (torchvision ToPILImage on a float tensor is mul(255).byte(): truncation, inference.py:57-60). */
 int fnst_u8_to_nchw(const void* in, float* out, int n, int h, int w, const float* mean3, const float* std3, int device, void* stream);
 int fnst_nchw_to_u8(const float* in, void* out, int n, int h, int w, const float* mean3, const float* std3, int device, void* stream);
 

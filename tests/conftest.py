@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# no network here: the drop-in VGG19 would otherwise try to download the pretrained weights like the reference does
+# (models/vgg19_net.py:27) and raise; tests load seeded random weights themselves
+os.environ.setdefault("FNST_VGG19_RANDOM_INIT", "1")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")

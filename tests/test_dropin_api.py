@@ -89,6 +89,41 @@ def test_vgg_contract(dropin):
     assert hasattr(vgg, "slice5")
 
 
+def test_vgg_weight_policy(dropin, monkeypatch, tmp_path):
+    """The reference builds vgg19(weights='DEFAULT') (models/vgg19_net.py:27).  The drop-in must never fall back to random
+    weights silently: offline override file -> explicit random opt-in -> torchvision's download, else raise."""
+    import torchvision.models as tvm
+    _, mv, _ = dropin
+    calls = []
+
+    def fake_vgg19(weights=None, **kw):
+        calls.append(weights)
+        if weights is not None:
+            raise OSError("no network in this test")
+        return _REAL_VGG19(weights=None)
+
+    global _REAL_VGG19
+    _REAL_VGG19 = tvm.vgg19
+    monkeypatch.setattr(tvm, "vgg19", fake_vgg19)
+    monkeypatch.delenv("FNST_VGG19_RANDOM_INIT", raising=False)
+    monkeypatch.delenv("FNST_VGG19_WEIGHTS", raising=False)
+    with pytest.raises(RuntimeError, match="FNST_VGG19_WEIGHTS"):
+        mv.VGG19()
+    assert calls == ["DEFAULT"]                                   # tried the reference's own source first
+    # offline override: a torchvision state dict on disk
+    torch.manual_seed(5)
+    src = _REAL_VGG19(weights=None)
+    path = tmp_path / "vgg19.pth"
+    torch.save(src.state_dict(), path)
+    monkeypatch.setenv("FNST_VGG19_WEIGHTS", str(path))
+    vgg = mv.VGG19()
+    assert torch.equal(vgg.slice5[1].weight, src.features[23].weight)
+    # explicit opt-in to random init
+    monkeypatch.delenv("FNST_VGG19_WEIGHTS")
+    monkeypatch.setenv("FNST_VGG19_RANDOM_INIT", "1")
+    assert mv.VGG19().precision == "bf16"                         # loss network default: bf16 (gradients need its range)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present on this machine")
 def test_same_seed_gives_the_reference_weights(dropin):
     """All 58 tensors: the drop-in constructed under a seed equals the unmodified reference module constructed under the

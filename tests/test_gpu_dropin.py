@@ -120,7 +120,11 @@ def test_cuda_graph_replay_tracks_inputs_and_weights(dropin):
 
 
 def test_stylize_uint8_matches_reference_postprocessing(dropin):
-    """uint8 in / uint8 out on the GPU == inference.py:44-60 (ToTensor, forward, de-normalise, clamp, x255)."""
+    """uint8 in / uint8 out on the GPU == inference.py:44-60 (ToTensor, forward, de-normalise, clamp, ToPILImage).
+    ToPILImage on a float tensor is `pic.mul(255).byte()` -- truncation, not rounding -- so the reference pixel is
+    floor(clamp(...) * 255); compared here against torchvision's own to_pil_image."""
+    import numpy as np
+    from torchvision.transforms.functional import to_pil_image
     mm, _, _ = dropin
     p = O.make_net_params(seed=0)
     net = mm.StyleTransferNet().to(DEV); net.load_state_dict(p); net.precision = "fp32"; net.eval()
@@ -129,7 +133,10 @@ def test_stylize_uint8_matches_reference_postprocessing(dropin):
     out = net.stylize_uint8(img.to(DEV)).cpu()
     x = img.permute(0, 3, 1, 2).float() / 255.0                            # transforms.ToTensor()
     with torch.no_grad():
-        ref = O.to_pixels(O.stylenet_forward(p, x)).round().clamp(0, 255).permute(0, 2, 3, 1)
+        y01 = O.to_pixels(O.stylenet_forward(p, x)) / 255.0                # de-normalise + clamp to [0,1] (inference.py:52-56)
+    ref = torch.stack([torch.from_numpy(np.asarray(to_pil_image(y01[i]))) for i in range(y01.shape[0])])     # inference.py:59
     assert out.shape == ref.shape and out.dtype == torch.uint8
-    diff = (out.float() - ref).abs()
-    assert float(diff.max()) <= 1.0 and float((diff > 0).float().mean()) < 0.01     # rounding ties only
+    diff = (out.float() - ref.float()).abs()
+    # values within fp32 noise of an integer boundary may land on either side; a rounding implementation would be off by
+    # one on about half of the pixels
+    assert float(diff.max()) <= 1.0 and float((diff > 0).float().mean()) < 0.01

@@ -1,5 +1,6 @@
 """Where does the graphed training step spend its time?  CUDA-event timing of the step's phases."""
 import sys, os, time, torch
+os.environ.setdefault('FNST_VGG19_RANDOM_INIT', '1')
 sys.path.insert(0, '.'); sys.path.insert(0, 'fast_neural_style_transfer_b200/dropin')
 from oracle import stylenet_oracle as O
 from models.model import StyleTransferNet
