@@ -57,10 +57,10 @@ def gram(feat: torch.Tensor) -> torch.Tensor:
 
 # ---- sum of squared differences ----------------------------------------------------------------------
 
-def _sse_forward(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    acc = torch.zeros((), dtype=torch.float64, device=a.device)
-    ops.sse(a, b, acc)
-    return acc.float()
+def _sse_forward(a: torch.Tensor, b: torch.Tensor, scale: float) -> torch.Tensor:
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    ops.sse_scaled(a, b, scale, out)                      # one launch: reduction, normalisation and the fp32 scalar
+    return out
 
 
 def _match_layout(a: torch.Tensor, b: torch.Tensor):
@@ -74,48 +74,54 @@ def _match_layout(a: torch.Tensor, b: torch.Tensor):
 
 class _SSE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, scale):
         an, bn = _match_layout(a.detach(), b.detach())
         ctx.save_for_backward(an, bn)
-        ctx.is_feat = a.dim() == 4
-        return _sse_forward(an, bn)
+        ctx.is_feat, ctx.scale = a.dim() == 4, scale
+        return _sse_forward(an, bn, scale)
 
     @staticmethod
     def backward(ctx, g):
         from . import backward
         an, bn = ctx.saved_tensors
-        da = backward.sse_backward(an, bn, g)
-        return (da.permute(0, 3, 1, 2) if ctx.is_feat else da), None
+        da = backward.sse_backward(an, bn, g, ctx.scale)
+        return (da.permute(0, 3, 1, 2) if ctx.is_feat else da), None, None
 
 
-def sse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """sum((a - b)^2) with b broadcast over the leading (batch) dimension; differentiable in a."""
+def sse(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """scale * sum((a - b)^2) with b broadcast over the leading (batch) dimension; differentiable in a."""
     _need_cuda(a, "mse/sse")
     if torch.is_grad_enabled() and a.requires_grad:
-        return _SSE.apply(a, b)
+        return _SSE.apply(a, b, float(scale))
     an, bn = _match_layout(a.detach(), b.detach())
-    return _sse_forward(an, bn)
+    return _sse_forward(an, bn, float(scale))
 
 
 # ---- fused style loss ----------------------------------------------------------------------------------------
 
+def _style_forward(fs, targets, coefs):
+    """Gram matrices of the layers (one zero fill for all of them) and sum_l coef_l * SSE(G_l, T_l) as one fp32 scalar."""
+    dev = fs[0].device
+    arena = ops.ZeroArena(sum(f.shape[0] * f.shape[3] * f.shape[3] for f in fs) + 4 * len(fs), dev)
+    grams = [ops.gram(f, use_tc=_gram_tc_ok(f), out=arena.take(f.shape[0], f.shape[3], f.shape[3])) for f in fs]
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    for i, (g, t, coef) in enumerate(zip(grams, targets, coefs)):
+        ops.sse_scaled(g, t, coef, out, accumulate=i > 0)
+    return grams, out
+
+
 class _StyleLoss(torch.autograd.Function):
     """sum_l w_l * SSE(gram(F_l), T_l) / c_l^2 over the given layers as ONE autograd node (losses/losses.py:15-44).
-    Backward per layer: one kernel builds S = g*w/c^2 * 2*((G-T) + (G-T)^T)/... in the feature dtype, one batched 1x1
+    Backward per layer: one kernel builds S = g*w/c^2 * 2*((G-T) + (G-T)^T)/... in the gradient dtype, one batched 1x1
     gather-GEMM computes dF = F S -- instead of ~10 autograd nodes per layer on the critical path after the NaN check."""
 
     @staticmethod
     def forward(ctx, weights, targets, cs, *feats):
         fs = [_as_nhwc(f.detach()) for f in feats]
-        grams = [ops.gram(f, use_tc=_gram_tc_ok(f)) for f in fs]
-        acc = torch.zeros(len(fs), dtype=torch.float64, device=fs[0].device)
-        coefs = []
-        for i, (g, t, w, c) in enumerate(zip(grams, targets, weights, cs)):
-            ops.sse(g, t, acc[i:i + 1].view(()))
-            coefs.append(w / (c * c))
+        coefs = [w / (c * c) for w, c in zip(weights, cs)]
+        grams, out = _style_forward(fs, targets, coefs)
         ctx.fs, ctx.grams, ctx.targets, ctx.coefs = fs, grams, targets, coefs
-        coef_t = torch.tensor(coefs, dtype=torch.float64, device=acc.device)
-        return (acc * coef_t).sum().float()
+        return out
 
     @staticmethod
     def backward(ctx, g):
@@ -136,39 +142,39 @@ def style_loss_fused(feats: Sequence[torch.Tensor], targets: Sequence[torch.Tens
     targets = [t.detach().float().contiguous() for t in targets]
     if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
         return _StyleLoss.apply(list(weights), targets, list(cs), *feats)
-    total = None
-    for f, t, w, c in zip(feats, targets, weights, cs):
-        term = (w * sse(gram(f), t)) / (c * c)
-        total = term if total is None else total + term
-    return total
+    fs = [_as_nhwc(f.detach()) for f in feats]
+    return _style_forward(fs, targets, [w / (c * c) for w, c in zip(weights, cs)])[1]
 
 
 # ---- total variation ---------------------------------------------------------------------------------
 
+def _tv_forward(x: torch.Tensor, scale: float) -> torch.Tensor:
+    out = torch.empty((), dtype=torch.float32, device=x.device)
+    ops.tv_scaled(x, scale, out)
+    return out
+
+
 class _TV(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, img):
+    def forward(ctx, img, scale):
         x = img.detach().float().contiguous()
         ctx.save_for_backward(x)
-        acc = torch.zeros((), dtype=torch.float64, device=x.device)
-        ops.tv(x, acc)
-        return acc.float()
+        ctx.scale = scale
+        return _tv_forward(x, scale)
 
     @staticmethod
     def backward(ctx, g):
         from . import backward
         (x,) = ctx.saved_tensors
-        return backward.tv_backward(x, g)
+        return backward.tv_backward(x, g, ctx.scale), None
 
 
-def tv(img: torch.Tensor) -> torch.Tensor:
+def tv(img: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """scale * (sum dh^2 + sum dw^2); differentiable in img."""
     _need_cuda(img, "total_variation_loss")
     if torch.is_grad_enabled() and img.requires_grad:
-        return _TV.apply(img)
-    x = img.detach().float().contiguous()
-    acc = torch.zeros((), dtype=torch.float64, device=x.device)
-    ops.tv(x, acc)
-    return acc.float()
+        return _TV.apply(img, float(scale))
+    return _tv_forward(img.detach().float().contiguous(), float(scale))
 
 
 # ---- whole-network functions -----------------------------------------------------------------------------
@@ -272,13 +278,17 @@ class StyleNetTrainGraph:
         return self.fwd(x, *(drops if self.has_drop else []))
 
     def backward(self, dy):
+        """Captured: the whole backward up to the packed weight gradients / InstanceNorm sums (static buffers).  Eager: the
+        two assembly launches, which write the 58 gradients into a FRESH flat buffer (nothing the caller receives aliases
+        graph memory; no concatenation, no clone)."""
         from . import backward, graphs
         if self.bwd is None:
             def bwd(dy_):
-                g = backward.stylenet_backward(self.plan, self.tape, dy_)
-                return torch.cat([g[n].reshape(-1) for n in self.names])
+                self.core = backward.stylenet_backward_core(self.plan, self.tape, dy_)
+                return self.core["staging"]
             self.bwd = graphs.GraphedPlan(bwd, [dy.float().contiguous()])
-        flat = self.bwd(dy).clone()
+        self.bwd(dy)
+        flat = backward.assemble_gradients(self.core, self.names, self.params)
         return [t.view_as(self.params[n]) for t, n in zip(torch.split(flat, self.numels), self.names)]
 
 

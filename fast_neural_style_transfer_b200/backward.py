@@ -69,45 +69,150 @@ def unpack_conv_transpose(db: torch.Tensor, cin: int, cout: int) -> torch.Tensor
     return dw
 
 
-def _affine_grads(dgb: torch.Tensor):
-    return dgb[0], dgb[1]                                   # d gamma, d beta (accumulated by inorm_bwd_reduce)
-
-
 def _tc_ok(use_tc: bool, kc: int, n_gemm: int) -> bool:
     return use_tc and kc % 64 == 0 and (n_gemm == 16 or n_gemm % 32 == 0)
-
-
-def _wgrad(tc: bool, spec: ConvSpec, a, a_dims, g, out_hw, out=None, out_zeroed=False) -> torch.Tensor:
-    """Weight gradient of `spec`; tensor cores whenever the channel window is a multiple of 64."""
-    use_tc = tc and spec.kc % 64 == 0
-    if use_tc and a.dtype != g.dtype:
-        a = ops.cast(a, g.dtype)         # kind::f16 MMAs need both operands in one 16-bit format
-    return ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, out=out, out_zeroed=out_zeroed)
 
 
 # -------------------------------------------------------------------------------------------------------
 # StyleTransferNet backward
 # -------------------------------------------------------------------------------------------------------
+#
+# Gradient plumbing.  Every weight-gradient GEMM writes its packed result into a slice of ONE zeroed fp32 staging buffer;
+# every InstanceNorm backward writes its per-plane sums into a slice of ONE sums buffer.  Two launches then assemble the
+# 58 gradients in the reference's parameter layouts inside ONE flat fp32 buffer (`assemble_gradients`): a gather through
+# a cached index map (weights: packed -> OIHW / IOHW; conv biases in front of an InstanceNorm: zero) and a fixed-order
+# reduction over the images for d gamma / d beta.  The per-parameter gradients are views of that buffer (so the
+# data-parallel all-reduce and the optimizer tail see one contiguous bucket).
+
+NORM_LAYERS = (["norm1", "norm2"] + [f"res_blocks.{i}.{n}" for i in range(5) for n in ("in1", "in2")] + ["norm3", "norm4"])
+
+
+def _staging_layout(tc: bool):
+    """name -> (element offset, shape) of the packed weight gradients inside the staging buffer; total elements."""
+    items = [("res", (10, 256, 2304)), ("up1", (256, 1024)), ("up2", (128, 256)), ("conv2", (256, 576)),
+             ("conv1", (64, 576) if tc else (243, 64)), ("final", (128, 576) if tc else (16, 81 * 32)), ("final_bias", (3,))]
+    off, out = 0, {}
+    for name, shape in items:
+        n = 1
+        for d in shape:
+            n *= d
+        out[name] = (off, shape)
+        off += (n + 3) // 4 * 4
+    return out, off
+
+
+_FINAL_KW = torch.arange(8, -1, -1)          # final_conv weight-gradient window: kw -> pixel index i = 8 - kw
+
+
+def _unpack_fns(tc: bool):
+    """parameter name -> (staging slice name, slice selector, layout function packed -> parameter layout)."""
+    fns = {}
+    for k in range(10):
+        name = f"res_blocks.{k // 2}.conv{k % 2 + 1}.conv.weight"
+        fns[name] = ("res", k, lambda t: t.view(256, 3, 3, 256).permute(0, 3, 1, 2))
+    fns["up1.upsample_conv.weight"] = ("up1", None, lambda t: unpack_conv_transpose(t, 256, 64))
+    fns["up2.upsample_conv.weight"] = ("up2", None, lambda t: unpack_conv_transpose(t, 64, 32))
+    fns["conv2.conv.weight"] = ("conv2", None, lambda t: unpack_conv(t, 256, 64, 3))
+    if tc:
+        fns["conv1.conv.weight"] = ("conv1", None, lambda t: t.view(64, 9, 16, 4)[:, :, :9, :3].permute(0, 3, 1, 2))
+        # (i, j, kh, jj, c) -> (j, c, kh, kw), kw = 8 - i from the jj = 0 entries
+        fns["final_conv.conv.weight"] = ("final", None, lambda t: t.view(16, 8, 9, 2, 32)[_FINAL_KW, :3, :, 0, :].permute(1, 3, 2, 0))
+    else:
+        fns["conv1.conv.weight"] = ("conv1", None, lambda t: t.view(3, 9, 9, 64).permute(3, 0, 1, 2))
+        fns["final_conv.conv.weight"] = ("final", None, lambda t: unpack_conv(t, 3, 32, 9))
+    fns["final_conv.conv.bias"] = ("final_bias", None, lambda t: t)
+    return fns
+
+
+_ASSEMBLY = {}
+
+
+def _assembly(names: Sequence[str], shapes: Sequence[torch.Size], tc: bool, device) -> dict:
+    """Cached per (parameter list, path, device): flat offsets, the int32 gather map staging -> flat (-1 = zero)."""
+    key = (tuple(names), tc, str(device))
+    ent = _ASSEMBLY.get(key)
+    if ent is not None:
+        return ent
+    layout, _ = _staging_layout(tc)
+    fns = _unpack_fns(tc)
+    offsets, off = {}, 0
+    pieces = []
+    for name, shape in zip(names, shapes):
+        numel = 1
+        for d in shape:
+            numel *= d
+        offsets[name] = off
+        off += numel
+        if name in fns:
+            slot, sel, fn = fns[name]
+            base, sshape = layout[slot]
+            cnt = 1
+            for d in sshape:
+                cnt *= d
+            probe = (torch.arange(cnt, dtype=torch.float64) + (base + 1)).reshape(sshape)      # element number + 1 (0 = zero fill)
+            probe = probe if sel is None else probe[sel]
+            res = fn(probe)
+            assert tuple(res.shape) == tuple(shape), (name, res.shape, shape)
+            pieces.append((res.reshape(-1).round().to(torch.int64) - 1).to(torch.int32))
+        else:
+            pieces.append(torch.full((numel,), -1, dtype=torch.int32))       # zero (conv bias under InstanceNorm) or written by affine_grads
+    ent = _ASSEMBLY[key] = dict(offsets=offsets, total=off, idx=torch.cat(pieces).to(device))
+    return ent
+
+
+def assemble_gradients(core: dict, names: Sequence[str], params: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Flat fp32 gradient of all parameters (in `names` order) from the staging / sums buffers of `stylenet_backward_core`."""
+    asm = _assembly(names, [params[n].shape for n in names], core["tc"], core["staging"].device)
+    flat = torch.empty(asm["total"], dtype=torch.float32, device=core["staging"].device)
+    ops.gather_index(core["staging"], asm["idx"], flat)
+    entries = [(src, c, asm["offsets"][ln + ".weight"], asm["offsets"][ln + ".bias"]) for ln, (src, c) in core["norm_sums"].items()]
+    ops.affine_grads(core["sums"], entries, core["batch"], flat)
+    return flat
+
 
 def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor) -> Dict[str, torch.Tensor]:
-    """dy: (B,3,H',W') fp32.  Returns gradients for all 58 reference parameter names."""
+    """dy: (B,3,H',W') fp32.  Returns gradients for all 58 reference parameter names (views of one flat fp32 buffer)."""
+    names = list(plan.params)
+    flat = assemble_gradients(stylenet_backward_core(plan, tape, dy), names, plan.params)
+    return dict(zip(names, [t.view_as(plan.params[n]) for t, n in zip(torch.split(flat, [plan.params[n].numel() for n in names]), names)]))
+
+
+def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor) -> dict:
+    """Everything of the backward pass except the final assembly: returns the staging buffer (packed weight gradients), the
+    InstanceNorm sums buffer and where each norm layer's sums live -- static tensors when captured in a CUDA graph."""
     p = plan.params
     gdt = grad_dtype(plan.precision)
     tc = plan.use_tc
     dev = dy.device
     dy = dy.contiguous().float()
     B, _, H4, W4 = dy.shape
-    grads: Dict[str, torch.Tensor] = {}
+    layout, staging_total = _staging_layout(tc)
+    staging = torch.zeros(staging_total, dtype=torch.float32, device=dev)       # split-K targets of every weight gradient: ONE memset
 
-    zero_names = [n for n in p if n.endswith(".bias") and ("conv" in n) and not n.startswith("final_conv")]
-    zero_flat = torch.zeros(sum(p[n].numel() for n in zero_names), dtype=torch.float32, device=dev)
-    zero_views = dict(zip(zero_names, torch.split(zero_flat, [p[n].numel() for n in zero_names])))
-    # reduction buffers of the 14 InstanceNorm backward passes ([B,C,2] sums + [2,C] d gamma / d beta each), zeroed once:
-    # no memset in front of the individual kernels, so programmatic dependent launch can chain them
-    arena = ops.ZeroArena((2 * B + 2) * engine.STATS_CHANNELS + 64 * 14, dev)
+    def slot(name):
+        off, shape = layout[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return staging[off:off + n].view(shape)
 
-    def zeros_like_param(name):
-        return zero_views[name]
+    # per-plane sums of the 14 InstanceNorm backward passes, [B,C,2] each (zeroed once: the two-pass fallback accumulates)
+    arena = ops.ZeroArena(2 * B * engine.STATS_CHANNELS + 64 * 14, dev)
+    norm_sums: Dict[str, tuple] = {}
+    wtw = tape.get("w") or {}                    # bf16 twins of the saved activations (None entries: use the activation itself)
+
+    def inorm_backward(layer, gsrc, extra, raw, stats, drop, relu, pad=0, pad_mode=PAD_NONE, s2d=False, out_s2d=False, want_gy=False):
+        """d_raw (and gy when asked) of one InstanceNorm layer; its sums slice is registered for the affine gradients."""
+        ga, ba = plan._affine(layer)
+        src_off = arena.used
+        sums = arena.take(B, raw.shape[-1], 2)
+        norm_sums[layer] = (src_off, raw.shape[-1])
+        if ops.inorm_bwd_fused_parts(raw, gdt) > 0:
+            d_raw, gy, _ = ops.inorm_bwd_fused(gsrc, extra, raw, stats, ga, ba, drop, gdt, relu, pad, pad_mode, s2d, out_s2d, want_gy, sums)
+            return d_raw, gy
+        gy, _ = ops.inorm_bwd_reduce(gsrc, extra, raw, stats, ga, ba, drop, gdt, relu, pad, pad_mode, s2d, sums=sums)
+        d_raw, _ = ops.inorm_bwd_apply(gy, raw, stats, sums, ga, out_s2d=out_s2d, want_dgb=False)
+        return d_raw, gy
 
     # Weight gradients are off the critical path (nothing downstream in this backward consumes them): they run on a
     # side stream forked from the main stream right after their operands are produced and joined at the end.  Under
@@ -134,6 +239,15 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         keep_alive.extend(tensors)
         return _Side()
 
+    def wgrad(spec, a, a_twin, a_dims, g, out_hw, out):
+        """Weight gradient of `spec` into a staging slice; tensor cores whenever the channel window is a multiple of 64
+        (operand = the activation's bf16 twin when the forward wrote one, else a cast)."""
+        use_tc = tc and spec.kc % 64 == 0
+        if use_tc and a.dtype != g.dtype:
+            a = a_twin if a_twin is not None else ops.cast(a, g.dtype)
+            keep_alive.append(a)
+        ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, out=out, out_zeroed=True)
+
     gp, f64 = ops.gather_pack, torch.float64
 
     def dgrad(g, g_dims, wd, fwd_taps, fwd_kc, out_shape, out_hw, h0=0, w0=0):
@@ -146,7 +260,7 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         return out
 
     # ---- final_conv (9x9, 32 -> 3) -------------------------------------------------------------------
-    grads["final_conv.conv.bias"] = ops.channel_sum(dy)
+    ops.channel_sum(dy, out=slot("final_bias"))
     act4 = tape["act4"]
     Hq, Wq = act4.shape[1], act4.shape[2]
     taps81 = taps_kxk(9)
@@ -159,22 +273,20 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         rows_g, pitch_g = H4 + 16, W4 + 16
         g8 = ops.image_to_halo(dy, 8, PAD_ZERO, 8, rows_g, pitch_g, gdt)
         g_str = (rows_g * pitch_g * 8, pitch_g * 8, 8)
-        flat = tape["act4_flat"]
+        flat_act = tape["act4_flat"]
         taps9 = [(kh - 8, 0, 0) for kh in range(9)]
-        idx = torch.arange(8, -1, -1)                                         # kw -> i = 8 - kw (jj = 0 entries); layout maps run on the CPU
-        with on_side(g8, flat):
-            a_g = flat if flat.dtype == gdt else ops.cast(flat, gdt)
-            db = ops.wgrad(ConvSpec(taps9, 64, None, 128, 128), a_g, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), g8,
-                           (rows_g, pitch_g), use_tc=True, g_strides=g_str)
-            # (i, j, kh, jj, c) -> (j, c, kh, kw), kw = 8 - i from the jj = 0 entries
-            grads["final_conv.conv.weight"] = gp("final_wgrad_unpack", lambda t: t.view(16, 8, 9, 2, 32)[idx, :3, :, 0, :]
-                                                 .permute(1, 3, 2, 0).contiguous(), db, torch.float32)
-            keep_alive.extend([a_g, db])
+        with on_side(g8, flat_act):
+            a_g = flat_act
+            if a_g.dtype != gdt:
+                a_g = wtw.get("act4_flat") if wtw.get("act4_flat") is not None else ops.cast(flat_act, gdt)
+            ops.wgrad(ConvSpec(taps9, 64, None, 128, 128), a_g, (B, Hq, Wq, 64), (Hq * Wq * 32, Wq * 32, 32), g8,
+                      (rows_g, pitch_g), use_tc=True, g_strides=g_str, out=slot("final"), out_zeroed=True)
+            keep_alive.append(a_g)
 
         def final_dgrad_layout(wt):                                           # (3, 32, 9, 9) -> (32, 18*64)
             wd = torch.zeros((32, 9, 2, 8, 8), dtype=wt.dtype)                # (c, kh, a, i, j)
             wperm = wt.permute(1, 2, 3, 0)                                    # (c, kh, kw, j)
-            wd[:, :, 0, :, :3] = wperm[:, :, idx[:8], :]                # a = 0: pixel i <-> kw = 8 - i
+            wd[:, :, 0, :, :3] = wperm[:, :, _FINAL_KW[:8], :]                # a = 0: pixel i <-> kw = 8 - i
             wd[:, :, 1, 0, :3] = wperm[:, :, 0, :]                            # a = 1: pixel 0 <-> kw = 0
             return wd.reshape(32, 18 * 64)
 
@@ -184,40 +296,29 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
                         (B, rows_g, pitch_g, 64), g_str, d_act4, (Hq, Wq), None, True)
     else:
         g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
-        db = _wgrad(tc, ConvSpec(taps81, 32, None, 16, 3), act4, (B, Hq, Wq, 32), g16, (H4, W4))
-        grads["final_conv.conv.weight"] = unpack_conv(db, 3, 32, 9)
+        wgrad(ConvSpec(taps81, 32, None, 16, 3), act4, None, (B, Hq, Wq, 32), g16, (H4, W4), slot("final"))
         wd_fin = gp("final_plain_dgrad", lambda t: pack_dgrad(engine.pack_final_plain(t, f64), 81, 32, f64), wfin, gdt)
         d_act4 = dgrad(g16, (B, H4, W4, 16), wd_fin, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
 
     # ---- norm4 + up2 ------------------------------------------------------------------------------------
-    g4, b4 = plan._affine("norm4")
-    gy, sums = ops.inorm_bwd_reduce(d_act4, None, tape["raw4"], tape["st4"], g4, b4, None, gdt, True, 4, PAD_REFLECT, arena=arena)
-    d_raw4, dgb = ops.inorm_bwd_apply(gy, tape["raw4"], tape["st4"], sums, g4, out_s2d=True)     # (B,H3,W3,128)
-    grads["norm4.weight"], grads["norm4.bias"] = _affine_grads(dgb)
+    d_raw4, _ = inorm_backward("norm4", d_act4, None, tape["raw4"], tape["st4"], None, True, 4, PAD_REFLECT, out_s2d=True)   # (B,H3,W3,128)
     act3 = tape["act3"]
     H3, W3 = act3.shape[1], act3.shape[2]
     with on_side(act3, d_raw4):
-        db = _wgrad(tc, ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, (B, H3, W3, 64), d_raw4, (H3, W3))
-        grads["up2.upsample_conv.weight"] = gp("convT_unpack", lambda t: unpack_conv_transpose(t, 64, 32), db, torch.float32)
-        keep_alive.append(db)
-    grads["up2.upsample_conv.bias"] = zeros_like_param("up2.upsample_conv.bias")
+        wgrad(ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, wtw.get("act3"), (B, H3, W3, 64), d_raw4, (H3, W3), slot("up2"))
     convT_dgrad = lambda kc: (lambda t: pack_dgrad(engine.pack_conv_transpose(t, f64), 4, kc, f64))
     wd_up2 = gp("convT_dgrad", convT_dgrad(64), p["up2.upsample_conv.weight"], gdt)
     d_act3 = dgrad(d_raw4, (B, H3, W3, 128), wd_up2, TAPS_2X2, 64, (B, H3, W3, 64), (H3, W3))
 
     # ---- norm3 + up1 ------------------------------------------------------------------------------------
-    g3, b3 = plan._affine("norm3")
-    gy, sums = ops.inorm_bwd_reduce(d_act3, None, tape["raw3"], tape["st3"], g3, b3, None, gdt, True, arena=arena)
-    d_raw3, dgb = ops.inorm_bwd_apply(gy, tape["raw3"], tape["st3"], sums, g3, out_s2d=True)     # (B,H2,W2,256)
-    grads["norm3.weight"], grads["norm3.bias"] = _affine_grads(dgb)
+    d_raw3, _ = inorm_backward("norm3", d_act3, None, tape["raw3"], tape["st3"], None, True, out_s2d=True)     # (B,H2,W2,256)
     trunk = tape["trunk"]
+    trunk_w = wtw.get("trunk") or [None] * len(trunk)
+    mid_w = wtw.get("mid") or [None] * 5
     last = trunk[5]
     H2, W2 = last.shape[1], last.shape[2]
     with on_side(last, d_raw3):
-        db = _wgrad(tc, ConvSpec(TAPS_2X2, 256, None, 256, 64), last, (B, H2, W2, 256), d_raw3, (H2, W2))
-        grads["up1.upsample_conv.weight"] = gp("convT_unpack", lambda t: unpack_conv_transpose(t, 256, 64), db, torch.float32)
-        keep_alive.append(db)
-    grads["up1.upsample_conv.bias"] = zeros_like_param("up1.upsample_conv.bias")
+        wgrad(ConvSpec(TAPS_2X2, 256, None, 256, 64), last, trunk_w[5], (B, H2, W2, 256), d_raw3, (H2, W2), slot("up1"))
     wd_up1 = gp("convT_dgrad", convT_dgrad(256), p["up1.upsample_conv.weight"], gdt)
     g_plain = dgrad(d_raw3, (B, H2, W2, 256), wd_up1, TAPS_2X2, 256, (B, H2, W2, 256), (H2, W2))
 
@@ -225,12 +326,10 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
     taps9 = taps_kxk(3)
     pdims = (B, H2 + 2, W2 + 2, 256)
     gsrc, extra = None, g_plain          # gradient of the block output = fold(gsrc) + extra
-    # the ten 3x3 weights are handled as one stacked tensor: one kernel packs all data-gradient operands, one kernel
-    # turns all ten weight gradients back into the OIHW parameter layout
+    # the ten 3x3 weights are handled as one stacked tensor: one kernel packs all data-gradient operands
     res_fwd = plan.w["res_all"]                                              # (10, 256, 9*256) forward operands
-    res_dg = torch.empty((10, 256, 9 * 256), dtype=gdt, device=dev)
-    res_dg.view(10, 256, 9, 256).copy_(res_fwd.view(10, 256, 9, 256).permute(0, 3, 2, 1))
-    res_db = torch.zeros((10, 256, 9 * 256), dtype=torch.float32, device=dev)    # split-K targets, zeroed once
+    res_dg = gp("res_dgrad", lambda t: t.view(10, 256, 9, 256).permute(0, 3, 2, 1).reshape(10, 256, 9 * 256), res_fwd, gdt)
+    res_db = slot("res")
 
     def res_dgrad(g, idx):
         out = torch.empty(pdims, dtype=gdt, device=dev)
@@ -242,57 +341,34 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         blk = tape["blocks"][i]
         pre = f"res_blocks.{i}"
         # in2 (no ReLU); the total output gradient also feeds the skip connection
-        ga, ba = plan._affine(pre + ".in2")
-        g_out, sums = ops.inorm_bwd_reduce(gsrc, extra, blk["raw_b"], blk["st_b"], ga, ba, None, gdt, False,
-                                           1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE, arena=arena)
-        d_raw_b, dgb = ops.inorm_bwd_apply(g_out, blk["raw_b"], blk["st_b"], sums, ga)
-        grads[pre + ".in2.weight"], grads[pre + ".in2.bias"] = _affine_grads(dgb)
+        d_raw_b, g_out = inorm_backward(pre + ".in2", gsrc, extra, blk["raw_b"], blk["st_b"], None, False,
+                                        1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE, want_gy=True)
         mid = blk["mid"]
         with on_side(mid, d_raw_b):
-            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, pdims, d_raw_b, (H2, W2), out=res_db[2 * i + 1], out_zeroed=True)
-        grads[pre + ".conv2.conv.bias"] = zeros_like_param(pre + ".conv2.conv.bias")
+            wgrad(ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, mid_w[i], pdims, d_raw_b, (H2, W2), res_db[2 * i + 1])
         d_mid = res_dgrad(d_raw_b, 2 * i + 1)
         # in1 + ReLU + Dropout2d
-        ga, ba = plan._affine(pre + ".in1")
-        gy, sums = ops.inorm_bwd_reduce(d_mid, None, blk["raw_a"], blk["st_a"], ga, ba, blk["drop"], gdt, True, 1, PAD_REFLECT, arena=arena)
-        d_raw_a, dgb = ops.inorm_bwd_apply(gy, blk["raw_a"], blk["st_a"], sums, ga)
-        grads[pre + ".in1.weight"], grads[pre + ".in1.bias"] = _affine_grads(dgb)
+        d_raw_a, _ = inorm_backward(pre + ".in1", d_mid, None, blk["raw_a"], blk["st_a"], blk["drop"], True, 1, PAD_REFLECT)
         cur = trunk[i]
         with on_side(cur, d_raw_a):
-            _wgrad(tc, ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, pdims, d_raw_a, (H2, W2), out=res_db[2 * i], out_zeroed=True)
-        grads[pre + ".conv1.conv.bias"] = zeros_like_param(pre + ".conv1.conv.bias")
+            wgrad(ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, trunk_w[i], pdims, d_raw_a, (H2, W2), res_db[2 * i])
         gsrc = res_dgrad(d_raw_a, 2 * i)
         extra = g_out
-    res_dw = torch.empty((10, 256, 256, 3, 3), dtype=torch.float32, device=dev)
-    with on_side(res_db):
-        res_dw.copy_(res_db.view(10, 256, 3, 3, 256).permute(0, 1, 4, 2, 3))
-    for i in range(5):
-        grads[f"res_blocks.{i}.conv1.conv.weight"] = res_dw[2 * i]
-        grads[f"res_blocks.{i}.conv2.conv.weight"] = res_dw[2 * i + 1]
 
     # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
-    g2, b2 = plan._affine("norm2")
-    gy, sums = ops.inorm_bwd_reduce(gsrc, extra, tape["raw2"], tape["st2"], g2, b2, None, gdt, True, 1, PAD_REFLECT, arena=arena)
-    d_raw2, dgb = ops.inorm_bwd_apply(gy, tape["raw2"], tape["st2"], sums, g2)
-    grads["norm2.weight"], grads["norm2.bias"] = _affine_grads(dgb)
+    d_raw2, _ = inorm_backward("norm2", gsrc, extra, tape["raw2"], tape["st2"], None, True, 1, PAD_REFLECT)
     buf2 = tape["buf2"]
     Hs, Ws = buf2.shape[1], buf2.shape[2]
     with on_side(buf2, d_raw2):
-        db = _wgrad(tc, ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, (B, Hs, Ws, 256), d_raw2, (H2, W2))
-        grads["conv2.conv.weight"] = gp("conv_unpack_3x3", lambda t: unpack_conv(t, 256, 64, 3), db, torch.float32)
-        keep_alive.append(db)
-    grads["conv2.conv.bias"] = zeros_like_param("conv2.conv.bias")
+        wgrad(ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, wtw.get("buf2"), (B, Hs, Ws, 256), d_raw2, (H2, W2), slot("conv2"))
     wd2 = gp("s2d_dgrad", lambda t: pack_dgrad_s2d(t, f64), p["conv2.conv.weight"], gdt)
     d_buf2 = torch.empty((B, Hs, Ws, 256), dtype=gdt, device=dev)
     ops.conv_gather(ConvSpec(_neg(TAPS_2X2), 256, wd2, 256, 256), d_raw2, (B, H2, W2, 256), _nhwc_strides(d_raw2), d_buf2,
                     (Hs, Ws), None, tc)
 
     # ---- norm1 + conv1 -----------------------------------------------------------------------------------------
-    g1, b1 = plan._affine("norm1")
     raw1 = tape["raw1"]
-    gy, sums = ops.inorm_bwd_reduce(d_buf2, None, raw1, tape["st1"], g1, b1, None, gdt, True, 1, PAD_REFLECT, True, arena=arena)
-    d_raw1, dgb = ops.inorm_bwd_apply(gy, raw1, tape["st1"], sums, g1)
-    grads["norm1.weight"], grads["norm1.bias"] = _affine_grads(dgb)
+    d_raw1, _ = inorm_backward("norm1", d_buf2, None, raw1, tape["st1"], None, True, 1, PAD_REFLECT, s2d=True)
     if tc:
         # same window view as the forward (engine.StyleNetPlan.forward): taps = kernel rows, 16-pixel x 4-channel windows
         x = tape["x"]
@@ -300,19 +376,14 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
         rows, pitch = 2 * (H1 + 4), (x.shape[3] + 8 + 1) // 2 * 2
         img = ops.image_to_halo(x, 4, PAD_REFLECT, 4, rows, pitch, gdt)
         taps = [(kh >> 1, 0, (kh & 1) * pitch * 4) for kh in range(9)]
-        db = ops.wgrad(ConvSpec(taps, 64, None, 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64), (rows * pitch * 4, 2 * pitch * 4, 8),
-                       d_raw1, (H1, W1), use_tc=True)
-        grads["conv1.conv.weight"] = gp("conv1_wgrad_unpack", lambda t: t.view(64, 9, 16, 4)[:, :, :9, :3].permute(0, 3, 1, 2).contiguous(),
-                                        db, torch.float32)
+        ops.wgrad(ConvSpec(taps, 64, None, 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64), (rows * pitch * 4, 2 * pitch * 4, 8),
+                  d_raw1, (H1, W1), use_tc=True, out=slot("conv1"), out_zeroed=True)
     else:
-        dw1 = ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT)             # tap-major (243, 64)
-        grads["conv1.conv.weight"] = dw1.view(3, 9, 9, 64).permute(3, 0, 1, 2).contiguous()
-    grads["conv1.conv.bias"] = zeros_like_param("conv1.conv.bias")
+        ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT, out=slot("conv1"))             # tap-major (243, 64)
     if side_stream is not None:
         main_stream.wait_stream(side_stream)             # join the weight-gradient branch
-    out = {k: v.to(p[k].dtype) for k, v in grads.items()}
     del keep_alive[:]
-    return out
+    return dict(staging=staging, sums=arena.buf, norm_sums=norm_sums, batch=B, tc=tc)
 
 
 # -------------------------------------------------------------------------------------------------------
@@ -412,9 +483,9 @@ def gram_apply(f: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def sse_backward(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
-    return ops.sse_bwd(a, b, g.reshape(1).float(), grad_dtype_of(a.dtype))
+def sse_backward(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor, coef: float = 1.0) -> torch.Tensor:
+    return ops.sse_bwd(a, b, g.reshape(1).float(), grad_dtype_of(a.dtype), coef=coef)
 
 
-def tv_backward(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
-    return ops.tv_bwd(x, g.reshape(1).float())
+def tv_backward(x: torch.Tensor, g: torch.Tensor, coef: float = 1.0) -> torch.Tensor:
+    return ops.tv_bwd(x, g.reshape(1).float(), coef=coef)

@@ -365,6 +365,216 @@ __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-pass InstanceNorm backward.  A slab = (image n, 16-channel group) is owned by a thread-block CLUSTER of K CTAs
+// (K = 1, 2, 4 or 8; CTA k takes rows [k*rows_per_part, ...)).  Each CTA streams its part of the slab ONCE:
+//   phase 1  g = (fold(gsrc) + extra) * dropout * relu-mask and the raw activation go to shared memory; per-channel
+//            sum g and sum g*xhat are reduced warp -> CTA -> cluster (partials exchanged through distributed shared memory,
+//            summed in rank order: deterministic);
+//   phase 2  d_raw = gamma*rstd * (g - mean(g) - xhat * mean(g*xhat)) from shared memory.
+// HBM/L2 traffic: read gsrc (+extra) + raw, write d_raw (+gy): nothing is read twice, no gy round trip, no atomics.
+// Two adjacent threads cover one pixel's 16 channels = one full 32-byte sector per 16-bit tensor.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dsmem_map(const void* p, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float dsmem_ld_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+constexpr int IBF_THREADS = 256;
+constexpr int IBF_CH = 16;                   // channels per slab
+constexpr int IBF_PL = IBF_THREADS / 2;      // pixel lanes (two threads per pixel)
+
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(IBF_THREADS, 1)
+inorm_bwd_fused_kernel(const TG* __restrict__ gsrc, const TG* __restrict__ extra, const TA* __restrict__ raw,
+                       const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const float* __restrict__ drop, TG* __restrict__ draw, TG* __restrict__ gy_out, float* __restrict__ sums,
+                       HaloLayout L, int relu, float eps, int out_s2d, int rows_per_part, int K) {
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t ibf_smem[];
+  __shared__ float red[IBF_THREADS / 32][32];
+  __shared__ float cta_tot[32];              // [half][s1 x 8 | s2 x 8]
+  __shared__ float tot[32];
+  const int part = blockIdx.x, n = blockIdx.z;
+  const int half = threadIdx.x & 1, pl = threadIdx.x >> 1;
+  const int c0 = blockIdx.y * IBF_CH + half * 8;
+  const int C = L.C, H = L.H, W = L.W;
+  const int r0 = part * rows_per_part, r1 = min(H, r0 + rows_per_part);
+  const int npx = max(0, r1 - r0) * W;
+  TG* g_s = reinterpret_cast<TG*>(ibf_smem);
+  TA* x_s = reinterpret_cast<TA*>(ibf_smem + (size_t)rows_per_part * W * IBF_CH * sizeof(TG));
+  pdl_wait();
+
+  float a[8], b[8], mean[8], rstd[8], ds[8];
+  {
+    const float inv_cnt = 1.f / (float)(H * W);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* st = stats + ((size_t)n * C + c0 + i) * 2;
+      const float m = st[0] * inv_cnt;
+      const float r = rsqrtf(fmaxf(st[1] * inv_cnt - m * m, 0.f) + eps);
+      mean[i] = m; rstd[i] = r;
+      a[i] = gamma[c0 + i] * r; b[i] = beta[c0 + i] - m * a[i];
+      ds[i] = drop ? drop[(size_t)n * C + c0 + i] : 1.f;
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+
+  // ---- phase 1 ------------------------------------------------------------------------------
+  constexpr int U = 4;                       // pixels in flight per thread
+  for (int p0 = pl; p0 < npx; p0 += U * IBF_PL) {
+    Raw8<TG> gc[U], ge[U];
+    Raw8<TA> xr[U];
+    int hh[U], ww[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * IBF_PL;
+      if (p < npx) {
+        const int h = r0 + p / W, w = p - (p / W) * W;
+        hh[u] = h; ww[u] = w;
+        const size_t idx = (((size_t)n * H + h) * W + w) * C + c0;
+        if (gsrc) gc[u] = load_raw8<TG>(gsrc + L.index(n, h + L.pad, w + L.pad, c0));
+        if (extra) ge[u] = load_raw8<TG>(extra + idx);
+        xr[u] = load_raw8<TA>(raw + idx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * IBF_PL;
+      if (p >= npx) continue;
+      const int h = hh[u], w = ww[u];
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+      if (gsrc) {
+        float t[8];
+        raw8_to_f32<TG>(gc[u], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = t[i];
+        if (L.reflect && (h <= L.pad || h >= H - 1 - L.pad || w <= L.pad || w >= W - 1 - L.pad)) {
+          // ReflectionPad2d fold: halo positions that were copied from (h, w) (border pixels only)
+          int hs[3], wsrc[3];
+          const int nh = L.sources(h, H, hs), nw = L.sources(w, W, wsrc);
+          for (int ih = 0; ih < nh; ++ih)
+            for (int iw = (ih == 0 ? 1 : 0); iw < nw; ++iw) {
+              load8<TG>(gsrc + L.index(n, hs[ih], wsrc[iw], c0), t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] += t[i];
+            }
+        }
+      }
+      if (extra) {
+        float t[8];
+        raw8_to_f32<TG>(ge[u], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += t[i];
+      }
+      float x[8];
+      raw8_to_f32<TA>(xr[u], x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = fmaf(x[i], a[i], b[i]);
+        float gv = g[i] * ds[i];
+        if (relu && !(y > 0.f)) gv = 0.f;
+        g[i] = gv;
+        s1[i] += gv;
+        s2[i] = fmaf(gv, (x[i] - mean[i]) * rstd[i], s2[i]);
+      }
+      store8<TG>(g_s + (size_t)p * IBF_CH + half * 8, g);
+      if (sizeof(TA) == 2) *reinterpret_cast<uint4*>(x_s + (size_t)p * IBF_CH + half * 8) = *reinterpret_cast<const uint4*>(&xr[u]);
+      else store8<TA>(x_s + (size_t)p * IBF_CH + half * 8, x);
+      if (gy_out) store8<TG>(gy_out + (((size_t)n * H + h) * W + w) * C + c0, g);
+    }
+  }
+
+  // ---- reduction: lanes of equal parity -> warp -> CTA -> cluster (fixed order everywhere) ----
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 2; o < 32; o <<= 1) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane < 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[wid][lane * 16 + i] = s1[i]; red[wid][lane * 16 + 8 + i] = s2[i]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < IBF_THREADS / 32; ++q) t += red[q][threadIdx.x];
+    cta_tot[threadIdx.x] = t;
+  }
+  if (K > 1) {
+    cluster_barrier();                       // every CTA's cta_tot is written (and visible cluster-wide)
+    if (threadIdx.x < 32) {
+      float t = 0.f;
+      for (int r = 0; r < K; ++r) t += dsmem_ld_f32(dsmem_map(&cta_tot[threadIdx.x], (uint32_t)r));
+      tot[threadIdx.x] = t;
+    }
+  } else {
+    __syncthreads();
+    if (threadIdx.x < 32) tot[threadIdx.x] = cta_tot[threadIdx.x];
+  }
+  __syncthreads();
+  if (part == 0 && threadIdx.x < 32) {
+    // per-(n,c) sums for d gamma / d beta (summed over images by fnst_affine_grads): [n][c][0] = sum g, [1] = sum g*xhat
+    const int hf = threadIdx.x >> 4, j = threadIdx.x & 15, which = j >> 3, ch = blockIdx.y * IBF_CH + hf * 8 + (j & 7);
+    sums[((size_t)n * C + ch) * 2 + which] = tot[threadIdx.x];
+  }
+  float m1[8], m2[8];
+  {
+    const float inv_cnt = 1.f / (float)(H * W);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { m1[i] = tot[half * 16 + i] * inv_cnt; m2[i] = tot[half * 16 + 8 + i] * inv_cnt; }
+  }
+
+  // ---- phase 2 ------------------------------------------------------------------------------
+  for (int p = pl; p < npx; p += IBF_PL) {
+    const int h = r0 + p / W, w = p - (p / W) * W;
+    float g[8], x[8];
+    load8<TG>(g_s + (size_t)p * IBF_CH + half * 8, g);
+    load8<TA>(x_s + (size_t)p * IBF_CH + half * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = a[i] * (g[i] - m1[i] - (x[i] - mean[i]) * rstd[i] * m2[i]);
+    TG* dst = out_s2d ? draw + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c0
+                      : draw + (((size_t)n * H + h) * W + w) * C + c0;
+    store8<TG>(dst, g);
+  }
+  if (K > 1) cluster_barrier();              // no CTA of the cluster leaves while a partner may still read its cta_tot
+}
+
+// d gamma[c] = sum_n sums[n][c][1], d beta[c] = sum_n sums[n][c][0] for a list of InstanceNorm layers in one launch
+// (fixed summation order).  table[l] = {offset of the layer's [N][C][2] block in `sums`, C, offset of d gamma in `out`,
+// offset of d beta in `out`}; one block per (layer, 256-channel chunk).
+struct AffineGradEntry { int64_t src, dgamma, dbeta; int32_t C, pad_; };
+__global__ void __launch_bounds__(256) affine_grads_kernel(const float* __restrict__ sums, const AffineGradEntry* __restrict__ table,
+                                                           int N, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const AffineGradEntry e = table[blockIdx.x];
+  for (int c = blockIdx.y * 256 + threadIdx.x; c < e.C; c += gridDim.y * 256) {
+    float dg = 0.f, db = 0.f;
+    for (int i = 0; i < N; ++i) { db += sums[e.src + ((size_t)i * e.C + c) * 2 + 0]; dg += sums[e.src + ((size_t)i * e.C + c) * 2 + 1]; }
+    out[e.dgamma + c] = dg; out[e.dbeta + c] = db;
+  }
+}
+
 template <typename TA, typename TG>
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const TA* __restrict__ in, const TG* __restrict__ gout,
                                                            const TG* __restrict__ extra, TG* __restrict__ gin,
@@ -423,11 +633,11 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const TA* __restrict_
 
 template <typename TA, typename TB, typename TG>
 __global__ void __launch_bounds__(256) sse_bwd_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t count,
-                                                      int64_t period, const float* __restrict__ scale, TG* __restrict__ da,
-                                                      int relu_mask) {
+                                                      int64_t period, const float* __restrict__ scale, float coef,
+                                                      TG* __restrict__ da, int relu_mask) {
   pdl_trigger();
   pdl_wait();
-  const float s = 2.f * scale[0];
+  const float s = 2.f * coef * scale[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     const float av = to_f32<TA>(a[i]);
     float v = s * (av - to_f32<TB>(b[i % period]));
@@ -476,11 +686,11 @@ __global__ void __launch_bounds__(256) gram_diff_sym_kernel(const float* __restr
 }
 
 __global__ void __launch_bounds__(256) tv_bwd_kernel(const float* __restrict__ img, int planes, int H, int W,
-                                                     const float* __restrict__ scale, float* __restrict__ dimg) {
+                                                     const float* __restrict__ scale, float coef, float* __restrict__ dimg) {
   pdl_trigger();
   pdl_wait();
   const int64_t total = (int64_t)planes * H * W;
-  const float s = 2.f * scale[0];
+  const float s = 2.f * coef * scale[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = i % W; const int y = (i / W) % H;
     const float v = img[i];
@@ -616,6 +826,57 @@ extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float
   return launch_status("inorm_bwd_apply");
 }
 
+// Number of cluster CTAs per slab the fused kernel needs for an h x w plane (0: the plane does not fit, use
+// fnst_inorm_bwd_reduce + fnst_inorm_bwd_apply).
+static int ibf_parts(int h, int w, int act_dtype, int g_dtype) {
+  const size_t per_px = (size_t)IBF_CH * (dtype_size(act_dtype) + dtype_size(g_dtype));
+  const size_t budget = 200 * 1024;
+  for (int k = 1; k <= 8; k *= 2) {
+    const int rows = (h + k - 1) / k;
+    if ((size_t)rows * w * per_px <= budget) return k;
+  }
+  return 0;
+}
+
+extern "C" int fnst_inorm_bwd_fused_parts(int h, int w, int c, int act_dtype, int g_dtype) {
+  if (c % IBF_CH != 0 || h <= 0 || w <= 0) return 0;
+  return ibf_parts(h, w, act_dtype, g_dtype);
+}
+
+extern "C" int fnst_inorm_bwd_fused(const void* gsrc, const void* extra, const void* raw, const float* stats,
+                                    const float* gamma, const float* beta, const float* drop, void* draw, void* gy_out,
+                                    float* sums, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
+                                    int pad, int pad_mode, int s2d, int out_s2d, int device, void* stream) {
+  FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && draw && sums, "inorm_bwd_fused: null pointer");
+  FNST_CHECK_ARG(c % IBF_CH == 0, "inorm_bwd_fused: channel count %d must be a multiple of %d", c, IBF_CH);
+  FNST_CHECK_ARG(!out_s2d || (h % 2 == 0 && w % 2 == 0), "inorm_bwd_fused: space-to-depth output needs even h, w");
+  const int K = ibf_parts(h, w, act_dtype, g_dtype);
+  FNST_CHECK_ARG(K > 0, "inorm_bwd_fused: a %dx%d plane does not fit the shared memory of 8 CTAs (use the two-pass operators)", h, w);
+  FNST_DEVICE(device);
+  HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d};
+  const int rows = (h + K - 1) / K;
+  const size_t smem = (size_t)rows * w * IBF_CH * (dtype_size(act_dtype) + dtype_size(g_dtype));
+  dim3 grid(K, c / IBF_CH, n);
+  FNST_DISPATCH_DTYPE(act_dtype, TA, {
+    FNST_DISPATCH_DTYPE(g_dtype, TG, {
+      auto kern = inorm_bwd_fused_kernel<TA, TG>;
+      FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      launch_pdl_cluster(kern, grid, dim3(IBF_THREADS), smem, (cudaStream_t)stream, K,
+          reinterpret_cast<const TG*>(gsrc), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(raw), stats, gamma,
+          beta, drop, reinterpret_cast<TG*>(draw), reinterpret_cast<TG*>(gy_out), sums, L, relu, eps, out_s2d, rows, K);
+    });
+  });
+  return launch_status("inorm_bwd_fused");
+}
+
+extern "C" int fnst_affine_grads(const float* sums, const void* table, int layers, int n, int max_c, float* out, int device, void* stream) {
+  FNST_CHECK_ARG(sums && table && out && layers > 0 && n > 0 && max_c > 0, "affine_grads: bad arguments");
+  FNST_DEVICE(device);
+  dim3 grid(layers, (max_c + 255) / 256);
+  launch_pdl(affine_grads_kernel, grid, dim3(256), 0, (cudaStream_t)stream, sums, reinterpret_cast<const AffineGradEntry*>(table), n, out);
+  return launch_status("affine_grads");
+}
+
 extern "C" int fnst_maxpool2_bwd(const void* in, const void* gout, const void* extra, void* gin, int n, int h, int w, int c,
                                  int act_dtype, int g_dtype, int device, void* stream) {
   FNST_CHECK_ARG(in && gout && gin && c % 8 == 0 && h >= 2 && w >= 2, "maxpool2_bwd: bad arguments");
@@ -632,14 +893,14 @@ extern "C" int fnst_maxpool2_bwd(const void* in, const void* gout, const void* e
 }
 
 extern "C" int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
-                            const float* scale, void* da, int g_dtype, int relu_mask, int device, void* stream) {
+                            const float* scale, float coef, void* da, int g_dtype, int relu_mask, int device, void* stream) {
   FNST_CHECK_ARG(a && b && scale && da && count > 0 && b_period > 0, "sse_bwd: bad arguments");
   FNST_DEVICE(device);
   FNST_DISPATCH_DTYPE(dtype_a, TA, {
     FNST_DISPATCH_DTYPE(dtype_b, TB, {
       FNST_DISPATCH_DTYPE(g_dtype, TG, {
         launch_pdl(sse_bwd_kernel<TA, TB, TG>, dim3(grid_cap(count / 4)), dim3(256), 0, (cudaStream_t)stream, 
-            reinterpret_cast<const TA*>(a), reinterpret_cast<const TB*>(b), count, b_period, scale, reinterpret_cast<TG*>(da), relu_mask);
+            reinterpret_cast<const TA*>(a), reinterpret_cast<const TB*>(b), count, b_period, scale, coef, reinterpret_cast<TG*>(da), relu_mask);
       });
     });
   });
@@ -672,10 +933,11 @@ extern "C" int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c,
   return launch_status("gram_diff_sym");
 }
 
-extern "C" int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream) {
+extern "C" int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float coef, float* dimg, int device,
+                           void* stream) {
   FNST_CHECK_ARG(img && scale && dimg && planes > 0 && h > 0 && w > 0, "tv_bwd: bad arguments");
   FNST_DEVICE(device);
-  launch_pdl(tv_bwd_kernel, dim3(grid_cap((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w, scale, dimg);
+  launch_pdl(tv_bwd_kernel, dim3(grid_cap((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w, scale, coef, dimg);
   return launch_status("tv_bwd");
 }
 

@@ -17,8 +17,8 @@ template <typename TI, typename T, int U, bool SPLIT>
 __global__ void __launch_bounds__(256) inorm_apply_kernel(const TI* __restrict__ raw, const float* __restrict__ stats,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ drop, const T* __restrict__ res, int res_pad,
-                                                          T* __restrict__ out, int H, int W, int C, int relu, float eps,
-                                                          int pad, int pad_mode, int s2d, int rows_per_block) {
+                                                          T* __restrict__ out, __nv_bfloat16* __restrict__ out2, int H, int W, int C,
+                                                          int relu, float eps, int pad, int pad_mode, int s2d, int rows_per_block) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float s_ab[];          // [2][C]: per-channel scale a and shift b of this image (keeps registers low)
@@ -109,6 +109,14 @@ __global__ void __launch_bounds__(256) inorm_apply_kernel(const TI* __restrict__
         T* dst;
         if (!s2d) dst = out + (((size_t)n * Hp + hp) * Wp + wp) * CO + c0;
         else dst = out + (((size_t)n * Hp2 + (hp >> 1)) * Wp2 + (wp >> 1)) * (4 * CO) + ((hp & 1) * 2 + (wp & 1)) * CO + c0;
+        if (out2) {
+          // second copy of the same activation in bfloat16, same geometry with C channels per pixel: the weight-gradient
+          // GEMM's operand (kind::f16 MMAs take ONE 16-bit format and gradients are bf16), written here instead of by a
+          // separate cast pass over the tensor
+          __nv_bfloat16* d2 = !s2d ? out2 + (((size_t)n * Hp + hp) * Wp + wp) * C + c0
+                                   : out2 + (((size_t)n * Hp2 + (hp >> 1)) * Wp2 + (wp >> 1)) * (4 * C) + ((hp & 1) * 2 + (wp & 1)) * C + c0;
+          store8<__nv_bfloat16>(d2, vv);
+        }
         if (SPLIT) {
           float hi[8], lo[8];
 #pragma unroll
@@ -181,6 +189,85 @@ __global__ void __launch_bounds__(256) tv_kernel(const float* __restrict__ img, 
     if (x + 1 < W) { const float d = img[i + 1] - v; s = fmaf(d, d, s); }
   }
   block_accumulate(s, acc);
+}
+
+// ---- loss scalars in one launch (no memset in front, no host arithmetic behind) ---------------------------------
+// workspace: double partial[LOSS_MAX_BLOCKS] followed by one unsigned counter; zeroed once by the caller.  Every block
+// stores its partial, the last block to finish sums them in block order (deterministic), writes scale * sum to out[0]
+// and leaves the counter at zero for the next launch.
+constexpr int LOSS_MAX_BLOCKS = 148 * 16;
+
+__device__ __forceinline__ void loss_finish(float v, double* ws, float scale, float* out, int accumulate) {
+  __shared__ float s_part[32];
+  __shared__ bool s_last;
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += (double)s_part[i];
+    ws[blockIdx.x] = t;
+    __threadfence();
+    unsigned* counter = reinterpret_cast<unsigned*>(ws + LOSS_MAX_BLOCKS);
+    s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last block: ordered sum of the partials (pairwise over 256 strided lanes, fixed order)
+  double t = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(ws + i);
+  __shared__ double s_d[256];
+  s_d[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_d[threadIdx.x] += s_d[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float r = (float)(s_d[0] * (double)scale);
+    out[0] = accumulate ? out[0] + r : r;
+    *reinterpret_cast<unsigned*>(ws + LOSS_MAX_BLOCKS) = 0u;
+  }
+}
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) sse_scaled_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t count,
+                                                         int64_t period, float scale, double* ws, float* out, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
+  float s = 0.f;
+  if (period == count && count % 8 == 0) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count / 8; i += (int64_t)gridDim.x * blockDim.x) {
+      float x[8], y[8];
+      load8<TA>(a + i * 8, x);
+      load8<TB>(b + i * 8, y);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = x[k] - y[k]; s = fmaf(d, d, s); }
+    }
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+      const float d = to_f32<TA>(a[i]) - to_f32<TB>(b[i % period]);
+      s = fmaf(d, d, s);
+    }
+  }
+  loss_finish(s, ws, scale, out, accumulate);
+}
+
+__global__ void __launch_bounds__(256) tv_scaled_kernel(const float* __restrict__ img, int planes, int H, int W, float scale,
+                                                        double* ws, float* out) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t total = (int64_t)planes * H * W;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = i % W; const int y = (i / W) % H;
+    const float v = img[i];
+    if (y + 1 < H) { const float d = img[i + W] - v; s = fmaf(d, d, s); }
+    if (x + 1 < W) { const float d = img[i + 1] - v; s = fmaf(d, d, s); }
+  }
+  loss_finish(s, ws, scale, out, 0);
 }
 
 // [HW][C] (T) <-> [C][HW] (fp32) per image, 32x32 smem tiles.
@@ -320,7 +407,7 @@ static int grid_for(int64_t work_items, int threads = 256) {
 using namespace fnst;
 
 extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, const float* beta,
-                                const float* drop, const void* res, int res_pad, void* out,
+                                const float* drop, const void* res, int res_pad, void* out, void* out_bf16,
                                 int n, int h, int w, int c, int dtype, int relu, float eps,
                                 int pad, int pad_mode, int s2d, int raw_dtype, int split, int device, void* stream) {
   FNST_CHECK_ARG(raw_dtype == dtype || (raw_dtype == FNST_F32 && dtype == FNST_F16 && split),
@@ -342,14 +429,14 @@ extern "C" int fnst_inorm_apply(const void* raw, const float* stats, const float
   if (split) {
     launch_pdl(inorm_apply_kernel<float, __half, 2, true>, dim3(grid), dim3(256), sizeof(float) * 2 * c, (cudaStream_t)stream, 
         reinterpret_cast<const float*>(raw), stats, gamma, beta, drop, reinterpret_cast<const __half*>(res), res_pad,
-        reinterpret_cast<__half*>(out), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
+        reinterpret_cast<__half*>(out), reinterpret_cast<__nv_bfloat16*>(out_bf16), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
     return launch_status("inorm_apply");
   }
   FNST_DISPATCH_DTYPE(dtype, T, {
     auto kern = inorm_apply_kernel<T, T, 2, false>;   // 2 pixels (x raw + residual) in flight per thread: measured best, 77-96 % of copy peak
     launch_pdl(kern, dim3(grid), dim3(256), sizeof(float) * 2 * c, (cudaStream_t)stream,
         reinterpret_cast<const T*>(raw), stats, gamma, beta, drop, reinterpret_cast<const T*>(res), res_pad,
-        reinterpret_cast<T*>(out), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
+        reinterpret_cast<T*>(out), reinterpret_cast<__nv_bfloat16*>(out_bf16), h, w, c, relu, eps, pad, pad_mode, s2d, rows_per_block);
   });
   return launch_status("inorm_apply");
 }
@@ -384,6 +471,31 @@ extern "C" int fnst_tv(const float* img, int planes, int h, int w, double* acc, 
   FNST_DEVICE(device);
   launch_pdl(tv_kernel, dim3(grid_for((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w, acc);
   return launch_status("tv");
+}
+
+extern "C" int64_t fnst_loss_workspace_bytes(void) { return (int64_t)sizeof(double) * (LOSS_MAX_BLOCKS + 1); }
+
+extern "C" int fnst_sse_scaled(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b, float scale,
+                               void* workspace, float* out, int accumulate, int device, void* stream) {
+  FNST_CHECK_ARG(a && b && workspace && out && count > 0 && b_period > 0, "sse_scaled: bad arguments");
+  FNST_DEVICE(device);
+  FNST_DISPATCH_DTYPE(dtype_a, TA, {
+    FNST_DISPATCH_DTYPE(dtype_b, TB, {
+      launch_pdl(sse_scaled_kernel<TA, TB>, dim3(grid_for(count / 8)), dim3(256), 0, (cudaStream_t)stream,
+          reinterpret_cast<const TA*>(a), reinterpret_cast<const TB*>(b), count, b_period, scale, reinterpret_cast<double*>(workspace),
+          out, accumulate);
+    });
+  });
+  return launch_status("sse_scaled");
+}
+
+extern "C" int fnst_tv_scaled(const float* img, int planes, int h, int w, float scale, void* workspace, float* out, int device,
+                              void* stream) {
+  FNST_CHECK_ARG(img && workspace && out && planes > 0 && h > 0 && w > 0, "tv_scaled: bad arguments");
+  FNST_DEVICE(device);
+  launch_pdl(tv_scaled_kernel, dim3(grid_for((int64_t)planes * h * w / 4)), dim3(256), 0, (cudaStream_t)stream, img, planes, h, w,
+             scale, reinterpret_cast<double*>(workspace), out);
+  return launch_status("tv_scaled");
 }
 
 extern "C" int fnst_nhwc_to_nchw(const void* in, float* out, int n, int h, int w, int c, int dtype, int device, void* stream) {

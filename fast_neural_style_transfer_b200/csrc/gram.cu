@@ -63,11 +63,12 @@ int gram_tc(const void* feat, float* out, int n, int hw, int c, int dtype, int d
 
 using namespace fnst;
 
-extern "C" int fnst_gram(const void* feat, float* out, int n, int hw, int c, int dtype, int use_tc, int device, void* stream) {
+extern "C" int fnst_gram(const void* feat, float* out, int n, int hw, int c, int dtype, int use_tc, int prezeroed, int device,
+                         void* stream) {
   FNST_CHECK_ARG(feat && out && n > 0 && hw > 0 && c > 0, "gram: bad arguments");
   FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
-  FNST_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * c * c, st));
+  if (!prezeroed) FNST_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n * c * c, st));
   if (use_tc) return gram_tc(feat, out, n, hw, c, dtype, device, st);
   const int ksplit = (hw + GR_PIX - 1) / GR_PIX;
   dim3 grid((c + GR_T - 1) / GR_T, (c + GR_T - 1) / GR_T, n * ksplit);

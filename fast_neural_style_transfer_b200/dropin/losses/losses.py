@@ -37,10 +37,10 @@ def content_loss(input_features, target_features):
     """SSE(feat[4], target[4]) / (c*h*w) (losses/losses.py:46-60)."""
     a, t = input_features[4], target_features[4]
     _, c, h, w = a.size()
-    return _fn.sse(a, t) / (c * h * w)
+    return _fn.sse(a, t, scale=1.0 / (c * h * w))          # normalisation folded into the reduction kernel
 
 
 def total_variation_loss(img):
     """(sum dh^2 + sum dw^2) / (b*c*h*w) (losses/losses.py:62-73)."""
     b, c, h, w = img.size()
-    return _fn.tv(img) / (b * c * h * w)
+    return _fn.tv(img, scale=1.0 / (b * c * h * w))

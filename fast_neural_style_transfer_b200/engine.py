@@ -269,6 +269,10 @@ class StyleNetPlan:
         dev, dt, tc = x.device, self.dtype, self.use_tc
         w = self.w
         new = lambda *s: torch.empty(s, dtype=dt, device=dev)
+        # training on the fp16 path: every saved activation is also written as bfloat16 by the kernel that produces it (the
+        # weight-gradient GEMM multiplies it with a bf16 gradient and kind::f16 MMAs take one 16-bit format)
+        twin = tape is not None and tc and dt != torch.bfloat16
+        new2 = (lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)) if twin else (lambda *s: None)
         arena = ops.ZeroArena(B * 2 * STATS_CHANNELS, dev)          # all InstanceNorm statistics: one memset per forward
         stats = lambda c: arena.take(B, c, 2)
         if H <= 4 or W <= 4:
@@ -291,9 +295,14 @@ class StyleNetPlan:
         # (the space-to-depth buffer is written completely by inorm_apply when the padded extent is even; with an odd
         # extent the last half-filled row / column of phases must read as zero)
         buf2 = (torch.empty if Hp % 2 == 0 and Wp % 2 == 0 else torch.zeros)((B, Hs, Ws, 256), dtype=dt, device=dev)
+        buf2_b = (torch.empty if Hp % 2 == 0 and Wp % 2 == 0 else torch.zeros)((B, Hs, Ws, 256), dtype=torch.bfloat16, device=dev) if twin else None
         Hq, Wq = H4 + 8, W4 + 8
         flat = torch.empty(B * Hq * Wq * 32 + 128, dtype=dt, device=dev)   # slack: paired / 4-pixel window views
         flat[-128:].zero_()
+        flat_b = None
+        if twin:
+            flat_b = torch.empty(B * Hq * Wq * 32 + 128, dtype=torch.bfloat16, device=dev)
+            flat_b[-128:].zero_()
         raw1, st1 = new(B, H1, W1, 64), stats(64)
         if tc:
             # tensor-core form: 4-channel reflect-halo image; kernel row kh = tap (row pair kh>>1, row parity via the
@@ -307,16 +316,18 @@ class StyleNetPlan:
             ops.conv_first(x, w["conv1"], None, 9, 2, 4, PAD_REFLECT, False, raw1, st1)
         # norm1 + relu -> space-to-depth halo buffer for the stride-2 conv2
         g, b = self._affine("norm1")
-        ops.inorm_apply(raw1, st1, g, b, buf2, relu=True, pad=1, pad_mode=PAD_REFLECT, s2d=True)
+        ops.inorm_apply(raw1, st1, g, b, buf2, relu=True, pad=1, pad_mode=PAD_REFLECT, s2d=True, out2=buf2_b)
         # conv2: 3x3 stride 2 as a 9-tap gather over the s2d buffer
         raw2, st2 = new(B, H2, W2, 256), stats(256)
         spec = ConvSpec(taps_s2d_3x3(64), 64, w["conv2"], 256, 256)
         ops.conv_gather(spec, buf2, (B, Hs, Ws, 256), _nhwc_strides(buf2), raw2, (H2, W2), st2, tc, stats_zeroed=True)
-        cur = new(B, H2 + 2, W2 + 2, 256)
+        cur, cur_b = new(B, H2 + 2, W2 + 2, 256), new2(B, H2 + 2, W2 + 2, 256)
         g, b = self._affine("norm2")
-        ops.inorm_apply(raw2, st2, g, b, cur, relu=True, pad=1, pad_mode=PAD_REFLECT)
+        ops.inorm_apply(raw2, st2, g, b, cur, relu=True, pad=1, pad_mode=PAD_REFLECT, out2=cur_b)
         if tape is not None:
             tape.update(raw1=raw1, st1=st1, buf2=buf2, raw2=raw2, st2=st2, trunk=[cur])
+            # bf16 twins (None when the activations already are bf16 / fp32): operands of the weight-gradient GEMMs
+            tape["w"] = dict(buf2=buf2_b, trunk=[cur_b], mid=[], act4_flat=flat_b)
 
         # residual trunk
         taps9 = taps_kxk(3)
@@ -324,21 +335,24 @@ class StyleNetPlan:
             raw_a, st_a = new(B, H2, W2, 256), stats(256)
             ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}a"], 256, 256, tag=f"res{i}a"), cur, (B, H2 + 2, W2 + 2, 256),
                             _nhwc_strides(cur), raw_a, (H2, W2), st_a, tc, stats_zeroed=True)
-            mid = new(B, H2 + 2, W2 + 2, 256)
+            mid, mid_b = new(B, H2 + 2, W2 + 2, 256), new2(B, H2 + 2, W2 + 2, 256)
             g, b = self._affine(f"res_blocks.{i}.in1")
             drop = None if drop_scales is None else drop_scales[i].float().contiguous()
-            ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop)
+            ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop, out2=mid_b)
             raw_b, st_b = new(B, H2, W2, 256), stats(256)
             ops.conv_gather(ConvSpec(taps9, 256, w[f"res{i}b"], 256, 256, tag=f"res{i}b"), mid, (B, H2 + 2, W2 + 2, 256),
                             _nhwc_strides(mid), raw_b, (H2, W2), st_b, tc, stats_zeroed=True)
             last = i == 4
             nxt = new(B, H2, W2, 256) if last else new(B, H2 + 2, W2 + 2, 256)
+            nxt_b = new2(B, H2, W2, 256) if last else new2(B, H2 + 2, W2 + 2, 256)
             g, b = self._affine(f"res_blocks.{i}.in2")
             ops.inorm_apply(raw_b, st_b, g, b, nxt, relu=False, pad=0 if last else 1,
-                            pad_mode=PAD_NONE if last else PAD_REFLECT, res=cur, res_pad=1)
+                            pad_mode=PAD_NONE if last else PAD_REFLECT, res=cur, res_pad=1, out2=nxt_b)
             if tape is not None:
                 tape.setdefault("blocks", []).append(dict(raw_a=raw_a, st_a=st_a, mid=mid, raw_b=raw_b, st_b=st_b, drop=drop))
                 tape["trunk"].append(nxt)
+                tape["w"]["trunk"].append(nxt_b)
+                tape["w"]["mid"].append(mid_b)
             cur = nxt
 
         # up1: ConvTranspose2d(256->64) = 2x2-tap gather, 256 columns, depth-to-space
@@ -346,9 +360,9 @@ class StyleNetPlan:
         raw3, st3 = new(B, H3, W3, 64), stats(64)
         ops.conv_gather(ConvSpec(TAPS_2X2, 256, w["up1"], 256, 64, epilogue=EPI_D2S), cur, (B, H2, W2, 256),
                         _nhwc_strides(cur), raw3, (H2, W2), st3, tc, stats_zeroed=True)
-        act3 = new(B, H3, W3, 64)
+        act3, act3_b = new(B, H3, W3, 64), new2(B, H3, W3, 64)
         g, b = self._affine("norm3")
-        ops.inorm_apply(raw3, st3, g, b, act3, relu=True)
+        ops.inorm_apply(raw3, st3, g, b, act3, relu=True, out2=act3_b)
         # up2: ConvTranspose2d(64->32)
         raw4, st4 = new(B, H4, W4, 32), stats(32)
         ops.conv_gather(ConvSpec(TAPS_2X2, 64, w["up2"], 128, 32, epilogue=EPI_D2S), act3, (B, H3, W3, 64),
@@ -356,7 +370,7 @@ class StyleNetPlan:
         # norm4 + relu -> reflect-4 halo buffer (+ slack so the paired view of the last pixel stays in bounds)
         act4 = flat[:B * Hq * Wq * 32].view(B, Hq, Wq, 32)
         g, b = self._affine("norm4")
-        ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT)
+        ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT, out2=flat_b)
         # final_conv 9x9 -> NCHW fp32
         y = torch.empty((B, 3, H4, W4), dtype=torch.float32, device=dev)
         if tc and FINAL_STREAM and B * H4 * W4 >= FINAL_STREAM_MIN_PIXELS:
@@ -371,6 +385,7 @@ class StyleNetPlan:
             ops.conv_gather(spec, act4, (B, Hq, Wq, 32), _nhwc_strides(act4), y, (H4, W4), None, False)
         if tape is not None:
             tape.update(raw3=raw3, st3=st3, act3=act3, raw4=raw4, st4=st4, act4=act4, act4_flat=flat, x=x)
+            tape["w"]["act3"] = act3_b
         return y
 
 

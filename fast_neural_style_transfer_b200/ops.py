@@ -209,11 +209,14 @@ def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
 def inorm_apply(raw: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, out: torch.Tensor,
                 relu: bool, pad: int = 0, pad_mode: int = _lib.PAD_NONE, s2d: bool = False,
                 drop: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, res_pad: int = 0,
-                eps: float = 1e-5, split: bool = False) -> None:
-    """split: raw is fp32, out/res are fp16 buffers with 2c channels per pixel [hi | lo] (fp16x3 path)."""
+                eps: float = 1e-5, split: bool = False, out2: Optional[torch.Tensor] = None) -> None:
+    """split: raw is fp32, out/res are fp16 buffers with 2c channels per pixel [hi | lo] (fp16x3 path).
+    out2: optional bfloat16 twin of `out` (same geometry, c channels per pixel) for the weight-gradient GEMM."""
     n, h, w, c = raw.shape
     dev, st = _ctx(raw)
-    check(lib.fnst_inorm_apply(_ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(res), res_pad, _ptr(out),
+    if out2 is not None:
+        assert out2.dtype == torch.bfloat16 and out2.is_contiguous() and out2.numel() * (2 if split else 1) >= out.numel()
+    check(lib.fnst_inorm_apply(_ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(res), res_pad, _ptr(out), _ptr(out2),
                                n, h, w, c, dt(out.dtype), int(relu), eps, pad, pad_mode, int(s2d), dt(raw.dtype), int(split),
                                dev, st), "inorm_apply")
     _count()
@@ -228,13 +231,17 @@ def maxpool2(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gram(feat_nhwc: torch.Tensor, use_tc: bool) -> torch.Tensor:
+def gram(feat_nhwc: torch.Tensor, use_tc: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out: optional ZEROED fp32 (n,c,c) tensor (e.g. a ZeroArena slice): the call then issues no memset."""
     n, h, w, c = feat_nhwc.shape
     assert feat_nhwc.is_contiguous()
-    out = torch.empty((n, c, c), dtype=torch.float32, device=feat_nhwc.device)
+    prezeroed = out is not None
+    if out is None:
+        out = torch.empty((n, c, c), dtype=torch.float32, device=feat_nhwc.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (n, c, c)
     dev, st = _ctx(feat_nhwc)
-    check(lib.fnst_gram(_ptr(feat_nhwc), _ptr(out), n, h * w, c, dt(feat_nhwc.dtype), int(use_tc), dev, st), "gram")
-    _count(2)
+    check(lib.fnst_gram(_ptr(feat_nhwc), _ptr(out), n, h * w, c, dt(feat_nhwc.dtype), int(use_tc), int(prezeroed), dev, st), "gram")
+    _count(1 if prezeroed else 2)
     return out
 
 
@@ -305,10 +312,12 @@ def wgrad(spec: ConvSpec, a: torch.Tensor, a_dims, a_strides, g: torch.Tensor, o
     return out
 
 
-def conv_first_wgrad(x: torch.Tensor, g: torch.Tensor, k: int, stride: int, pad: int, pad_mode: int) -> torch.Tensor:
+def conv_first_wgrad(x: torch.Tensor, g: torch.Tensor, k: int, stride: int, pad: int, pad_mode: int,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     n, c, h, w = x.shape
     c_out = g.shape[-1]
-    dw = torch.empty((3 * k * k, c_out), dtype=torch.float32, device=x.device)
+    dw = torch.empty((3 * k * k, c_out), dtype=torch.float32, device=x.device) if out is None else out
+    assert dw.is_contiguous() and dw.dtype == torch.float32 and dw.numel() == 3 * k * k * c_out
     dev, st = _ctx(x)
     check(lib.fnst_conv_first_wgrad(_ptr(x), n, h, w, _ptr(g), dt(g.dtype), c_out, k, stride, pad, pad_mode, _ptr(dw), dev, st),
           "conv_first_wgrad")
@@ -317,12 +326,16 @@ def conv_first_wgrad(x: torch.Tensor, g: torch.Tensor, k: int, stride: int, pad:
 
 
 def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=_lib.PAD_NONE, s2d=False,
-                     eps: float = 1e-5, arena: Optional[ZeroArena] = None):
-    """arena: take the (zeroed) reduction buffers from it instead of having the call memset fresh ones."""
+                     eps: float = 1e-5, arena: Optional[ZeroArena] = None, sums: Optional[torch.Tensor] = None):
+    """arena / sums: take the (zeroed) reduction buffer from the arena, or use the given zeroed [n,c,2] tensor, instead of
+    having the call memset a fresh one."""
     n, h, w, c = raw.shape
     gy = torch.empty((n, h, w, c), dtype=gdtype, device=raw.device)
     dgb = None                   # d gamma / d beta come out of pass 2 (inorm_bwd_apply): no same-address atomics in pass 1
-    if arena is not None:
+    prezeroed = arena is not None or sums is not None
+    if sums is not None:
+        assert sums.dtype == torch.float32 and sums.is_contiguous() and sums.numel() == n * c * 2
+    elif arena is not None:
         sums = arena.take(n, c, 2)
     else:
         sums = torch.empty((n, c, 2), dtype=torch.float32, device=raw.device)
@@ -331,22 +344,66 @@ def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, p
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_bwd_reduce(_ptr(gsrc), _ptr(extra), _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(gy),
                                     _ptr(sums), _ptr(dgb), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
-                                    int(arena is not None), dev, st), "inorm_bwd_reduce")
-    _count(1 if arena is not None else 2)
+                                    int(prezeroed), dev, st), "inorm_bwd_reduce")
+    _count(1 if prezeroed else 2)
     return gy, sums
 
 
-def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-5):
-    """Returns (d_raw, dgb) with dgb = [d gamma; d beta] (2, c) fp32."""
+def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-5, want_dgb: bool = True):
+    """Returns (d_raw, dgb) with dgb = [d gamma; d beta] (2, c) fp32 (None unless want_dgb)."""
     n, h, w, c = raw.shape
     shape = (n, h // 2, w // 2, 4 * c) if out_s2d else (n, h, w, c)
     draw = torch.empty(shape, dtype=gy.dtype, device=raw.device)
-    dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device) if want_dgb else None
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_bwd_apply(_ptr(gy), _ptr(raw), _ptr(stats), _ptr(sums), _ptr(gamma), _ptr(draw), _ptr(dgb), n, h, w, c,
                                    dt(raw.dtype), dt(gy.dtype), eps, int(out_s2d), dev, st), "inorm_bwd_apply")
     _count()
     return draw, dgb
+
+
+def inorm_bwd_fused_parts(raw: torch.Tensor, gdtype: torch.dtype) -> int:
+    """Cluster size the one-pass kernel needs for raw's plane; 0 = does not fit (use inorm_bwd_reduce + inorm_bwd_apply)."""
+    n, h, w, c = raw.shape
+    return int(lib.fnst_inorm_bwd_fused_parts(h, w, c, dt(raw.dtype), dt(gdtype)))
+
+
+def inorm_bwd_fused(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=_lib.PAD_NONE, s2d=False,
+                    out_s2d=False, want_gy=False, sums: Optional[torch.Tensor] = None, eps: float = 1e-5):
+    """InstanceNorm backward in one pass (reduce + apply).  Returns (d_raw, gy or None, sums [n,c,2])."""
+    n, h, w, c = raw.shape
+    shape = (n, h // 2, w // 2, 4 * c) if out_s2d else (n, h, w, c)
+    draw = torch.empty(shape, dtype=gdtype, device=raw.device)
+    gy = torch.empty((n, h, w, c), dtype=gdtype, device=raw.device) if want_gy else None
+    if sums is None:
+        sums = torch.empty((n, c, 2), dtype=torch.float32, device=raw.device)
+    for t in (gsrc, extra):
+        assert t is None or (t.dtype == gdtype and t.is_contiguous())
+    dev, st = _ctx(raw)
+    check(lib.fnst_inorm_bwd_fused(_ptr(gsrc), _ptr(extra), _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(draw),
+                                   _ptr(gy), _ptr(sums), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
+                                   int(out_s2d), dev, st), "inorm_bwd_fused")
+    _count()
+    return draw, gy, sums
+
+
+_AFFINE_TABLES = {}
+
+
+def affine_grads(sums_flat: torch.Tensor, entries: Sequence[Tuple[int, int, int, int]], n: int, out: torch.Tensor) -> None:
+    """entries: (offset of the layer's [n][C][2] block in sums_flat, C, offset of d gamma in out, offset of d beta in out).
+    out[dgamma + c] = sum over images of sum(gy*xhat), out[dbeta + c] = sum over images of sum(gy)."""
+    key = (tuple(entries), sums_flat.device)
+    table = _AFFINE_TABLES.get(key)
+    if table is None:
+        rows = []
+        for src, c, dg, db in entries:
+            rows += [src, dg, db, c]              # int64 src, dgamma, dbeta; {int32 C, int32 pad} packed into one int64
+        table = _AFFINE_TABLES[key] = torch.tensor(rows, dtype=torch.int64).to(sums_flat.device)
+    assert sums_flat.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
+    dev, st = _ctx(sums_flat)
+    check(lib.fnst_affine_grads(_ptr(sums_flat), _ptr(table), len(entries), n, max(e[1] for e in entries), _ptr(out), dev, st), "affine_grads")
+    _count()
 
 
 def maxpool2_bwd(inp, gout, extra):
@@ -360,29 +417,31 @@ def maxpool2_bwd(inp, gout, extra):
     return gin
 
 
-def sse_bwd(a, b, scale, gdtype, relu_mask=False):
-    """2*scale*(a-b) (b broadcast); scale is a 1-element fp32 CUDA tensor."""
+def sse_bwd(a, b, scale, gdtype, relu_mask=False, coef: float = 1.0):
+    """2*coef*scale*(a-b) (b broadcast); scale is a 1-element fp32 CUDA tensor, coef a host constant."""
     assert a.is_contiguous() and b.is_contiguous() and scale.dtype == torch.float32
     da = torch.empty(a.shape, dtype=gdtype, device=a.device)
     dev, st = _ctx(a)
-    check(lib.fnst_sse_bwd(_ptr(a), _ptr(b), a.numel(), b.numel(), dt(a.dtype), dt(b.dtype), _ptr(scale), _ptr(da), dt(gdtype),
-                           int(relu_mask), dev, st), "sse_bwd")
+    check(lib.fnst_sse_bwd(_ptr(a), _ptr(b), a.numel(), b.numel(), dt(a.dtype), dt(b.dtype), _ptr(scale), float(coef), _ptr(da),
+                           dt(gdtype), int(relu_mask), dev, st), "sse_bwd")
     _count()
     return da
 
 
-def tv_bwd(img, scale):
+def tv_bwd(img, scale, coef: float = 1.0):
     b, c, h, w = img.shape
     out = torch.empty_like(img)
     dev, st = _ctx(img)
-    check(lib.fnst_tv_bwd(_ptr(img), b * c, h, w, _ptr(scale), _ptr(out), dev, st), "tv_bwd")
+    check(lib.fnst_tv_bwd(_ptr(img), b * c, h, w, _ptr(scale), float(coef), _ptr(out), dev, st), "tv_bwd")
     _count()
     return out
 
 
-def channel_sum(x):
+def channel_sum(x, out: Optional[torch.Tensor] = None):
     n, c, h, w = x.shape
-    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(c, dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.numel() == c and out.is_contiguous()
     dev, st = _ctx(x)
     check(lib.fnst_channel_sum(_ptr(x), n, c, h * w, _ptr(out), dev, st), "channel_sum")
     _count(2)
@@ -439,8 +498,8 @@ def gram_diff_sym(g: torch.Tensor, gt: torch.Tensor, scale: torch.Tensor, coef: 
 _GATHER_MAPS = {}
 
 
-def gather_pack(key: str, layout_fn, src: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
-    """out = layout_fn(src).to(out_dtype) as ONE kernel.  `layout_fn` must be a pure re-layout (every output element is
+def gather_pack(key: str, layout_fn, src: torch.Tensor, out_dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = layout_fn(src).to(out_dtype) as ONE kernel (written into `out` when given: a contiguous tensor of that size).  `layout_fn` must be a pure re-layout (every output element is
     one input element or zero); its index map is derived once per (key, shape, device) by running it on a CPU tensor of
     element numbers and cached on the device.  (First use does host work: warm up before CUDA-graph capture.)"""
     ck = (key, tuple(src.shape), src.device)
@@ -454,11 +513,52 @@ def gather_pack(key: str, layout_fn, src: torch.Tensor, out_dtype: torch.dtype) 
     s = src.detach()
     if not s.is_contiguous():
         s = s.contiguous()
-    out = torch.empty(shape, dtype=out_dtype, device=src.device)
+    if out is None:
+        out = torch.empty(shape, dtype=out_dtype, device=src.device)
+    else:
+        assert out.is_contiguous() and out.dtype == out_dtype and out.numel() == idx.numel()
     dev, st = _ctx(s)
     check(lib.fnst_gather_cast(_ptr(s), dt(s.dtype), _ptr(idx), _ptr(out), dt(out_dtype), idx.numel(), dev, st), "gather_cast")
     _count()
     return out
+
+
+def gather_index(src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor) -> None:
+    """out[i] = idx[i] < 0 ? 0 : src[idx[i]] with a caller-built int32 index map (gradient assembly)."""
+    assert idx.dtype == torch.int32 and idx.numel() == out.numel() and out.is_contiguous() and src.is_contiguous()
+    dev, st = _ctx(src)
+    check(lib.fnst_gather_cast(_ptr(src), dt(src.dtype), _ptr(idx), _ptr(out), dt(out.dtype), idx.numel(), dev, st), "gather_cast")
+    _count()
+
+
+_LOSS_WS = {}
+
+
+def _loss_workspace(device: torch.device) -> torch.Tensor:
+    """Zeroed once; the loss kernels leave it zeroed.  One per (device, stream)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    ws = _LOSS_WS.get(key)
+    if ws is None:
+        ws = _LOSS_WS[key] = torch.zeros(int(lib.fnst_loss_workspace_bytes()) // 8, dtype=torch.float64, device=device)
+    return ws
+
+
+def sse_scaled(a: torch.Tensor, b: torch.Tensor, scale: float, out: torch.Tensor, accumulate: bool = False) -> None:
+    """out[0] (+)= scale * sum (a - b)^2 ; b broadcast with period b.numel().  One launch, fp32 result on the device."""
+    assert a.is_contiguous() and b.is_contiguous() and out.dtype == torch.float32 and a.numel() % b.numel() == 0
+    dev, st = _ctx(a)
+    check(lib.fnst_sse_scaled(_ptr(a), _ptr(b), a.numel(), b.numel(), dt(a.dtype), dt(b.dtype), float(scale),
+                              _ptr(_loss_workspace(a.device)), _ptr(out), int(accumulate), dev, st), "sse_scaled")
+    _count()
+
+
+def tv_scaled(img: torch.Tensor, scale: float, out: torch.Tensor) -> None:
+    b, c, h, w = img.shape
+    assert img.dtype == torch.float32 and img.is_contiguous() and out.dtype == torch.float32
+    dev, st = _ctx(img)
+    check(lib.fnst_tv_scaled(_ptr(img), b * c, h, w, float(scale), _ptr(_loss_workspace(img.device)), _ptr(out), dev, st), "tv_scaled")
+    _count()
 
 
 def _f3(v):

@@ -145,12 +145,15 @@ int fnst_conv_first(const float* x, int n, int h, int w, const float* wgt, const
  *   res   or NULL                  residual source: NHWC buffer with halo `res_pad`
  *   out                            [n, h+2*pad, w+2*pad, c]; if s2d: [n, ceil((h+2p)/2), ceil((w+2p)/2), 4c]
  *                                  with channel = ((hp&1)*2 + (wp&1))*c + ch
+ *   out_bf16 or NULL               second copy of the same activation as bfloat16, same geometry with c channels per pixel
+ *                                  (also when `split`): the operand of the weight-gradient GEMM, whose other operand --
+ *                                  the gradient -- is bf16 (saves a cast pass over every saved activation in training)
  *   raw_dtype                      element type of raw (== dtype, or FNST_F32 with split)
  *   split                          error-compensated fp16 pair: out (and res) hold 2c channels per pixel [hi(c) | lo(c)],
  *                                  hi = fp16(y), lo = fp16(y - hi)  (fp16x3 path: hi*hi + hi*lo + lo*hi on tensor cores)
  */
 int fnst_inorm_apply(const void* raw, const float* stats, const float* gamma, const float* beta,
-                     const float* drop, const void* res, int res_pad, void* out,
+                     const float* drop, const void* res, int res_pad, void* out, void* out_bf16,
                      int n, int h, int w, int c, int dtype, int relu, float eps,
                      int pad, int pad_mode, int s2d, int raw_dtype, int split, int device, void* stream);
 
@@ -170,13 +173,24 @@ int fnst_maxpool2(const void* in, void* out, int n, int h, int w, int c, int dty
 /*
  * Gram matrix G[n] = F[n]^T F[n] for NHWC features F[n] = [h*w][c]  (losses/losses.py:6-13).
  * out fp32 [n][c][c].  use_tc: tcgen05 path (dtype F16/BF16, c % 64 == 0), else CUDA cores.
+ * prezeroed != 0: `out` is already zero (the split-K partial tiles are accumulated into it); else the call memsets it.
  */
-int fnst_gram(const void* feat, float* out, int n, int hw, int c, int dtype, int use_tc, int device, void* stream);
+int fnst_gram(const void* feat, float* out, int n, int hw, int c, int dtype, int use_tc, int prezeroed, int device, void* stream);
 
 /* acc[0] += sum (a-b)^2 over `count` elements (double accumulator)  (losses/losses.py:41,54).
  * b_period: b is indexed modulo b_period (target Gram broadcast over the batch). */
 int fnst_sse(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
              double* acc, int device, void* stream);
+
+/* Loss scalars in one launch each, no memset, no host arithmetic (losses/losses.py:41,54,71 incl. their normalisation):
+ *   out[0] (+)= scale * sum (a-b)^2        (accumulate != 0: add to out[0]; else overwrite)
+ *   out[0]   = scale * TV(img)
+ * Block partials go to `workspace` (fnst_loss_workspace_bytes() bytes, zeroed ONCE by the caller) and are summed in block
+ * order by the last block to finish (deterministic), which also resets the workspace. */
+int64_t fnst_loss_workspace_bytes(void);
+int fnst_sse_scaled(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b, float scale,
+                    void* workspace, float* out, int accumulate, int device, void* stream);
+int fnst_tv_scaled(const float* img, int planes, int h, int w, float scale, void* workspace, float* out, int device, void* stream);
 
 /* acc[0] += sum of squared vertical and horizontal differences of an NCHW fp32 image
  * (losses/losses.py:62-73; the caller divides by b*c*h*w). */
@@ -233,14 +247,35 @@ int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, co
                          void* draw, float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps,
                          int out_s2d, int device, void* stream);
 
+/*
+ * InstanceNorm2d backward in ONE pass (same semantics as fnst_inorm_bwd_reduce followed by fnst_inorm_bwd_apply; autograd of
+ * nn.InstanceNorm2d / F.relu / nn.Dropout2d / ReflectionPad2d / `x + y`, models/model.py:51-61,74-75,86-90 under train.py:200).
+ * A slab (image, 16 channels) is held in the shared memory of a thread-block cluster of K CTAs; the per-channel sums travel
+ * through distributed shared memory, so every tensor is read once and nothing is re-read or atomically accumulated:
+ *   draw    [n,h,w,c] (or space-to-depth if out_s2d)   gradient of the raw conv output
+ *   gy_out  or NULL  [n,h,w,c]                           the gradient gy itself (the residual branch re-uses it)
+ *   sums    [n][c][2] fp32, WRITTEN (not accumulated)     (sum gy, sum gy*xhat) per plane, for fnst_affine_grads
+ * fnst_inorm_bwd_fused_parts returns K for a plane size (0: does not fit 8 CTAs' shared memory -> use the two-pass operators).
+ */
+int fnst_inorm_bwd_fused_parts(int h, int w, int c, int act_dtype, int g_dtype);
+int fnst_inorm_bwd_fused(const void* gsrc, const void* extra, const void* raw, const float* stats,
+                         const float* gamma, const float* beta, const float* drop, void* draw, void* gy_out,
+                         float* sums, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
+                         int pad, int pad_mode, int s2d, int out_s2d, int device, void* stream);
+/* d gamma / d beta of `layers` InstanceNorm layers in one launch: table = device array of {int64 src, int64 dgamma,
+ * int64 dbeta, int32 C, int32 pad} (element offsets: the layer's [n][C][2] block in `sums`; its d gamma / d beta in `out`).
+ * out[dgamma + c] = sum_i sums[src + (i*C + c)*2 + 1], out[dbeta + c] = sum_i sums[src + (i*C + c)*2] (fixed order). */
+int fnst_affine_grads(const float* sums, const void* table, int layers, int n, int max_c, float* out, int device, void* stream);
+
 /* MaxPool2d(2,2) backward fused with the ReLU mask of its input: gin = (extra + route(gout)) * (in > 0);
  * the first maximal element of each window receives the gradient (PyTorch tie rule). */
 int fnst_maxpool2_bwd(const void* in, const void* gout, const void* extra, void* gin, int n, int h, int w, int c,
                       int act_dtype, int g_dtype, int device, void* stream);
 
-/* da = 2 * scale[0] * (a - b) (b broadcast with period b_period), optionally masked by (a > 0). */
+/* da = 2 * coef * scale[0] * (a - b) (b broadcast with period b_period), optionally masked by (a > 0).  scale: device
+ * scalar (the incoming gradient of the loss); coef: host constant (the loss's normalisation, losses/losses.py:41,54). */
 int fnst_sse_bwd(const void* a, const void* b, int64_t count, int64_t b_period, int dtype_a, int dtype_b,
-                 const float* scale, void* da, int g_dtype, int relu_mask, int device, void* stream);
+                 const float* scale, float coef, void* da, int g_dtype, int relu_mask, int device, void* stream);
 
 /* out = (g + extra) * (act > 0): ReLU backward with an optional second gradient branch (count % 8 == 0). */
 int fnst_relu_mask(const void* g, const void* extra, const void* act, void* out, int64_t count, int act_dtype,
@@ -251,8 +286,8 @@ int fnst_relu_mask(const void* g, const void* extra, const void* act, void* out,
 int fnst_gram_diff_sym(const float* g, const float* gt, int n, int c, int64_t gt_numel, const float* scale, float coef,
                        void* s_out, int out_dtype, int device, void* stream);
 
-/* Gradient of fnst_tv: dimg = scale[0] * d/dimg sum(dh^2 + dw^2), NCHW fp32. */
-int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float* dimg, int device, void* stream);
+/* Gradient of fnst_tv: dimg = coef * scale[0] * d/dimg sum(dh^2 + dw^2), NCHW fp32 (scale: device scalar, coef: host constant). */
+int fnst_tv_bwd(const float* img, int planes, int h, int w, const float* scale, float coef, float* dimg, int device, void* stream);
 
 /* Element-type conversion of a contiguous tensor (count % 8 == 0).  tcgen05 kind::f16 needs both operands in the
  * same 16-bit format, so saved fp16 activations are converted to the bf16 gradient format for fnst_wgrad_tc. */

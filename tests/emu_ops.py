@@ -97,7 +97,7 @@ def image_to_halo(x, pad, pad_mode, c_pad, rows, pitch, dtype, split=False):
 
 
 def inorm_apply(raw, stats, gamma, beta, out, relu, pad=0, pad_mode=PAD_NONE, s2d=False, drop=None, res=None,
-                res_pad=0, eps=1e-5, split=False):
+                res_pad=0, eps=1e-5, split=False, out2=None):
     n, h, w, c = raw.shape
     cnt = h * w
     mean = stats[:, :, 0].double() / cnt
@@ -112,23 +112,30 @@ def inorm_apply(raw, stats, gamma, beta, out, relu, pad=0, pad_mode=PAD_NONE, s2
     if res is not None:
         r = res.double()[:, res_pad:res_pad + h, res_pad:res_pad + w, :]
         y = y + (r[..., :c] + r[..., c:] if split else r)
+
+    def geometry(t):                                       # halo + space-to-depth, any channel count
+        cc = t.shape[-1]
+        if pad:
+            if pad_mode == PAD_REFLECT:
+                hi = _reflect(torch.arange(-pad, h + pad), h)
+                wi = _reflect(torch.arange(-pad, w + pad), w)
+                t = t[:, hi][:, :, wi]
+            else:
+                t = F.pad(t, (0, 0, pad, pad, pad, pad))
+        if s2d:
+            hp, wp = t.shape[1], t.shape[2]
+            t = F.pad(t, (0, 0, 0, wp % 2, 0, hp % 2))
+            hs, ws = t.shape[1] // 2, t.shape[2] // 2
+            t = t.view(n, hs, 2, ws, 2, cc).permute(0, 1, 3, 2, 4, 5).reshape(n, hs, ws, 4 * cc)
+        return t
+
+    if out2 is not None:                                   # bf16 twin: same geometry, c channels per pixel, never split
+        t2 = geometry(y)
+        out2.view(-1)[:t2.numel()].copy_(t2.reshape(-1).to(out2.dtype))
     if split:                                              # [hi | lo] fp16 pair per pixel
         hi = y.to(out.dtype).double()
         y = torch.cat([hi, y - hi], dim=-1)
-        c = 2 * c
-    if pad:
-        if pad_mode == PAD_REFLECT:
-            hi = _reflect(torch.arange(-pad, h + pad), h)
-            wi = _reflect(torch.arange(-pad, w + pad), w)
-            y = y[:, hi][:, :, wi]
-        else:
-            y = F.pad(y, (0, 0, pad, pad, pad, pad))
-    if s2d:
-        hp, wp = y.shape[1], y.shape[2]
-        y = F.pad(y, (0, 0, 0, wp % 2, 0, hp % 2))
-        hs, ws = y.shape[1] // 2, y.shape[2] // 2
-        y = y.view(n, hs, 2, ws, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, hs, ws, 4 * c)
-    out.copy_(y.to(out.dtype))
+    out.copy_(geometry(y).to(out.dtype))
 
 
 def maxpool2(x):
@@ -137,15 +144,31 @@ def maxpool2(x):
     return v.amax(dim=(2, 4))
 
 
-def gram(feat_nhwc, use_tc):
+def gram(feat_nhwc, use_tc, out=None):
     n, h, w, c = feat_nhwc.shape
     f = feat_nhwc.reshape(n, h * w, c).double()
-    return (f.transpose(1, 2) @ f).float()
+    res = (f.transpose(1, 2) @ f).float()
+    if out is None:
+        return res
+    out += res                                             # split-K partials accumulate into the zeroed tensor
+    return out
 
 
 def sse(a, b, acc):
     d = a.double().reshape(-1, b.numel()) - b.double().reshape(1, -1)
     acc += (d * d).sum()
+
+
+def sse_scaled(a, b, scale, out, accumulate=False):
+    d = a.double().reshape(-1, b.numel()) - b.double().reshape(1, -1)
+    r = (scale * (d * d).sum()).float()
+    out.copy_(out + r if accumulate else r)
+
+
+def tv_scaled(img, scale, out):
+    acc = torch.zeros((), dtype=torch.float64)
+    tv(img, acc)
+    out.copy_((scale * acc).float())
 
 
 def tv(img, acc):
@@ -171,8 +194,18 @@ def finalconv_stream(act_flat, n, h, w, wpacked, bias, out):
     out.copy_(F.conv2d(act.permute(0, 3, 1, 2), wt, bias[:3].double()))
 
 
-def gather_pack(key, layout_fn, src, out_dtype):
-    return layout_fn(src.detach().double()).to(out_dtype)
+def gather_pack(key, layout_fn, src, out_dtype, out=None):
+    res = layout_fn(src.detach().double()).to(out_dtype)
+    if out is None:
+        return res
+    out.view(-1).copy_(res.reshape(-1))
+    return out
+
+
+def gather_index(src, idx, out):
+    flat = src.reshape(-1)
+    i = idx.long()
+    out.view(-1).copy_(torch.where(i < 0, torch.zeros((), dtype=flat.dtype), flat[i.clamp_min(0)]).to(out.dtype))
 
 
 def require_tensor_cores(device):
@@ -181,7 +214,7 @@ def require_tensor_cores(device):
 
 def install(monkeypatch, ops_module):
     """Substitute every operator of `ops_module` by its emulation."""
-    for name in ("require_tensor_cores", "conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "nhwc_to_nchw", "nchw_to_nhwc", "gather_pack", "finalconv_stream"):
+    for name in ("require_tensor_cores", "conv_gather", "conv_first", "image_to_halo", "inorm_apply", "maxpool2", "gram", "sse", "tv", "sse_scaled", "tv_scaled", "nhwc_to_nchw", "nchw_to_nhwc", "gather_pack", "gather_index", "finalconv_stream"):
         monkeypatch.setattr(ops_module, name, globals()[name])
 
 
@@ -217,7 +250,15 @@ def wgrad(spec, a, a_dims, a_strides, g, out_hw, use_tc=False, g_strides=None, o
     return out
 
 
-def conv_first_wgrad(x, g, k, stride, pad, pad_mode):
+def conv_first_wgrad(x, g, k, stride, pad, pad_mode, out=None):
+    res = _conv_first_wgrad(x, g, k, stride, pad, pad_mode)
+    if out is None:
+        return res
+    out.view(-1).copy_(res.reshape(-1))
+    return out
+
+
+def _conv_first_wgrad(x, g, k, stride, pad, pad_mode):
     xp = F.pad(x.double(), (pad,) * 4, mode="reflect" if pad_mode == PAD_REFLECT else "constant")
     n, c, _, _ = x.shape
     _, ho, wo, co = g.shape
@@ -235,8 +276,31 @@ def _norm_consts(raw, stats, eps):
     return mean, rstd, xhat
 
 
+def inorm_bwd_fused_parts(raw, gdtype):
+    return 1 if raw.shape[-1] % 16 == 0 and raw.shape[1] * raw.shape[2] <= 64 * 64 else 0     # exercise both paths on CPU
+
+
+def inorm_bwd_fused(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=PAD_NONE, s2d=False,
+                    out_s2d=False, want_gy=False, sums=None, eps=1e-5):
+    tmp = torch.zeros(raw.shape[0], raw.shape[-1], 2, dtype=torch.float32)
+    gy, tmp = inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad, pad_mode, s2d, eps, sums=tmp)
+    d, _ = inorm_bwd_apply(gy, raw, stats, tmp, gamma, out_s2d, eps)
+    if sums is None:
+        sums = tmp
+    else:
+        sums.copy_(tmp)                                    # written, not accumulated
+    return d, (gy if want_gy else None), sums
+
+
+def affine_grads(sums_flat, entries, n, out):
+    for src, c, dg, db in entries:
+        blk = sums_flat[src:src + n * c * 2].view(n, c, 2).double()
+        out[dg:dg + c] = blk[:, :, 1].sum(0).float()
+        out[db:db + c] = blk[:, :, 0].sum(0).float()
+
+
 def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=PAD_NONE, s2d=False, eps=1e-5,
-                     arena=None):
+                     arena=None, sums=None):
     n, h, w, c = raw.shape
     g = torch.zeros((n, h, w, c), dtype=torch.float64)
     if gsrc is not None:
@@ -262,14 +326,15 @@ def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, p
     if relu:
         y = xhat * gamma.double() + beta.double()
         g = g * (y > 0)
-    sums = arena.take(n, c, 2) if arena is not None else torch.zeros((n, c, 2), dtype=torch.float32)
+    if sums is None:
+        sums = arena.take(n, c, 2) if arena is not None else torch.zeros((n, c, 2), dtype=torch.float32)
     gy = g.to(gdtype)
     sums[:, :, 0] += g.sum(dim=(1, 2)).float()
     sums[:, :, 1] += (g * xhat).sum(dim=(1, 2)).float()
     return gy, sums
 
 
-def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps=1e-5):
+def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps=1e-5, want_dgb=True):
     n, h, w, c = raw.shape
     cnt = h * w
     _, rstd, xhat = _norm_consts(raw, stats, eps)
@@ -297,15 +362,15 @@ def relu_mask(g, extra, act):
     return (v * (act.double() > 0)).to(g.dtype)
 
 
-def sse_bwd(a, b, scale, gdtype, relu_mask=False):
-    d = 2.0 * scale.double()[0] * (a.double().reshape(-1, b.numel()) - b.double().reshape(1, -1))
+def sse_bwd(a, b, scale, gdtype, relu_mask=False, coef=1.0):
+    d = 2.0 * coef * scale.double()[0] * (a.double().reshape(-1, b.numel()) - b.double().reshape(1, -1))
     d = d.view(a.shape)
     if relu_mask:
         d = d * (a.double() > 0)
     return d.to(gdtype)
 
 
-def tv_bwd(img, scale):
+def tv_bwd(img, scale, coef=1.0):
     x = img.double()
     d = torch.zeros_like(x)
     dh = x[:, :, 1:] - x[:, :, :-1]
@@ -314,11 +379,15 @@ def tv_bwd(img, scale):
     d[:, :, :-1] -= 2 * dh
     d[:, :, :, 1:] += 2 * dw
     d[:, :, :, :-1] -= 2 * dw
-    return (scale.double()[0] * d).float()
+    return (coef * scale.double()[0] * d).float()
 
 
-def channel_sum(x):
-    return x.double().sum(dim=(0, 2, 3)).float()
+def channel_sum(x, out=None):
+    res = x.double().sum(dim=(0, 2, 3)).float()
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
 
 
 def cast(x, dtype):
@@ -333,8 +402,8 @@ def gram_diff_sym(g, gt, scale, coef, dtype):
 def install_backward(monkeypatch, ops_module):
     """Substitute the backward operators too, and make the stream plumbing of backward.py a no-op on CPU."""
     install(monkeypatch, ops_module)
-    for name in ("wgrad", "conv_first_wgrad", "inorm_bwd_reduce", "inorm_bwd_apply", "maxpool2_bwd", "relu_mask", "sse_bwd",
-                 "tv_bwd", "channel_sum", "cast", "gram_diff_sym"):
+    for name in ("wgrad", "conv_first_wgrad", "inorm_bwd_reduce", "inorm_bwd_apply", "inorm_bwd_fused", "inorm_bwd_fused_parts",
+                 "affine_grads", "maxpool2_bwd", "relu_mask", "sse_bwd", "tv_bwd", "channel_sum", "cast", "gram_diff_sym"):
         monkeypatch.setattr(ops_module, name, globals()[name])
     monkeypatch.setenv("FNST_WGRAD_STREAM", "0")                   # no side stream for the weight-gradient branch
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: None)

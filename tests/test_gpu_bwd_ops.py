@@ -125,9 +125,13 @@ def test_conv_first_wgrad():
                                  dict(c=64, pad=1, s2d=True, relu=True, drop=False, extra=False, out_s2d=False),
                                  dict(c=32, pad=4, s2d=False, relu=True, drop=False, extra=False, out_s2d=True),
                                  dict(c=64, pad=0, s2d=False, relu=True, drop=False, extra=False, out_s2d=True)])
-def test_inorm_backward(cfg, gdtype):
+@pytest.mark.parametrize("mode,hw", [("two_pass", (10, 12)), ("fused", (10, 12)), ("fused", (72, 48)), ("fused", (100, 98)), ("fused", (160, 160))])
+def test_inorm_backward(cfg, gdtype, mode, hw):
+    """Two-pass operators (reduce + apply) and the one-pass cluster kernel (1, 2, 4 and 8 CTAs per slab by plane size)."""
     g = torch.Generator().manual_seed(23)
-    n, h, w, c = 2, 10, 12, cfg["c"]
+    n, (h, w), c = 2, hw, cfg["c"]
+    if h * w > 4096:
+        c = min(c, 32)                          # large planes: fewer channels keep the float64 reference quick
     adt = torch.float32 if gdtype == torch.float32 else torch.float16
     raw = (torch.randn((n, h, w, c), generator=g) * 1.5 + 0.3).to(adt)
     gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
@@ -159,16 +163,31 @@ def test_inorm_backward(cfg, gdtype):
         gs = F.pad(gs.float(), (0, 0, 0, wp % 2, 0, hp % 2)).to(gdtype)
         gs = gs.view(n, gs.shape[1] // 2, 2, gs.shape[2] // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, gs.shape[1] // 2, gs.shape[2] // 2, 4 * c).contiguous()
     st = torch.stack([raw.double().sum((1, 2)), (raw.double() ** 2).sum((1, 2))], dim=-1).float()
-    gy, sums = ops.inorm_bwd_reduce(gs.to(DEV), None if extra is None else extra.to(DEV), raw.to(DEV), st.to(DEV), gamma.to(DEV),
-                                    beta.to(DEV), None if drop is None else drop.to(DEV), gdtype, cfg["relu"], pad,
-                                    _lib.PAD_REFLECT if pad else _lib.PAD_NONE, cfg["s2d"])
-    draw, dgb = ops.inorm_bwd_apply(gy, raw.to(DEV), st.to(DEV), sums, gamma.to(DEV), out_s2d=cfg["out_s2d"])
+    args = (gs.to(DEV), None if extra is None else extra.to(DEV), raw.to(DEV), st.to(DEV), gamma.to(DEV),
+            beta.to(DEV), None if drop is None else drop.to(DEV), gdtype, cfg["relu"], pad,
+            _lib.PAD_REFLECT if pad else _lib.PAD_NONE, cfg["s2d"])
+    if mode == "two_pass":
+        gy, sums = ops.inorm_bwd_reduce(*args)
+        draw, dgb = ops.inorm_bwd_apply(gy, raw.to(DEV), st.to(DEV), sums, gamma.to(DEV), out_s2d=cfg["out_s2d"])
+    else:
+        parts = ops.inorm_bwd_fused_parts(raw.to(DEV), gdtype)
+        expect = {(10, 12): 1, (72, 48): 2, (100, 98): 4, (160, 160): 8}[hw] * (2 if gdtype == torch.float32 else 1)
+        assert parts == (expect if expect <= 8 else 0), (parts, expect)
+        if parts == 0:
+            pytest.skip("plane does not fit the shared memory of 8 CTAs in fp32: the plan falls back to the two-pass operators")
+        draw, gy, sums = ops.inorm_bwd_fused(*args, out_s2d=cfg["out_s2d"], want_gy=True)
+        draw2, gy2, _ = ops.inorm_bwd_fused(*args, out_s2d=cfg["out_s2d"], want_gy=False)
+        assert gy2 is None and torch.equal(draw2, draw)                        # deterministic, with or without the gy output
+        gy_ref, sums_ref = ops.inorm_bwd_reduce(*args)
+        assert rel_l2(gy, gy_ref) < 1e-6 and rel_l2(sums, sums_ref) < 2e-5
+        dgb = torch.empty((2, c), dtype=torch.float32, device=DEV)
+        ops.affine_grads(sums.reshape(-1), [(0, c, 0, c)], n, dgb.view(-1))
     ref = r64.grad
     if cfg["out_s2d"]:
         ref = ref.view(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c)
     tol = 2e-5 if gdtype == torch.float32 else 1e-2
     assert rel_l2(draw, ref) < tol
-    dgam, dbet = backward._affine_grads(dgb)
+    dgam, dbet = dgb[0], dgb[1]
     assert rel_l2(sums.sum(0)[:, 1], dgam) < 1e-5 and rel_l2(sums.sum(0)[:, 0], dbet) < 1e-5
     assert rel_l2(dgam, g64.grad) < tol and rel_l2(dbet, b64.grad) < tol
 

@@ -195,6 +195,15 @@ def test_inorm_apply(dtype, cfg):
                     None if drop is None else drop.to(DEV), None if res is None else res.to(DEV), 1)
     tol = {torch.float32: 3e-6, torch.float16: 1e-3, torch.bfloat16: 6e-3}[dtype]
     assert rel_l2(out, ref) < tol
+    # bf16 twin written by the same launch (operand of the weight-gradient GEMM): same geometry, bf16 rounding of the same values
+    out_b = torch.zeros(oshape, dtype=dtype, device=DEV)
+    twin = torch.zeros(oshape, dtype=torch.bfloat16, device=DEV)
+    ops.inorm_apply(raw.to(DEV), st.to(DEV), gamma.to(DEV), beta.to(DEV), out_b, cfg["relu"], pad, cfg["mode"], cfg["s2d"],
+                    None if drop is None else drop.to(DEV), None if res is None else res.to(DEV), 1, out2=twin)
+    assert torch.equal(out_b, out)
+    assert rel_l2(twin, ref) < 6e-3
+    if dtype == torch.float32:
+        assert torch.equal(twin, out.to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
@@ -209,6 +218,21 @@ def test_maxpool_gram_sse_tv_layout(dtype):
     ops.sse(x.to(DEV), y.to(DEV), acc)
     ref = torch.zeros((), dtype=torch.float64); emu_ops.sse(x, y, ref)
     assert abs(float(acc) / float(ref) - 1) < 1e-5
+    # one-launch scaled forms (loss scalar incl. normalisation, deterministic block-ordered sum, self-cleaning workspace)
+    o1 = torch.full((), 7.0, dtype=torch.float32, device=DEV)
+    ops.sse_scaled(x.to(DEV), y.to(DEV), 0.25, o1)
+    assert abs(float(o1) / (0.25 * float(ref)) - 1) < 1e-5
+    ops.sse_scaled(x.to(DEV), y.to(DEV), 0.5, o1, accumulate=True)
+    assert abs(float(o1) / (0.75 * float(ref)) - 1) < 1e-5
+    o2 = torch.empty((), dtype=torch.float32, device=DEV)
+    ops.sse_scaled(x.to(DEV), y.to(DEV), 0.25, o2)
+    ops.sse_scaled(x.to(DEV), y.to(DEV), 0.5, o2, accumulate=True)
+    assert torch.equal(o1, o2)                                   # run-to-run identical
+    big = torch.randn((3, 3, 300, 301), generator=g)
+    rtv = torch.zeros((), dtype=torch.float64); emu_ops.tv(big, rtv)
+    o3 = torch.empty((), dtype=torch.float32, device=DEV)
+    ops.tv_scaled(big.to(DEV), 1.0 / big.numel(), o3)
+    assert abs(float(o3) / (float(rtv) / big.numel()) - 1) < 1e-5
     tgt = torch.randn((64, 64), generator=g)
     acc.zero_(); ops.sse(gr, tgt.to(DEV), acc)
     ref.zero_(); emu_ops.sse(gr.cpu(), tgt, ref)
