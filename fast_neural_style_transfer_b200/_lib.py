@@ -80,7 +80,7 @@ EXPORTS = {
                                         C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "fnst_inorm_bwd_reduce": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fnst_inorm_bwd_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
-    "fnst_inorm_bwd_fused_parts": (C.c_int, [C.c_int] * 5),
+    "fnst_inorm_bwd_fused_parts": (C.c_int, [C.c_int] * 9),
     "fnst_inorm_bwd_fused": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fnst_affine_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "fnst_loss_workspace_bytes": (C.c_int64, []),

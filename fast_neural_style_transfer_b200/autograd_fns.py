@@ -268,14 +268,18 @@ class StyleNetTrainGraph:
 
         def fwd(x_, *drops_):
             self.tape.clear()
-            self.plan = engine.StyleNetPlan(precision).pack(self.params)
-            return self.plan.forward(x_, list(drops_) if self.has_drop else None, self.tape)
+            self.plan = engine.StyleNetPlan(precision).pack(self.params, for_backward=True)
+            return self.plan.forward(x_, drops_[0] if self.has_drop else None, self.tape)
 
-        self.fwd = graphs.GraphedPlan(fwd, [x.float().contiguous()] + (list(drops) if self.has_drop else []))
+        # drops: one (5,B,256) tensor (a single graph input; the module draws the Bernoulli scales straight into it)
+        self.fwd = graphs.GraphedPlan(fwd, [x.float().contiguous()] + ([drops.float().contiguous()] if self.has_drop else []))
         self.bwd = None
 
+    def drop_input(self):
+        return self.fwd.static_inputs[1] if self.has_drop else None
+
     def forward(self, x, drops):
-        return self.fwd(x, *(drops if self.has_drop else []))
+        return self.fwd(x, *([drops] if self.has_drop else []))
 
     def backward(self, dy):
         """Captured: the whole backward up to the packed weight gradients / InstanceNorm sums (static buffers).  Eager: the

@@ -84,6 +84,13 @@ def _tc_ok(use_tc: bool, kc: int, n_gemm: int) -> bool:
 # reduction over the images for d gamma / d beta.  The per-parameter gradients are views of that buffer (so the
 # data-parallel all-reduce and the optimizer tail see one contiguous bucket).
 
+# FNST_INORM_BWD_FUSED=1 selects the one-pass InstanceNorm backward (TMA-staged cluster kernel) wherever the plane fits.
+# Default off -- measured on B200 at batch 4 (profiles/r02_inorm_bwd_fused.md): alone the one-pass kernel takes 16.6 us
+# against 14.5 + 7.3 us for the two passes, but inside the training step it LOSES 0.14 ms: its CTAs need a whole SM
+# (~200 KB of shared memory) in co-scheduled clusters, so they cannot share SMs with the weight-gradient GEMMs of the
+# side stream the way the small two-pass kernels do.
+FUSED_INORM_BWD = os.environ.get("FNST_INORM_BWD_FUSED", "0") not in ("", "0")
+
 NORM_LAYERS = (["norm1", "norm2"] + [f"res_blocks.{i}.{n}" for i in range(5) for n in ("in1", "in2")] + ["norm3", "norm4"])
 
 
@@ -170,6 +177,35 @@ def assemble_gradients(core: dict, names: Sequence[str], params: Dict[str, torch
     return flat
 
 
+def _final_dgrad_layout(wt):                                              # (3, 32, 9, 9) -> (32, 18*64)
+    wd = torch.zeros((32, 9, 2, 8, 8), dtype=wt.dtype)                # (c, kh, a, i, j)
+    wperm = wt.permute(1, 2, 3, 0)                                    # (c, kh, kw, j)
+    wd[:, :, 0, :, :3] = wperm[:, :, _FINAL_KW[:8], :]                # a = 0: pixel i <-> kw = 8 - i
+    wd[:, :, 1, 0, :3] = wperm[:, :, 0, :]                            # a = 1: pixel 0 <-> kw = 0
+    return wd.reshape(32, 18 * 64)
+
+
+def pack_dgrad_operands(plan: "engine.StyleNetPlan") -> Dict[str, torch.Tensor]:
+    """Data-gradient forms of all weights (packed / transposed per layer, gradient dtype): one gather kernel each.  They only
+    depend on the parameters, so the training forward issues them on a side stream next to its own kernels."""
+    p, tc = plan.params, plan.use_tc
+    gdt = grad_dtype(plan.precision)
+    gp, f64 = ops.gather_pack, torch.float64
+    convT_dgrad = lambda kc: (lambda t: pack_dgrad(engine.pack_conv_transpose(t, f64), 4, kc, f64))
+    wd = {
+        "res": gp("res_dgrad", lambda t: t.view(10, 256, 9, 256).permute(0, 3, 2, 1).reshape(10, 256, 9 * 256), plan.w["res_all"], gdt),
+        "up1": gp("convT_dgrad", convT_dgrad(256), p["up1.upsample_conv.weight"], gdt),
+        "up2": gp("convT_dgrad", convT_dgrad(64), p["up2.upsample_conv.weight"], gdt),
+        "conv2": gp("s2d_dgrad", lambda t: pack_dgrad_s2d(t, f64), p["conv2.conv.weight"], gdt),
+    }
+    wfin = p["final_conv.conv.weight"]
+    if tc:
+        wd["final"] = gp("final_dgrad", _final_dgrad_layout, wfin, gdt)
+    else:
+        wd["final"] = gp("final_plain_dgrad", lambda t: pack_dgrad(engine.pack_final_plain(t, f64), 81, 32, f64), wfin, gdt)
+    return wd
+
+
 def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor) -> Dict[str, torch.Tensor]:
     """dy: (B,3,H',W') fp32.  Returns gradients for all 58 reference parameter names (views of one flat fp32 buffer)."""
     names = list(plan.params)
@@ -207,7 +243,7 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
         src_off = arena.used
         sums = arena.take(B, raw.shape[-1], 2)
         norm_sums[layer] = (src_off, raw.shape[-1])
-        if ops.inorm_bwd_fused_parts(raw, gdt) > 0:
+        if FUSED_INORM_BWD and ops.inorm_bwd_fused_parts(raw, gdt, gsrc is not None, extra is not None, s2d) > 0:
             d_raw, gy, _ = ops.inorm_bwd_fused(gsrc, extra, raw, stats, ga, ba, drop, gdt, relu, pad, pad_mode, s2d, out_s2d, want_gy, sums)
             return d_raw, gy
         gy, _ = ops.inorm_bwd_reduce(gsrc, extra, raw, stats, ga, ba, drop, gdt, relu, pad, pad_mode, s2d, sums=sums)
@@ -248,7 +284,7 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
             keep_alive.append(a)
         ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, out=out, out_zeroed=True)
 
-    gp, f64 = ops.gather_pack, torch.float64
+    wd_all = getattr(plan, "wd", None) or pack_dgrad_operands(plan)     # packed by the training forward (side stream) when it ran
 
     def dgrad(g, g_dims, wd, fwd_taps, fwd_kc, out_shape, out_hw, h0=0, w0=0):
         """Data gradient of a forward gather-GEMM with plain taps (c0 == 0); wd = its data-gradient operand
@@ -283,22 +319,14 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
                       (rows_g, pitch_g), use_tc=True, g_strides=g_str, out=slot("final"), out_zeroed=True)
             keep_alive.append(a_g)
 
-        def final_dgrad_layout(wt):                                           # (3, 32, 9, 9) -> (32, 18*64)
-            wd = torch.zeros((32, 9, 2, 8, 8), dtype=wt.dtype)                # (c, kh, a, i, j)
-            wperm = wt.permute(1, 2, 3, 0)                                    # (c, kh, kw, j)
-            wd[:, :, 0, :, :3] = wperm[:, :, _FINAL_KW[:8], :]                # a = 0: pixel i <-> kw = 8 - i
-            wd[:, :, 1, 0, :3] = wperm[:, :, 0, :]                            # a = 1: pixel 0 <-> kw = 0
-            return wd.reshape(32, 18 * 64)
-
         taps18 = [(8 - kh, a * 8, 0) for kh in range(9) for a in (0, 1)]
         d_act4 = torch.empty((B, Hq, Wq, 32), dtype=gdt, device=dev)
-        ops.conv_gather(ConvSpec(taps18, 64, gp("final_dgrad", final_dgrad_layout, wfin, gdt), 32, 32), g8,
+        ops.conv_gather(ConvSpec(taps18, 64, wd_all["final"], 32, 32), g8,
                         (B, rows_g, pitch_g, 64), g_str, d_act4, (Hq, Wq), None, True)
     else:
         g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
         wgrad(ConvSpec(taps81, 32, None, 16, 3), act4, None, (B, Hq, Wq, 32), g16, (H4, W4), slot("final"))
-        wd_fin = gp("final_plain_dgrad", lambda t: pack_dgrad(engine.pack_final_plain(t, f64), 81, 32, f64), wfin, gdt)
-        d_act4 = dgrad(g16, (B, H4, W4, 16), wd_fin, taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
+        d_act4 = dgrad(g16, (B, H4, W4, 16), wd_all["final"], taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))
 
     # ---- norm4 + up2 ------------------------------------------------------------------------------------
     d_raw4, _ = inorm_backward("norm4", d_act4, None, tape["raw4"], tape["st4"], None, True, 4, PAD_REFLECT, out_s2d=True)   # (B,H3,W3,128)
@@ -306,9 +334,7 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
     H3, W3 = act3.shape[1], act3.shape[2]
     with on_side(act3, d_raw4):
         wgrad(ConvSpec(TAPS_2X2, 64, None, 128, 32), act3, wtw.get("act3"), (B, H3, W3, 64), d_raw4, (H3, W3), slot("up2"))
-    convT_dgrad = lambda kc: (lambda t: pack_dgrad(engine.pack_conv_transpose(t, f64), 4, kc, f64))
-    wd_up2 = gp("convT_dgrad", convT_dgrad(64), p["up2.upsample_conv.weight"], gdt)
-    d_act3 = dgrad(d_raw4, (B, H3, W3, 128), wd_up2, TAPS_2X2, 64, (B, H3, W3, 64), (H3, W3))
+    d_act3 = dgrad(d_raw4, (B, H3, W3, 128), wd_all["up2"], TAPS_2X2, 64, (B, H3, W3, 64), (H3, W3))
 
     # ---- norm3 + up1 ------------------------------------------------------------------------------------
     d_raw3, _ = inorm_backward("norm3", d_act3, None, tape["raw3"], tape["st3"], None, True, out_s2d=True)     # (B,H2,W2,256)
@@ -319,16 +345,13 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
     H2, W2 = last.shape[1], last.shape[2]
     with on_side(last, d_raw3):
         wgrad(ConvSpec(TAPS_2X2, 256, None, 256, 64), last, trunk_w[5], (B, H2, W2, 256), d_raw3, (H2, W2), slot("up1"))
-    wd_up1 = gp("convT_dgrad", convT_dgrad(256), p["up1.upsample_conv.weight"], gdt)
-    g_plain = dgrad(d_raw3, (B, H2, W2, 256), wd_up1, TAPS_2X2, 256, (B, H2, W2, 256), (H2, W2))
+    g_plain = dgrad(d_raw3, (B, H2, W2, 256), wd_all["up1"], TAPS_2X2, 256, (B, H2, W2, 256), (H2, W2))
 
     # ---- residual trunk -----------------------------------------------------------------------------------
     taps9 = taps_kxk(3)
     pdims = (B, H2 + 2, W2 + 2, 256)
     gsrc, extra = None, g_plain          # gradient of the block output = fold(gsrc) + extra
-    # the ten 3x3 weights are handled as one stacked tensor: one kernel packs all data-gradient operands
-    res_fwd = plan.w["res_all"]                                              # (10, 256, 9*256) forward operands
-    res_dg = gp("res_dgrad", lambda t: t.view(10, 256, 9, 256).permute(0, 3, 2, 1).reshape(10, 256, 9 * 256), res_fwd, gdt)
+    res_dg = wd_all["res"]                      # (10, 256, 9*256): the ten 3x3 data-gradient operands as one stacked tensor
     res_db = slot("res")
 
     def res_dgrad(g, idx):
@@ -361,9 +384,8 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
     Hs, Ws = buf2.shape[1], buf2.shape[2]
     with on_side(buf2, d_raw2):
         wgrad(ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, wtw.get("buf2"), (B, Hs, Ws, 256), d_raw2, (H2, W2), slot("conv2"))
-    wd2 = gp("s2d_dgrad", lambda t: pack_dgrad_s2d(t, f64), p["conv2.conv.weight"], gdt)
     d_buf2 = torch.empty((B, Hs, Ws, 256), dtype=gdt, device=dev)
-    ops.conv_gather(ConvSpec(_neg(TAPS_2X2), 256, wd2, 256, 256), d_raw2, (B, H2, W2, 256), _nhwc_strides(d_raw2), d_buf2,
+    ops.conv_gather(ConvSpec(_neg(TAPS_2X2), 256, wd_all["conv2"], 256, 256), d_raw2, (B, H2, W2, 256), _nhwc_strides(d_raw2), d_buf2,
                     (Hs, Ws), None, tc)
 
     # ---- norm1 + conv1 -----------------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 // Backward operators of the style-transfer path (see include/fnst.h, "Backward operators"):
 // weight gradients of gather-GEMM convolutions, InstanceNorm backward (with ReflectionPad2d
 // fold, ReLU mask, dropout and residual handling), max-pool / squared-error / TV backward.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace fnst {
 
@@ -368,12 +368,14 @@ __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restri
 // ---------------------------------------------------------------------------------------------
 // One-pass InstanceNorm backward.  A slab = (image n, 16-channel group) is owned by a thread-block CLUSTER of K CTAs
 // (K = 1, 2, 4 or 8; CTA k takes rows [k*rows_per_part, ...)).  Each CTA streams its part of the slab ONCE:
-//   phase 1  g = (fold(gsrc) + extra) * dropout * relu-mask and the raw activation go to shared memory; per-channel
-//            sum g and sum g*xhat are reduced warp -> CTA -> cluster (partials exchanged through distributed shared memory,
-//            summed in rank order: deterministic);
+//   stage    one thread issues TMA box loads {16 channels, W pixels, R rows} of raw, gsrc (interior of the halo buffer) and
+//            extra for the WHOLE part up front -- every byte the CTA needs is in flight at once (a latency-bound register
+//            pipeline reached 0.8-1.1 TB/s here; the bulk loads arrive at memory speed), chunk by chunk on mbarriers;
+//   phase 1  as chunks land: g = (fold(gsrc) + extra) * dropout * relu-mask overwrites the gsrc tile in shared memory;
+//            per-channel sum g and sum g*xhat are reduced warp -> CTA -> cluster (partials exchanged through distributed
+//            shared memory, summed in rank order: deterministic);
 //   phase 2  d_raw = gamma*rstd * (g - mean(g) - xhat * mean(g*xhat)) from shared memory.
 // HBM/L2 traffic: read gsrc (+extra) + raw, write d_raw (+gy): nothing is read twice, no gy round trip, no atomics.
-// Two adjacent threads cover one pixel's 16 channels = one full 32-byte sector per 16-bit tensor.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t dsmem_map(const void* p, uint32_t rank) {
   uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
@@ -390,31 +392,76 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-constexpr int IBF_THREADS = 256;
-constexpr int IBF_CH = 16;                   // channels per slab
-constexpr int IBF_PL = IBF_THREADS / 2;      // pixel lanes (two threads per pixel)
+constexpr int IBF_THREADS = 512;
+constexpr int IBF_MAX_CHUNKS = 32;           // TMA chunks (<= 256 pixels each) per CTA
+
+struct IbfParams {
+  HaloLayout L;
+  int relu, out_s2d, rows_per_part, K, chunk_rows, chunks, chunk_stride;   // chunk_stride: pixels between chunk starts in shared memory
+  int cw, tpp_log2;                                                         // channels per slab (16/32/64), log2(threads per pixel)
+  float eps;
+  unsigned long long* dbg;                                                  // measurement only (fnst_set_debug_buffer): 8 stamps per CTA
+};
+
+__device__ __forceinline__ void dsmem_st_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 
 template <typename TA, typename TG>
 __global__ void __launch_bounds__(IBF_THREADS, 1)
-inorm_bwd_fused_kernel(const TG* __restrict__ gsrc, const TG* __restrict__ extra, const TA* __restrict__ raw,
+inorm_bwd_fused_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_g,
+                       const __grid_constant__ CUtensorMap map_e, const TG* __restrict__ gsrc, int has_extra,
                        const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                        const float* __restrict__ drop, TG* __restrict__ draw, TG* __restrict__ gy_out, float* __restrict__ sums,
-                       HaloLayout L, int relu, float eps, int out_s2d, int rows_per_part, int K) {
+                       const IbfParams P) {
   pdl_trigger();
-  extern __shared__ __align__(16) uint8_t ibf_smem[];
-  __shared__ float red[IBF_THREADS / 32][32];
-  __shared__ float cta_tot[32];              // [half][s1 x 8 | s2 x 8]
-  __shared__ float tot[32];
-  const int part = blockIdx.x, n = blockIdx.z;
-  const int half = threadIdx.x & 1, pl = threadIdx.x >> 1;
-  const int c0 = blockIdx.y * IBF_CH + half * 8;
+  extern __shared__ uint8_t ibf_raw_smem[];
+  uint8_t* ibf_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ibf_raw_smem) + 127) & ~uintptr_t(127));
+  __shared__ float red[IBF_THREADS / 32][128];   // per warp: [sub][s1 x 8 | s2 x 8]
+  __shared__ float peer_tot[8][128];             // one row per cluster rank, written by that rank (remote stores)
+  __shared__ __align__(8) uint64_t full[IBF_MAX_CHUNKS];
+  const HaloLayout& L = P.L;
+  const int part = blockIdx.x, n = blockIdx.z, K = P.K;
+  unsigned long long* tl = P.dbg ? P.dbg + 8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  auto stamp = [&](int slot) {
+    if (tl && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); tl[slot] = t; }
+  };
+  stamp(0);
+  const int TPP = 1 << P.tpp_log2, PL = IBF_THREADS >> P.tpp_log2, cw = P.cw;
+  const int sub = threadIdx.x & (TPP - 1), pl = threadIdx.x >> P.tpp_log2;
+  const int c0 = blockIdx.y * cw + sub * 8;
   const int C = L.C, H = L.H, W = L.W;
-  const int r0 = part * rows_per_part, r1 = min(H, r0 + rows_per_part);
-  const int npx = max(0, r1 - r0) * W;
-  TG* g_s = reinterpret_cast<TG*>(ibf_smem);
-  TA* x_s = reinterpret_cast<TA*>(ibf_smem + (size_t)rows_per_part * W * IBF_CH * sizeof(TG));
+  const int r0 = part * P.rows_per_part, r1 = min(H, r0 + P.rows_per_part);
+  const int nrows = max(0, r1 - r0);
+  const size_t cap = (size_t)P.chunks * P.chunk_stride;                // pixel slots of each shared-memory tile
+  TA* x_s = reinterpret_cast<TA*>(ibf_smem);
+  TG* g_s = reinterpret_cast<TG*>(ibf_smem + cap * cw * sizeof(TA));  // gsrc tile, overwritten by g
+  TG* e_s = g_s + cap * cw;                                            // extra tile (when present)
+  if (!gsrc) { e_s = g_s; }                                            // extra only: its tile is the one overwritten by g
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_raw);
+    if (gsrc) tma_prefetch_desc(&map_g);
+    if (has_extra) tma_prefetch_desc(&map_e);
+    for (int i = 0; i < P.chunks; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   pdl_wait();
+  if (threadIdx.x == 0) {
+    // element unit of the maps is 2 bytes: channel coordinates / boxes are scaled by the element size
+    const int ca = blockIdx.y * cw * (int)(sizeof(TA) / 2), cg = blockIdx.y * cw * (int)(sizeof(TG) / 2);
+    const uint32_t bytes = (uint32_t)(P.chunk_rows * W) * cw * (uint32_t)(sizeof(TA) + (gsrc ? sizeof(TG) : 0) + (has_extra ? sizeof(TG) : 0));
+    for (int i = 0; i < P.chunks; ++i) {
+      const int r = r0 + i * P.chunk_rows;
+      const size_t so = (size_t)i * P.chunk_stride * cw;
+      mbar_arrive_expect_tx(&full[i], bytes);
+      tma_load_4d(x_s + so, &map_raw, &full[i], ca, 0, r, n);
+      if (gsrc) tma_load_4d(g_s + so, &map_g, &full[i], cg, L.pad, r + L.pad, n);
+      if (has_extra) tma_load_4d(e_s + so, &map_e, &full[i], cg, 0, r, n);
+    }
+  }
 
+  // per-channel constants (their global-memory latency overlaps the bulk loads)
   float a[8], b[8], mean[8], rstd[8], ds[8];
   {
     const float inv_cnt = 1.f / (float)(H * W);
@@ -422,141 +469,189 @@ inorm_bwd_fused_kernel(const TG* __restrict__ gsrc, const TG* __restrict__ extra
     for (int i = 0; i < 8; ++i) {
       const float* st = stats + ((size_t)n * C + c0 + i) * 2;
       const float m = st[0] * inv_cnt;
-      const float r = rsqrtf(fmaxf(st[1] * inv_cnt - m * m, 0.f) + eps);
+      const float r = rsqrtf(fmaxf(st[1] * inv_cnt - m * m, 0.f) + P.eps);
       mean[i] = m; rstd[i] = r;
       a[i] = gamma[c0 + i] * r; b[i] = beta[c0 + i] - m * a[i];
       ds[i] = drop ? drop[(size_t)n * C + c0 + i] : 1.f;
     }
   }
+
+  // ReflectionPad2d backward ("fold"): halo positions of the consumer's buffer that mirror an interior pixel add their gradient
+  // to it.  Only border pixels have such sources; they are enumerated explicitly and spread over ALL threads (inside the
+  // streaming loop the same few warps would meet a border column in every iteration and serialise one global-memory latency
+  // per pixel).  fold_tasks(PREFETCH): touch the sources while the bulk loads are in flight; fold_tasks(APPLY): add them into
+  // the staged tile (read straight from global memory: written by the data-gradient GEMM just before, now L1/L2 hits).
+  auto fold_tasks = [&](const bool apply) {
+    const int p2 = 2 * L.pad;
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: rows that are mirrored themselves (h in [1, pad] or [H-1-pad, H-2]): every pixel; pass 1: all other rows: 2*pad columns
+      const int per_row = pass == 0 ? W : p2;
+      for (int t = pl; t < nrows * per_row; t += PL) {
+        const int hr = t / per_row, j = t - hr * per_row, h = r0 + hr;
+        const bool row_mirrored = (h >= 1 && h <= L.pad) || (h <= H - 2 && h >= H - 1 - L.pad);
+        int w;
+        if (pass == 0) {
+          if (!row_mirrored) continue;
+          w = j;
+        } else {
+          if (row_mirrored) continue;
+          w = j < L.pad ? 1 + j : W - 1 - L.pad + (j - L.pad);
+          if (w < 1 || w > W - 2 || (j >= L.pad && w <= L.pad)) continue;      // narrow planes: the two column groups overlap
+        }
+        int hs[3], wsrc[3];
+        const int nh = L.sources(h, H, hs), nw = L.sources(w, W, wsrc);
+        if (nh == 1 && nw == 1) continue;
+        if (!apply) {
+          for (int ih = 0; ih < nh; ++ih)
+            for (int iw = (ih == 0 ? 1 : 0); iw < nw; ++iw)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(gsrc + L.index(n, hs[ih], wsrc[iw], c0)));
+          continue;
+        }
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int ih = 0; ih < nh; ++ih)
+          for (int iw = (ih == 0 ? 1 : 0); iw < nw; ++iw) {
+            float tt[8];
+            load8<TG>(gsrc + L.index(n, hs[ih], wsrc[iw], c0), tt);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += tt[i];
+          }
+        const int chh = hr / P.chunk_rows;
+        const size_t so = ((size_t)chh * P.chunk_stride + (size_t)(hr - chh * P.chunk_rows) * W + w) * cw + sub * 8;
+        float g[8];
+        load8<TG>(g_s + so, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] += acc[i];
+        store8<TG>(g_s + so, g);
+      }
+    }
+  };
+  const bool folding = gsrc && L.reflect && L.pad > 0;
+  if (folding) fold_tasks(false);
+  stamp(1);
+  for (int ch = 0; ch < P.chunks; ++ch) mbar_wait(&full[ch], 0);
+  stamp(2);
+  if (folding) {
+    fold_tasks(true);
+    __syncthreads();
+  }
+  stamp(3);
+
+  // ---- phase 1: g = (gsrc + extra) * dropout * relu-mask; s1 = sum g, s2 = sum g*x (xhat is affine in x: corrected below) ----
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-
-  // ---- phase 1 ------------------------------------------------------------------------------
-  constexpr int U = 4;                       // pixels in flight per thread
-  for (int p0 = pl; p0 < npx; p0 += U * IBF_PL) {
-    Raw8<TG> gc[U], ge[U];
-    Raw8<TA> xr[U];
-    int hh[U], ww[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + u * IBF_PL;
-      if (p < npx) {
-        const int h = r0 + p / W, w = p - (p / W) * W;
-        hh[u] = h; ww[u] = w;
-        const size_t idx = (((size_t)n * H + h) * W + w) * C + c0;
-        if (gsrc) gc[u] = load_raw8<TG>(gsrc + L.index(n, h + L.pad, w + L.pad, c0));
-        if (extra) ge[u] = load_raw8<TG>(extra + idx);
-        xr[u] = load_raw8<TA>(raw + idx);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + u * IBF_PL;
-      if (p >= npx) continue;
-      const int h = hh[u], w = ww[u];
-      float g[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+  const int npx = nrows * W;
+  const int step_rows = PL / W, step_w = PL - step_rows * W;           // pixel index advances by PL per iteration
+  {
+    int hr = pl / W, w = pl - hr * W;
+    for (int p = pl; p < npx; p += PL) {
+      const int chh = hr / P.chunk_rows;
+      const size_t so = ((size_t)chh * P.chunk_stride + (size_t)(hr - chh * P.chunk_rows) * W + w) * cw + sub * 8;
+      float g[8], x[8];
+      load8<TA>(x_s + so, x);
       if (gsrc) {
-        float t[8];
-        raw8_to_f32<TG>(gc[u], t);
+        load8<TG>(g_s + so, g);
+        if (has_extra) {
+          float t[8];
+          load8<TG>(e_s + so, t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = t[i];
-        if (L.reflect && (h <= L.pad || h >= H - 1 - L.pad || w <= L.pad || w >= W - 1 - L.pad)) {
-          // ReflectionPad2d fold: halo positions that were copied from (h, w) (border pixels only)
-          int hs[3], wsrc[3];
-          const int nh = L.sources(h, H, hs), nw = L.sources(w, W, wsrc);
-          for (int ih = 0; ih < nh; ++ih)
-            for (int iw = (ih == 0 ? 1 : 0); iw < nw; ++iw) {
-              load8<TG>(gsrc + L.index(n, hs[ih], wsrc[iw], c0), t);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) g[i] += t[i];
-            }
+          for (int i = 0; i < 8; ++i) g[i] += t[i];
         }
+      } else {
+        load8<TG>(e_s + so, g);
       }
-      if (extra) {
-        float t[8];
-        raw8_to_f32<TG>(ge[u], t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] += t[i];
-      }
-      float x[8];
-      raw8_to_f32<TA>(xr[u], x);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float y = fmaf(x[i], a[i], b[i]);
         float gv = g[i] * ds[i];
-        if (relu && !(y > 0.f)) gv = 0.f;
+        if (P.relu && !(fmaf(x[i], a[i], b[i]) > 0.f)) gv = 0.f;
         g[i] = gv;
         s1[i] += gv;
-        s2[i] = fmaf(gv, (x[i] - mean[i]) * rstd[i], s2[i]);
+        s2[i] = fmaf(gv, x[i], s2[i]);
       }
-      store8<TG>(g_s + (size_t)p * IBF_CH + half * 8, g);
-      if (sizeof(TA) == 2) *reinterpret_cast<uint4*>(x_s + (size_t)p * IBF_CH + half * 8) = *reinterpret_cast<const uint4*>(&xr[u]);
-      else store8<TA>(x_s + (size_t)p * IBF_CH + half * 8, x);
-      if (gy_out) store8<TG>(gy_out + (((size_t)n * H + h) * W + w) * C + c0, g);
+      store8<TG>(g_s + so, g);
+      if (gy_out) store8<TG>(gy_out + (((size_t)n * H + r0 + hr) * W + w) * C + c0, g);
+      hr += step_rows; w += step_w;
+      if (w >= W) { w -= W; ++hr; }
     }
   }
+  stamp(4);
 
-  // ---- reduction: lanes of equal parity -> warp -> CTA -> cluster (fixed order everywhere) ----
+  // ---- reduction: lanes of equal channel group -> warp -> CTA -> cluster (fixed order everywhere) ----
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-#pragma unroll
-    for (int o = 2; o < 32; o <<= 1) {
+    s2[i] = (s2[i] - mean[i] * s1[i]) * rstd[i];           // sum g*xhat = rstd * (sum g*x - mean * sum g)   (per thread: exact algebra)
+    for (int o = TPP; o < 32; o <<= 1) {
       s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
       s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
     }
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane < 2) {
+  if (lane < TPP) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { red[wid][lane * 16 + i] = s1[i]; red[wid][lane * 16 + 8 + i] = s2[i]; }
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
+  const int nred = TPP * 16;
+  if ((int)threadIdx.x < nred) {
     float t = 0.f;
 #pragma unroll
     for (int q = 0; q < IBF_THREADS / 32; ++q) t += red[q][threadIdx.x];
-    cta_tot[threadIdx.x] = t;
-  }
-  if (K > 1) {
-    cluster_barrier();                       // every CTA's cta_tot is written (and visible cluster-wide)
-    if (threadIdx.x < 32) {
-      float t = 0.f;
-      for (int r = 0; r < K; ++r) t += dsmem_ld_f32(dsmem_map(&cta_tot[threadIdx.x], (uint32_t)r));
-      tot[threadIdx.x] = t;
+    if (K > 1) {
+      // push this CTA's partial into row `part` of every cluster member's table (remote stores do not stall); after the
+      // cluster barrier every member sums the K rows in rank order -- identical, deterministic totals everywhere
+      for (int r = 0; r < K; ++r) dsmem_st_f32(dsmem_map(&peer_tot[part][threadIdx.x], (uint32_t)r), t);
+    } else {
+      peer_tot[0][threadIdx.x] = t;
     }
-  } else {
-    __syncthreads();
-    if (threadIdx.x < 32) tot[threadIdx.x] = cta_tot[threadIdx.x];
   }
-  __syncthreads();
-  if (part == 0 && threadIdx.x < 32) {
-    // per-(n,c) sums for d gamma / d beta (summed over images by fnst_affine_grads): [n][c][0] = sum g, [1] = sum g*xhat
-    const int hf = threadIdx.x >> 4, j = threadIdx.x & 15, which = j >> 3, ch = blockIdx.y * IBF_CH + hf * 8 + (j & 7);
-    sums[((size_t)n * C + ch) * 2 + which] = tot[threadIdx.x];
-  }
+  if (K > 1) cluster_barrier(); else __syncthreads();
   float m1[8], m2[8];
   {
     const float inv_cnt = 1.f / (float)(H * W);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { m1[i] = tot[half * 16 + i] * inv_cnt; m2[i] = tot[half * 16 + 8 + i] * inv_cnt; }
+    for (int i = 0; i < 8; ++i) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int r = 0; r < K; ++r) { t1 += peer_tot[r][sub * 16 + i]; t2 += peer_tot[r][sub * 16 + 8 + i]; }
+      m1[i] = t1; m2[i] = t2;
+    }
+    if (part == 0 && pl == 0) {
+      // per-(n,c) sums for d gamma / d beta (summed over images by fnst_affine_grads): [n][c][0] = sum g, [1] = sum g*xhat
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sums[((size_t)n * C + c0 + i) * 2 + 0] = m1[i]; sums[((size_t)n * C + c0 + i) * 2 + 1] = m2[i]; }
+    }
+    // d_raw = a*(g - mean_g - xhat*mean_gx) = A*g + B*x + D with xhat = (x - mean)*rstd
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float mg = m1[i] * inv_cnt, mgx = m2[i] * inv_cnt;
+      const float Bc = -a[i] * rstd[i] * mgx;
+      m1[i] = Bc;                                          // coefficient of x
+      m2[i] = -a[i] * mg - Bc * mean[i];                   // constant term
+    }
   }
+  stamp(5);
 
   // ---- phase 2 ------------------------------------------------------------------------------
-  for (int p = pl; p < npx; p += IBF_PL) {
-    const int h = r0 + p / W, w = p - (p / W) * W;
-    float g[8], x[8];
-    load8<TG>(g_s + (size_t)p * IBF_CH + half * 8, g);
-    load8<TA>(x_s + (size_t)p * IBF_CH + half * 8, x);
+  {
+    int hr = pl / W, w = pl - hr * W;
+    for (int p = pl; p < npx; p += PL) {
+      const int chh = hr / P.chunk_rows, h = r0 + hr;
+      const size_t so = ((size_t)chh * P.chunk_stride + (size_t)(hr - chh * P.chunk_rows) * W + w) * cw + sub * 8;
+      float g[8], x[8];
+      load8<TG>(g_s + so, g);
+      load8<TA>(x_s + so, x);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = a[i] * (g[i] - m1[i] - (x[i] - mean[i]) * rstd[i] * m2[i]);
-    TG* dst = out_s2d ? draw + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c0
-                      : draw + (((size_t)n * H + h) * W + w) * C + c0;
-    store8<TG>(dst, g);
+      for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], g[i], fmaf(m1[i], x[i], m2[i]));
+      TG* dst = P.out_s2d ? draw + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c0
+                          : draw + (((size_t)n * H + h) * W + w) * C + c0;
+      store8<TG>(dst, g);
+      hr += step_rows; w += step_w;
+      if (w >= W) { w -= W; ++hr; }
+    }
   }
-  if (K > 1) cluster_barrier();              // no CTA of the cluster leaves while a partner may still read its cta_tot
+  stamp(6);
+  // (no exit barrier: after the cluster barrier above nobody touches a partner's shared memory any more)
 }
 
 // d gamma[c] = sum_n sums[n][c][1], d beta[c] = sum_n sums[n][c][0] for a list of InstanceNorm layers in one launch
@@ -826,21 +921,63 @@ extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float
   return launch_status("inorm_bwd_apply");
 }
 
-// Number of cluster CTAs per slab the fused kernel needs for an h x w plane (0: the plane does not fit, use
-// fnst_inorm_bwd_reduce + fnst_inorm_bwd_apply).
-static int ibf_parts(int h, int w, int act_dtype, int g_dtype) {
-  const size_t per_px = (size_t)IBF_CH * (dtype_size(act_dtype) + dtype_size(g_dtype));
+// Geometry of the fused kernel.  chunk_rows x w <= 256 pixels per TMA box.  For each slab width cw (64 / 32 / 16 channels) the
+// smallest cluster K <= 8 whose parts (raw + gsrc + extra tiles) fit ~200 KB of shared memory; among the widths the one with
+// the most CTAs (capped at 128), ties to the widest (longest contiguous runs for TMA and DRAM).  K = 0: unsupported (w > 256 or
+// the plane does not fit) -> use fnst_inorm_bwd_reduce + fnst_inorm_bwd_apply.
+struct IbfGeometry { int K, rows_per_part, chunk_rows, chunks, chunk_stride, cw; size_t smem; };
+static IbfGeometry ibf_geometry(int n, int h, int w, int c, int act_dtype, int g_dtype, int tiles_g) {
+  IbfGeometry best{0, 0, 0, 0, 0, 0, 0};
+  if (w > 256 || w <= 0 || h <= 0 || n <= 0 || c % 16 != 0) return best;
+  const int chunk_rows = 256 / w < h ? 256 / w : h;
+  const int chunk_stride = (chunk_rows * w + 7) / 8 * 8;               // chunk starts stay 128-byte aligned in shared memory
   const size_t budget = 200 * 1024;
-  for (int k = 1; k <= 8; k *= 2) {
-    const int rows = (h + k - 1) / k;
-    if ((size_t)rows * w * per_px <= budget) return k;
+  long best_ctas = 0;
+  for (int cw = 64; cw >= 16; cw /= 2) {
+    if (c % cw != 0) continue;
+    const size_t per_slot = (size_t)cw * (dtype_size(act_dtype) + (size_t)tiles_g * dtype_size(g_dtype));
+    for (int k = 1; k <= 8; k *= 2) {
+      int rows = (h + k - 1) / k;
+      rows = (rows + chunk_rows - 1) / chunk_rows * chunk_rows;        // whole chunks
+      const int chunks = rows / chunk_rows;
+      const size_t bytes = (size_t)chunks * chunk_stride * per_slot;
+      if (bytes > budget || chunks > IBF_MAX_CHUNKS) continue;
+      long ctas = (long)k * (c / cw) * n;
+      if (ctas > 128) ctas = 128;
+      // ties: a cluster of 8 x ~200 KB places only one or two clusters per GPC (measured: two waves for 16 clusters), so
+      // prefer K <= 4; otherwise the wider slab (visited first)
+      if (ctas > best_ctas || (ctas == best_ctas && best.K > 4 && k <= 4)) {
+        best = IbfGeometry{k, rows, chunk_rows, chunks, chunk_stride, cw, bytes + 128};
+        best_ctas = ctas;
+      }
+      break;                                                           // smallest cluster that fits this width
+    }
   }
+  return best;
+}
+
+// tiled, un-swizzled tensor map over a tensor of 2-byte units (dims innermost first)
+static int encode_tensor_map_plain(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                   const uint32_t* box) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+  FNST_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  FNST_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    FNST_CHECK_ARG(strides_bytes[i] % 16 == 0, "TMA stride %d (%llu B) must be a multiple of 16", i, (unsigned long long)strides_bytes[i]);
+    gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FNST_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
 
-extern "C" int fnst_inorm_bwd_fused_parts(int h, int w, int c, int act_dtype, int g_dtype) {
-  if (c % IBF_CH != 0 || h <= 0 || w <= 0) return 0;
-  return ibf_parts(h, w, act_dtype, g_dtype);
+extern "C" int fnst_inorm_bwd_fused_parts(int n, int h, int w, int c, int act_dtype, int g_dtype, int has_gsrc, int has_extra, int s2d) {
+  if (c % 16 != 0 || s2d || (!has_gsrc && !has_extra) || n <= 0) return 0;
+  return ibf_geometry(n, h, w, c, act_dtype, g_dtype, (has_gsrc ? 1 : 0) + (has_extra ? 1 : 0)).K;
 }
 
 extern "C" int fnst_inorm_bwd_fused(const void* gsrc, const void* extra, const void* raw, const float* stats,
@@ -848,22 +985,49 @@ extern "C" int fnst_inorm_bwd_fused(const void* gsrc, const void* extra, const v
                                     float* sums, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
                                     int pad, int pad_mode, int s2d, int out_s2d, int device, void* stream) {
   FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && draw && sums, "inorm_bwd_fused: null pointer");
-  FNST_CHECK_ARG(c % IBF_CH == 0, "inorm_bwd_fused: channel count %d must be a multiple of %d", c, IBF_CH);
+  FNST_CHECK_ARG(c % 16 == 0, "inorm_bwd_fused: channel count %d must be a multiple of 16", c);
+  FNST_CHECK_ARG(!s2d, "inorm_bwd_fused: a space-to-depth gradient buffer needs the two-pass operators");
   FNST_CHECK_ARG(!out_s2d || (h % 2 == 0 && w % 2 == 0), "inorm_bwd_fused: space-to-depth output needs even h, w");
-  const int K = ibf_parts(h, w, act_dtype, g_dtype);
-  FNST_CHECK_ARG(K > 0, "inorm_bwd_fused: a %dx%d plane does not fit the shared memory of 8 CTAs (use the two-pass operators)", h, w);
+  FNST_CHECK_ARG(act_dtype != FNST_F32 || g_dtype == FNST_F32, "inorm_bwd_fused: fp32 activations need fp32 gradients");
+  const IbfGeometry G = ibf_geometry(n, h, w, c, act_dtype, g_dtype, (gsrc ? 1 : 0) + (extra ? 1 : 0));
+  FNST_CHECK_ARG(G.K > 0, "inorm_bwd_fused: a %dx%d plane does not fit the shared memory of 8 CTAs (use the two-pass operators)", h, w);
   FNST_DEVICE(device);
-  HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d};
-  const int rows = (h + K - 1) / K;
-  const size_t smem = (size_t)rows * w * IBF_CH * (dtype_size(act_dtype) + dtype_size(g_dtype));
-  dim3 grid(K, c / IBF_CH, n);
+  IbfParams P;
+  P.L = HaloLayout{h, w, c, gsrc ? pad : 0, (gsrc && pad_mode == FNST_PAD_REFLECT) ? 1 : 0, 0};
+  P.relu = relu; P.out_s2d = out_s2d; P.rows_per_part = G.rows_per_part; P.K = G.K; P.chunk_rows = G.chunk_rows; P.chunks = G.chunks;
+  P.chunk_stride = G.chunk_stride; P.cw = G.cw; P.tpp_log2 = G.cw == 64 ? 3 : (G.cw == 32 ? 2 : 1);
+  P.eps = eps;
+  P.dbg = tuning().debug_buf;
+  const uint64_t ea = dtype_size(act_dtype) / 2, eg = dtype_size(g_dtype) / 2;      // 2-byte units per element
+  CUtensorMap m_raw, m_g, m_e;
+  memset(&m_g, 0, sizeof(m_g)); memset(&m_e, 0, sizeof(m_e));
+  {
+    const uint64_t dims[4] = {(uint64_t)c * ea, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c * ea * 2, (uint64_t)c * ea * 2 * w, (uint64_t)c * ea * 2 * w * h};
+    const uint32_t box[4] = {(uint32_t)(G.cw * ea), (uint32_t)w, (uint32_t)G.chunk_rows, 1};
+    if (int r = encode_tensor_map_plain(&m_raw, raw, 4, dims, str, box)) return r;
+  }
+  if (gsrc) {
+    const uint64_t wp = w + 2 * P.L.pad, hp = h + 2 * P.L.pad;
+    const uint64_t dims[4] = {(uint64_t)c * eg, wp, hp, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c * eg * 2, (uint64_t)c * eg * 2 * wp, (uint64_t)c * eg * 2 * wp * hp};
+    const uint32_t box[4] = {(uint32_t)(G.cw * eg), (uint32_t)w, (uint32_t)G.chunk_rows, 1};
+    if (int r = encode_tensor_map_plain(&m_g, gsrc, 4, dims, str, box)) return r;
+  }
+  if (extra) {
+    const uint64_t dims[4] = {(uint64_t)c * eg, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c * eg * 2, (uint64_t)c * eg * 2 * w, (uint64_t)c * eg * 2 * w * h};
+    const uint32_t box[4] = {(uint32_t)(G.cw * eg), (uint32_t)w, (uint32_t)G.chunk_rows, 1};
+    if (int r = encode_tensor_map_plain(&m_e, extra, 4, dims, str, box)) return r;
+  }
+  dim3 grid(G.K, c / G.cw, n);
   FNST_DISPATCH_DTYPE(act_dtype, TA, {
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
       auto kern = inorm_bwd_fused_kernel<TA, TG>;
-      FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      launch_pdl_cluster(kern, grid, dim3(IBF_THREADS), smem, (cudaStream_t)stream, K,
-          reinterpret_cast<const TG*>(gsrc), reinterpret_cast<const TG*>(extra), reinterpret_cast<const TA*>(raw), stats, gamma,
-          beta, drop, reinterpret_cast<TG*>(draw), reinterpret_cast<TG*>(gy_out), sums, L, relu, eps, out_s2d, rows, K);
+      FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+      launch_pdl_cluster(kern, grid, dim3(IBF_THREADS), G.smem, (cudaStream_t)stream, G.K, m_raw, m_g, m_e,
+          reinterpret_cast<const TG*>(gsrc), extra ? 1 : 0, stats, gamma, beta, drop, reinterpret_cast<TG*>(draw),
+          reinterpret_cast<TG*>(gy_out), sums, P);
     });
   });
   return launch_status("inorm_bwd_fused");

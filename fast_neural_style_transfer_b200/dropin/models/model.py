@@ -95,13 +95,25 @@ class StyleTransferNet(nn.Module):
             self.__dict__["_plan_cache"] = cache
         return cache[1]
 
-    def _dropout_scales(self, x):
-        """One (B,256) Dropout2d scale per residual block, drawn from torch's RNG in block order with the
-        same call the reference makes per block (models/model.py:84,88; SURVEY 8c stochasticity)."""
+    def _dropout_scales(self, x, out=None):
+        """One (B,256) Dropout2d scale per residual block as a (5,B,256) tensor, drawn from torch's RNG in block order with
+        the same draw the reference makes per block (models/model.py:84,88; SURVEY 8c stochasticity).  `out`: draw into
+        this buffer (the captured training graph's own input: no copy)."""
         if not self.training:
             return None
-        ones = torch.ones((x.shape[0], 256, 1, 1), device=x.device)
-        return [F.dropout2d(ones, blk.dropout.p, True).view(x.shape[0], 256) for blk in self.res_blocks]
+        # Dropout2d on a (B,C,H,W) input draws noise = empty(B,C,1,1).bernoulli_(1-p).div_(1-p) (ATen feature_dropout): the same
+        # five draws, in block order, written straight into one (5,B,256) buffer -- 5 Philox launches + 1 scale instead of 5 x
+        # (ones, bernoulli, div, mul) + 5 copies into the captured graph's inputs
+        keep = [1.0 - blk.dropout.p for blk in self.res_blocks]
+        buf = out if out is not None else torch.empty((len(keep), x.shape[0], 256), dtype=torch.float32, device=x.device)
+        for i, q in enumerate(keep):
+            buf[i].view(x.shape[0], 256, 1, 1).bernoulli_(q)
+        if len(set(keep)) == 1:
+            buf.div_(keep[0])
+        else:
+            for i, q in enumerate(keep):
+                buf[i].div_(q)
+        return buf
 
     # Small no-grad forwards are launch-bound (59 launches): replay them as one CUDA graph per input shape.
     GRAPH_MAX_PIXELS = 4 * 1080 * 1920
@@ -150,7 +162,6 @@ class StyleTransferNet(nn.Module):
             raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
         params = list(self.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            drops = self._dropout_scales(x)
             if graphs.enabled() and not torch.cuda.is_current_stream_capturing():
                 # training step as two CUDA-graph replays (forward incl. weight re-pack, backward) per input shape
                 cache = self.__dict__.setdefault("_train_graphs", {})
@@ -158,14 +169,19 @@ class StyleTransferNet(nn.Module):
                 #  whose storage was replaced -- `.to()`, `p.data = ...` -- must not hit a stale capture)
                 key = (self.precision, tuple(x.shape), x.device.index, self.training, tuple(p.data_ptr() for p in params))
                 state = cache.get(key)
+                busy = state is not None and state.in_flight.busy()
+                # the Dropout2d scales are drawn straight into the captured graph's input buffer (unless that graph is in flight)
+                drops = self._dropout_scales(x, out=state.drop_input() if state is not None and not busy else None)
                 if state is None:
                     if len(cache) >= 4:
                         cache.clear()
                     state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(self.named_parameters()), self.precision, x, drops)
-                if not state.in_flight.busy():
+                if not busy:
                     return autograd_fns.stylenet_graphed_apply(state, x, drops, params)
                 # an earlier forward of this graph still waits for its backward (gradient accumulation, two losses on two
                 # inputs): the captured tape holds ONE forward, so this call takes the eager per-call-tape path below
+            else:
+                drops = self._dropout_scales(x)
             names = [n for n, _ in self.named_parameters()]
             return autograd_fns.stylenet_apply(self._plan(), names, x, drops, params)
         plan = self._plan()

@@ -221,9 +221,13 @@ class StyleNetPlan:
         w["final"] = pack_final_rowsum_x3(p["final_conv.conv.weight"])
         return w
 
-    def pack(self, params: Dict[str, torch.Tensor]) -> "StyleNetPlan":
+    def pack(self, params: Dict[str, torch.Tensor], for_backward: bool = False) -> "StyleNetPlan":
+        """for_backward: also pack the data-gradient operands (plan.wd) -- issued on a side stream that forward(tape=...)
+        joins at its end, so these small re-layout kernels run next to the forward instead of in front of the backward."""
         p = {k: v.detach() for k, v in params.items()}
         self.params = p
+        self.wd = None
+        self._wd_stream = None
         dt = self.dtype
         if self.split:
             self.w = self._pack_x3(p)
@@ -252,6 +256,15 @@ class StyleNetPlan:
         self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
         self.final_bias[:3] = p["final_conv.conv.bias"].float()
         self.w = w
+        if for_backward and w["final"].is_cuda:
+            from . import backward
+            dev = w["final"].device
+            main = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.wd = backward.pack_dgrad_operands(self)
+            self._wd_stream = side
         return self
 
     def _affine(self, name: str) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -386,6 +399,9 @@ class StyleNetPlan:
         if tape is not None:
             tape.update(raw3=raw3, st3=st3, act3=act3, raw4=raw4, st4=st4, act4=act4, act4_flat=flat, x=x)
             tape["w"]["act3"] = act3_b
+        if getattr(self, "_wd_stream", None) is not None:
+            torch.cuda.current_stream(dev).wait_stream(self._wd_stream)      # join the data-gradient operand packing branch
+            self._wd_stream = None
         return y
 
 

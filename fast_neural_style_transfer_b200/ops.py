@@ -362,10 +362,11 @@ def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-
     return draw, dgb
 
 
-def inorm_bwd_fused_parts(raw: torch.Tensor, gdtype: torch.dtype) -> int:
-    """Cluster size the one-pass kernel needs for raw's plane; 0 = does not fit (use inorm_bwd_reduce + inorm_bwd_apply)."""
+def inorm_bwd_fused_parts(raw: torch.Tensor, gdtype: torch.dtype, has_gsrc: bool = True, has_extra: bool = False, s2d: bool = False) -> int:
+    """Cluster size the one-pass kernel needs for this configuration; 0 = unsupported / does not fit (use inorm_bwd_reduce +
+    inorm_bwd_apply)."""
     n, h, w, c = raw.shape
-    return int(lib.fnst_inorm_bwd_fused_parts(h, w, c, dt(raw.dtype), dt(gdtype)))
+    return int(lib.fnst_inorm_bwd_fused_parts(n, h, w, c, dt(raw.dtype), dt(gdtype), int(has_gsrc), int(has_extra), int(s2d)))
 
 
 def inorm_bwd_fused(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=_lib.PAD_NONE, s2d=False,

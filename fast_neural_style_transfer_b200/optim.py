@@ -159,6 +159,15 @@ class Adam(torch.optim.Optimizer):
         self._share_steps()
         self._lists.clear()
 
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """`Optimizer.zero_grad` (train.py:199) without the generic per-dtype/device grouping (a few microseconds instead of
+        ~0.1 ms of host time for 58 parameters; the step is host-paced right after the NaN check)."""
+        if not set_to_none:
+            return super().zero_grad(set_to_none=False)
+        for group in self.param_groups:
+            for p in group["params"]:
+                p.grad = None
+
     @torch.no_grad()
     def step(self, closure=None, *, grad_scale: Optional[torch.Tensor] = None):
         """One update.  `grad_scale`: optional 1-element float32 device tensor multiplied into every gradient inside the

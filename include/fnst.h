@@ -250,14 +250,16 @@ int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, co
 /*
  * InstanceNorm2d backward in ONE pass (same semantics as fnst_inorm_bwd_reduce followed by fnst_inorm_bwd_apply; autograd of
  * nn.InstanceNorm2d / F.relu / nn.Dropout2d / ReflectionPad2d / `x + y`, models/model.py:51-61,74-75,86-90 under train.py:200).
- * A slab (image, 16 channels) is held in the shared memory of a thread-block cluster of K CTAs; the per-channel sums travel
- * through distributed shared memory, so every tensor is read once and nothing is re-read or atomically accumulated:
+ * A slab (image, 16 channels) is staged by TMA box loads into the shared memory of a thread-block cluster of K CTAs; the
+ * per-channel sums travel through distributed shared memory, so every tensor is read once and nothing is re-read or
+ * atomically accumulated (gsrc: plain halo layout only -- a space-to-depth gradient buffer needs the two-pass operators):
  *   draw    [n,h,w,c] (or space-to-depth if out_s2d)   gradient of the raw conv output
  *   gy_out  or NULL  [n,h,w,c]                           the gradient gy itself (the residual branch re-uses it)
  *   sums    [n][c][2] fp32, WRITTEN (not accumulated)     (sum gy, sum gy*xhat) per plane, for fnst_affine_grads
- * fnst_inorm_bwd_fused_parts returns K for a plane size (0: does not fit 8 CTAs' shared memory -> use the two-pass operators).
+ * fnst_inorm_bwd_fused_parts returns K for a configuration (0: w > 256, space-to-depth gsrc, or the plane does not fit 8 CTAs'
+ * shared memory -> use the two-pass operators).
  */
-int fnst_inorm_bwd_fused_parts(int h, int w, int c, int act_dtype, int g_dtype);
+int fnst_inorm_bwd_fused_parts(int n, int h, int w, int c, int act_dtype, int g_dtype, int has_gsrc, int has_extra, int s2d);
 int fnst_inorm_bwd_fused(const void* gsrc, const void* extra, const void* raw, const float* stats,
                          const float* gamma, const float* beta, const float* drop, void* draw, void* gy_out,
                          float* sums, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,

@@ -276,8 +276,8 @@ def _norm_consts(raw, stats, eps):
     return mean, rstd, xhat
 
 
-def inorm_bwd_fused_parts(raw, gdtype):
-    return 1 if raw.shape[-1] % 16 == 0 and raw.shape[1] * raw.shape[2] <= 64 * 64 else 0     # exercise both paths on CPU
+def inorm_bwd_fused_parts(raw, gdtype, has_gsrc=True, has_extra=False, s2d=False):
+    return 1 if raw.shape[-1] % 16 == 0 and raw.shape[1] * raw.shape[2] <= 64 * 64 and not s2d else 0     # exercise both paths on CPU
 
 
 def inorm_bwd_fused(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=PAD_NONE, s2d=False,

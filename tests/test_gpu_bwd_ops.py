@@ -170,16 +170,36 @@ def test_inorm_backward(cfg, gdtype, mode, hw):
         gy, sums = ops.inorm_bwd_reduce(*args)
         draw, dgb = ops.inorm_bwd_apply(gy, raw.to(DEV), st.to(DEV), sums, gamma.to(DEV), out_s2d=cfg["out_s2d"])
     else:
-        parts = ops.inorm_bwd_fused_parts(raw.to(DEV), gdtype)
-        expect = {(10, 12): 1, (72, 48): 2, (100, 98): 4, (160, 160): 8}[hw] * (2 if gdtype == torch.float32 else 1)
-        assert parts == (expect if expect <= 8 else 0), (parts, expect)
+        parts = ops.inorm_bwd_fused_parts(raw.to(DEV), gdtype, True, extra is not None, cfg["s2d"])
+        esz = raw.element_size()
+        cr = min(256 // w, h) if w <= 256 else 0                                 # rows per TMA chunk (<= 256 pixels)
+        stride = -(-(cr * w) // 8) * 8 if cr else 0
+
+        def choose():
+            """Mirror of ibf_geometry: per slab width the smallest cluster that fits ~200 KB; most CTAs (cap 128); ties: a cluster
+            of at most 4 beats one of 8, else the widest slab."""
+            best, best_ctas = 0, 0
+            for cw in (64, 32, 16):
+                if c % cw:
+                    continue
+                for k in (1, 2, 4, 8):
+                    rows = -(-(-(-h // k)) // cr) * cr                            # ceil(ceil(h / k) / cr) * cr: whole chunks
+                    if (rows // cr) * stride * cw * esz * (2 + (extra is not None)) <= 200 * 1024 and rows // cr <= 32:
+                        ctas = min(128, k * (c // cw) * n)
+                        if ctas > best_ctas or (ctas == best_ctas and best > 4 and k <= 4):
+                            best, best_ctas = k, ctas
+                        break
+            return best
+        expect = 0 if (cfg["s2d"] or not cr) else choose()
+        assert parts == expect, (parts, expect)
         if parts == 0:
-            pytest.skip("plane does not fit the shared memory of 8 CTAs in fp32: the plan falls back to the two-pass operators")
+            pytest.skip("space-to-depth gradient buffer / plane too large for 8 CTAs: the plan uses the two-pass operators here")
         draw, gy, sums = ops.inorm_bwd_fused(*args, out_s2d=cfg["out_s2d"], want_gy=True)
         draw2, gy2, _ = ops.inorm_bwd_fused(*args, out_s2d=cfg["out_s2d"], want_gy=False)
         assert gy2 is None and torch.equal(draw2, draw)                        # deterministic, with or without the gy output
         gy_ref, sums_ref = ops.inorm_bwd_reduce(*args)
-        assert rel_l2(gy, gy_ref) < 1e-6 and rel_l2(sums, sums_ref) < 2e-5
+        # (16-bit gradients: border pixels are rounded once more, when the folded halo contributions are added into the staged tile)
+        assert rel_l2(gy, gy_ref) < (1e-6 if gdtype == torch.float32 else 4e-3) and rel_l2(sums, sums_ref) < (2e-5 if gdtype == torch.float32 else 4e-3)
         dgb = torch.empty((2, c), dtype=torch.float32, device=DEV)
         ops.affine_grads(sums.reshape(-1), [(0, c, 0, c)], n, dgb.view(-1))
     ref = r64.grad

@@ -114,6 +114,39 @@ def case_inorm_bwd(B, sets, which, hw=64, c=256):
     return run_apply, sets, B * hw * hw * c * (2 + 2 + 2)
 
 
+def case_inorm_bwd_fused(B, sets, hw=64, c=256, want_gy=False, extra_on=False):
+    adt, gdt = torch.float16, torch.bfloat16
+    raws = [torch.randn((B, hw, hw, c), device=DEV).to(adt) for _ in range(sets)]
+    gsrc = [torch.randn((B, hw + 2, hw + 2, c), device=DEV).to(gdt) for _ in range(sets)]
+    extra = [torch.randn((B, hw, hw, c), device=DEV).to(gdt) if extra_on else None for _ in range(sets)]
+    st = torch.rand((B, c, 2), device=DEV) * hw * hw
+    st[:, :, 1] += hw * hw
+    g, b = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    sums = torch.empty((B, c, 2), device=DEV)
+
+    def run():
+        for r, gs_, ex in zip(raws, gsrc, extra):
+            ops.inorm_bwd_fused(gs_, ex, r, st, g, b, None, gdt, True, 1, PAD_REFLECT, want_gy=want_gy, sums=sums)
+    return run, sets, B * hw * hw * c * (2 + 2 + 2 + (2 if extra_on else 0) + (2 if want_gy else 0))
+
+
+def case_grad_assemble(sets):
+    from fast_neural_style_transfer_b200 import backward
+    sys.path.insert(0, os.path.join(ROOT, "fast_neural_style_transfer_b200", "dropin"))
+    from models.model import StyleTransferNet
+    net = StyleTransferNet().to(DEV)
+    names = [n for n, _ in net.named_parameters()]
+    params = dict(net.named_parameters())
+    _, total = backward._staging_layout(True)
+    cores = [dict(staging=torch.randn(total, device=DEV), sums=torch.randn(2 * 4 * engine.STATS_CHANNELS + 64 * 14, device=DEV),
+                  norm_sums={ln: (0, params[ln + ".weight"].numel()) for ln in backward.NORM_LAYERS}, batch=4, tc=True) for _ in range(sets)]
+
+    def run():
+        for core in cores:
+            backward.assemble_gradients(core, names, params)
+    return run, sets, 3 * 4.0 * sum(p.numel() for p in params.values())
+
+
 def case_optimizer_tail(sets, impl):
     """clip_grad_norm_(1.0) + Adam.step over the 58 StyleTransferNet parameter tensors (train.py:203-205): libfnst's three
     multi-tensor kernels vs torch's foreach implementations.  GPU time per whole tail; bytes = 4 + 8 + 28 per element."""
@@ -175,6 +208,10 @@ def main():
     for blocks in (1, 2):
         rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=1, inorm_bwd_blocks=blocks)
     rec("inorm_bwd_apply_256", lambda s: case_inorm_bwd(B, s, "apply"), pdl=1)
+    rec("inorm_bwd_fused_256", lambda s: case_inorm_bwd_fused(B, s), pdl=1)
+    rec("inorm_bwd_fused_256_extra_gy", lambda s: case_inorm_bwd_fused(B, s, want_gy=True, extra_on=True), pdl=1)
+    rec("inorm_bwd_fused_64ch_128px", lambda s: case_inorm_bwd_fused(B, s, hw=128, c=64), pdl=1)
+    rec("grad_assemble", lambda s: case_grad_assemble(min(s, 4)), pdl=1)
     rec("vgg_conv1_2_64", lambda s: case_conv3x3(B, s, dt=torch.bfloat16, hw=256, cin=64, cout=64), pdl=1)
     rec("vgg_conv2_2_128", lambda s: case_conv3x3(B, s, dt=torch.bfloat16, hw=128, cin=128, cout=128), pdl=1)
     for impl in ("fnst", "torch"):
