@@ -26,7 +26,7 @@ def run(args, wl, net, rank, world, dev, peaks):
     vgg = VGG19()
     vgg.load_state_dict(bench_data.vgg_state_dict(seed=1))
     vgg = vgg.to(dev).eval()
-    vgg.precision = "fp32" if args.precision == "fp32" else "bf16"
+    vgg.precision = {"fp32": "fp32", "fp16x3": "fp16"}.get(args.precision, "bf16")
     for p in vgg.parameters():
         p.requires_grad = False
     net.train()
@@ -106,10 +106,13 @@ def run(args, wl, net, rank, world, dev, peaks):
     value = world * args.steps / (ms / 1e3)
     line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
-            "dtype": {"fp16": "f16 fwd / bf16 grads", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "dtype": {"fp16": "f16 fwd / bf16 grads", "bf16": "bf16", "fp32": "f32",
+                      "fp16x3": "f16x3 fwd (hi,lo split, fp32-class) / bf16 grads"}[args.precision], "data": "synthetic",
             "config": B.train_config(world, bsz, h, w),
             "optimizer_impl": "libfnst multi-tensor kernels" if args.optimizer == "fnst" else "torch foreach",
-            "precision_note": "fp16 activations / bf16 gradients on tcgen05 (outputs and losses within the 1e-2 gate); VGG-19 in bf16",
+            "precision_note": {"fp16": "fp16 activations / bf16 gradients on tcgen05 (outputs and losses within the 1e-2 gate); VGG-19 in bf16",
+                               "fp16x3": "fp32-class forward on tcgen05 (fp16 hi,lo pairs, 3 MMAs per product) + bf16 backward: losses 1e-4, "
+                                         "every gradient tensor within 2e-2 of the fp32 oracle; VGG-19 fp16 inside / bf16 interface"}.get(args.precision, ""),
             "images_per_s": value * bsz,
             "whole_step_tflops": value * bsz * B.TRAIN_GFLOP_IMG / 1e3 / world,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (3x3 256->256 residual conv; forward launch, batch 4)",

@@ -67,7 +67,7 @@ def _match_layout(a: torch.Tensor, b: torch.Tensor):
     """Bring a (B,C,H,W)-logical pair to identical contiguous memory order; Gram-like (B,C,C)/(C,C) pass through."""
     if a.dim() == 4:
         an = _as_nhwc(a)
-        bn = _as_nhwc(b, an.dtype) if b.dim() == 4 else b
+        bn = _as_nhwc(b) if b.dim() == 4 else b                  # element types may differ (the reduction kernels take both)
         return an, bn.contiguous()
     return a.contiguous(), b.contiguous()
 
@@ -199,13 +199,21 @@ def stylenet_apply(plan, names: Sequence[str], x: torch.Tensor, drop, params: Se
     return _StyleNet.apply(plan, list(names), x, drop, *params)
 
 
+def _grad_interface(feats):
+    """Feature maps that will receive gradients are handed to autograd in the gradient element type: autograd casts an
+    incoming gradient to the dtype of the forward output, and fp16 cannot hold the un-normalised Gram / style gradients
+    (SURVEY 7.2).  fp16 features are therefore returned as bfloat16 copies (the fp16 originals stay on the tape: they are the
+    ReLU / max-pool masks and the operands of the next layer); bf16 / fp32 features pass through."""
+    return tuple(ops.cast(f, torch.bfloat16) if f.dtype == torch.float16 else f for f in feats)
+
+
 class _VGG(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, x):
         tape: dict = {}
         feats = plan.forward(x.detach(), tape)
         ctx.plan, ctx.tape = plan, tape
-        return tuple(feats)
+        return _grad_interface(feats)
 
     @staticmethod
     def backward(ctx, *dfeats):
@@ -325,7 +333,8 @@ class VGGGraph:
 
         def fwd(x_):
             self.tape.clear()
-            return tuple(plan.forward(x_, self.tape if with_tape else None))
+            feats = plan.forward(x_, self.tape if with_tape else None)
+            return _grad_interface(feats) if with_tape else tuple(feats)
 
         self.fwd = graphs.GraphedPlan(fwd, [x.float().contiguous()])
         self.bwd = {}

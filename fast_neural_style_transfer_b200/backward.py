@@ -192,8 +192,10 @@ def pack_dgrad_operands(plan: "engine.StyleNetPlan") -> Dict[str, torch.Tensor]:
     gdt = grad_dtype(plan.precision)
     gp, f64 = ops.gather_pack, torch.float64
     convT_dgrad = lambda kc: (lambda t: pack_dgrad(engine.pack_conv_transpose(t, f64), 4, kc, f64))
+    # the ten 3x3 weights as one stacked tensor (10, O, C, 3, 3) -> (10, C, 9*O): one gather for all data-gradient operands
+    stacked = torch.stack([p[f"res_blocks.{i}.{c}.conv.weight"] for i in range(5) for c in ("conv1", "conv2")])
     wd = {
-        "res": gp("res_dgrad", lambda t: t.view(10, 256, 9, 256).permute(0, 3, 2, 1).reshape(10, 256, 9 * 256), plan.w["res_all"], gdt),
+        "res": gp("res_dgrad", lambda t: t.permute(0, 2, 3, 4, 1).reshape(10, 256, 9 * 256), stacked, gdt),
         "up1": gp("convT_dgrad", convT_dgrad(256), p["up1.upsample_conv.weight"], gdt),
         "up2": gp("convT_dgrad", convT_dgrad(64), p["up2.upsample_conv.weight"], gdt),
         "conv2": gp("s2d_dgrad", lambda t: pack_dgrad_s2d(t, f64), p["conv2.conv.weight"], gdt),

@@ -11,10 +11,10 @@ reference does without a network: a perceptual loss against a silently random VG
 The reference constructor's undefined `slice5` (:51) is created here.
 
 Precision: `vgg.precision` in {"bf16" (default), "fp16", "fp32"}; FNST_VGG_PRECISION overrides, FNST_PRECISION=fp32
-selects fp32 for both networks.  Gradients of the features are bf16 on the tensor-core paths; because autograd casts an
-incoming gradient to the dtype of the forward output, feature maps that need a gradient must themselves be bf16 (or
-fp32) -- asking the fp16 path for gradients raises instead of overflowing (fp16 cannot hold the un-normalised
-Gram / style gradients).
+selects fp32 for both networks.  Gradients are bf16 on both tensor-core paths (fp16 cannot hold the un-normalised
+Gram / style gradients).  Because autograd casts an incoming gradient to the dtype of the forward output,
+"fp16" keeps fp16 activations INSIDE the stack (11-bit masks and operands) but returns feature maps that need a gradient
+as bfloat16 copies.
 """
 import os
 import sys
@@ -81,9 +81,6 @@ class VGG19(nn.Module):
             raise RuntimeError("VGG19 (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
         plan = self._plan()
         need_grad = torch.is_grad_enabled() and x.requires_grad
-        if need_grad and self.precision == "fp16":
-            raise RuntimeError("VGG19 (B200 drop-in): precision 'fp16' cannot back-propagate -- autograd would cast the bf16 feature "
-                               "gradients to fp16, which overflows on the un-normalised Gram / style gradients; use 'bf16' (default) or 'fp32'")
         small = x.shape[0] * x.shape[2] * x.shape[3] <= 16 * 256 * 256
         if graphs.enabled() and small and not torch.cuda.is_current_stream_capturing():
             cache = self.__dict__.setdefault("_graphs", {})

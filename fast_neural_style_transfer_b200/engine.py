@@ -233,6 +233,7 @@ class StyleNetPlan:
             self.w = self._pack_x3(p)
             self.final_bias = torch.zeros(16, dtype=torch.float32, device=self.w["final"].device)
             self.final_bias[:3] = p["final_conv.conv.bias"].float()
+            self._pack_for_backward(for_backward)
             return self
         # irregular re-layouts run as one gather kernel each (ops.gather_pack: cached index map of the layout function)
         gp, f64 = ops.gather_pack, torch.float64
@@ -256,16 +257,19 @@ class StyleNetPlan:
         self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
         self.final_bias[:3] = p["final_conv.conv.bias"].float()
         self.w = w
-        if for_backward and w["final"].is_cuda:
+        self._pack_for_backward(for_backward)
+        return self
+
+    def _pack_for_backward(self, for_backward: bool) -> None:
+        if for_backward and self.w["final"].is_cuda:
             from . import backward
-            dev = w["final"].device
+            dev = self.w["final"].device
             main = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self.wd = backward.pack_dgrad_operands(self)
             self._wd_stream = side
-        return self
 
     def _affine(self, name: str) -> Tuple[torch.Tensor, torch.Tensor]:
         return self.params[name + ".weight"].float().contiguous(), self.params[name + ".bias"].float().contiguous()
@@ -293,9 +297,7 @@ class StyleNetPlan:
         if tc:
             ops.require_tensor_cores(dev)
         if self.split:
-            if tape is not None:
-                raise RuntimeError("precision 'fp16x3' is a forward-only (inference) path; train with 'fp16' or 'fp32'")
-            return self._forward_x3(x, drop_scales)
+            return self._forward_x3(x, drop_scales, tape)
 
         # conv1: 9x9 stride 2, reflect 4 -> raw1 (B,H1,W1,64)
         H1, W1 = _half_up(H), _half_up(W)
@@ -405,11 +407,20 @@ class StyleNetPlan:
         return y
 
 
-    def _forward_x3(self, x: torch.Tensor, drop_scales) -> torch.Tensor:
+    def _forward_x3(self, x: torch.Tensor, drop_scales, tape: Optional[dict] = None) -> torch.Tensor:
         """fp16x3 forward: same operator sequence; activations are fp16 [hi | lo] pairs (2C channels per pixel), raw conv
-        outputs are fp32, every gather-GEMM runs three virtual taps per real tap (hi*hi, hi*lo, lo*hi)."""
+        outputs are fp32, every gather-GEMM runs three virtual taps per real tap (hi*hi, hi*lo, lo*hi).
+
+        With a tape (training): the fp32-class forward is what the gradients need -- ReLU / InstanceNorm make the gradient a
+        discontinuous function of the forward values, and rounding ANY forward operand to 16 bits moves the early layers'
+        gradients by ~5e-2 (tools/exp_grad_rounding_points.py), whereas bf16 rounding in the backward GEMMs costs ~1e-2.  So
+        the tape holds the fp32 raw outputs (masks, statistics) and, beside each split activation, a plain bfloat16 twin
+        written by the same inorm_apply launch: the operand of the bf16 weight-gradient GEMM.  The backward is the ordinary
+        bf16 tensor-core backward (backward.stylenet_backward_core)."""
         B, _, H, W = x.shape
         dev, w = x.device, self.w
+        twin = tape is not None
+        new2 = (lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)) if twin else (lambda *s: None)
         act = lambda *s: torch.empty(s, dtype=torch.float16, device=dev)
         raw = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         arena = ops.ZeroArena(B * 2 * STATS_CHANNELS, dev)          # all InstanceNorm statistics: one memset per forward
@@ -430,47 +441,67 @@ class StyleNetPlan:
         Hp, Wp = H1 + 2, W1 + 2
         Hs, Ws = _half_up(Hp), _half_up(Wp)
         buf2 = torch.zeros((B, Hs, Ws, 512), dtype=torch.float16, device=dev)
+        buf2_b = torch.zeros((B, Hs, Ws, 256), dtype=torch.bfloat16, device=dev) if twin else None
         g, b = self._affine("norm1")
-        ops.inorm_apply(raw1, st1, g, b, buf2, relu=True, pad=1, pad_mode=PAD_REFLECT, s2d=True, split=True)
+        ops.inorm_apply(raw1, st1, g, b, buf2, relu=True, pad=1, pad_mode=PAD_REFLECT, s2d=True, split=True, out2=buf2_b)
         H2, W2 = _half_up(H1), _half_up(W1)
         raw2, st2 = raw(B, H2, W2, 256), stats(256)
         conv(taps_s2d_3x3(64, 2), 64, 64, w["conv2"], 256, 256, buf2, (B, Hs, Ws, 512), raw2, (H2, W2), st2)
-        cur = act(B, H2 + 2, W2 + 2, 512)
+        cur, cur_b = act(B, H2 + 2, W2 + 2, 512), new2(B, H2 + 2, W2 + 2, 256)
         g, b = self._affine("norm2")
-        ops.inorm_apply(raw2, st2, g, b, cur, relu=True, pad=1, pad_mode=PAD_REFLECT, split=True)
+        ops.inorm_apply(raw2, st2, g, b, cur, relu=True, pad=1, pad_mode=PAD_REFLECT, split=True, out2=cur_b)
+        if twin:
+            tape.update(raw1=raw1, st1=st1, buf2=buf2, raw2=raw2, st2=st2, trunk=[cur], blocks=[])
+            tape["w"] = dict(buf2=buf2_b, trunk=[cur_b], mid=[])
         taps9 = taps_kxk(3)
         for i in range(5):
             raw_a, st_a = raw(B, H2, W2, 256), stats(256)
             conv(taps9, 256, 256, w[f"res{i}a"], 256, 256, cur, (B, H2 + 2, W2 + 2, 512), raw_a, (H2, W2), st_a)
-            mid = act(B, H2 + 2, W2 + 2, 512)
+            mid, mid_b = act(B, H2 + 2, W2 + 2, 512), new2(B, H2 + 2, W2 + 2, 256)
             g, b = self._affine(f"res_blocks.{i}.in1")
             drop = None if drop_scales is None else drop_scales[i].float().contiguous()
-            ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop, split=True)
+            ops.inorm_apply(raw_a, st_a, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop, split=True, out2=mid_b)
             raw_b, st_b = raw(B, H2, W2, 256), stats(256)
             conv(taps9, 256, 256, w[f"res{i}b"], 256, 256, mid, (B, H2 + 2, W2 + 2, 512), raw_b, (H2, W2), st_b)
             last = i == 4
             nxt = act(B, H2, W2, 512) if last else act(B, H2 + 2, W2 + 2, 512)
+            nxt_b = new2(B, H2, W2, 256) if last else new2(B, H2 + 2, W2 + 2, 256)
             g, b = self._affine(f"res_blocks.{i}.in2")
             ops.inorm_apply(raw_b, st_b, g, b, nxt, relu=False, pad=0 if last else 1,
-                            pad_mode=PAD_NONE if last else PAD_REFLECT, res=cur, res_pad=1, split=True)
+                            pad_mode=PAD_NONE if last else PAD_REFLECT, res=cur, res_pad=1, split=True, out2=nxt_b)
+            if twin:
+                tape["blocks"].append(dict(raw_a=raw_a, st_a=st_a, mid=mid, raw_b=raw_b, st_b=st_b, drop=drop))
+                tape["trunk"].append(nxt)
+                tape["w"]["trunk"].append(nxt_b)
+                tape["w"]["mid"].append(mid_b)
             cur = nxt
         H3, W3 = 2 * H2, 2 * W2
         raw3, st3 = raw(B, H3, W3, 64), stats(64)
         conv(TAPS_2X2, 256, 256, w["up1"], 256, 64, cur, (B, H2, W2, 512), raw3, (H2, W2), st3, epilogue=EPI_D2S)
-        act3 = act(B, H3, W3, 128)
+        act3, act3_b = act(B, H3, W3, 128), new2(B, H3, W3, 64)
         g, b = self._affine("norm3")
-        ops.inorm_apply(raw3, st3, g, b, act3, relu=True, split=True)
+        ops.inorm_apply(raw3, st3, g, b, act3, relu=True, split=True, out2=act3_b)
         H4, W4 = 2 * H3, 2 * W3
         raw4, st4 = raw(B, H4, W4, 32), stats(32)
         conv(TAPS_2X2, 64, 64, w["up2"], 128, 32, act3, (B, H3, W3, 128), raw4, (H3, W3), st4, epilogue=EPI_D2S)
         Hq, Wq = H4 + 8, W4 + 8
         act4 = act(B, Hq, Wq, 64)                           # one pixel = [hi32 | lo32] = one 128-byte row
+        flat_b = None
+        if twin:                                            # plain 32-channel bf16 copy (+ slack for the pixel-pair window view)
+            flat_b = torch.empty(B * Hq * Wq * 32 + 128, dtype=torch.bfloat16, device=dev)
+            flat_b[-128:].zero_()
         g, b = self._affine("norm4")
-        ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT, split=True)
+        ops.inorm_apply(raw4, st4, g, b, act4, relu=True, pad=4, pad_mode=PAD_REFLECT, split=True, out2=flat_b)
         y = torch.empty((B, 3, H4, W4), dtype=torch.float32, device=dev)
         taps = [(0, kw, 0) for kw in range(9) for _blk in (0, 1)]
         ops.conv_gather(ConvSpec(taps, 64, w["final"], 32, 3, epilogue=EPI_ROWSUM9, bias=self.final_bias), act4,
                         (B, Hq, Wq, 64), _nhwc_strides(act4), y, (H4, W4), None, True)
+        if twin:
+            tape.update(raw3=raw3, st3=st3, act3=act3, raw4=raw4, st4=st4, act4=act4, act4_flat=flat_b, x=x)
+            tape["w"].update(act3=act3_b, act4_flat=flat_b)
+        if getattr(self, "_wd_stream", None) is not None:
+            torch.cuda.current_stream(dev).wait_stream(self._wd_stream)      # join the data-gradient operand packing branch
+            self._wd_stream = None
         return y
 
 

@@ -35,8 +35,12 @@ def _step(dropin, precision, vgg_precision, b, h, w, seed=0):
     mm, mv, ll = dropin
     p = O.make_net_params(seed=seed, random_affine=True)
     vp = O.make_vgg_params(seed=1)
-    net = mm.StyleTransferNet().to(DEV); net.load_state_dict(p); net.precision = precision; net.train()
-    vgg = mv.VGG19().to(DEV); vgg.load_state_dict(vp); vgg.precision = vgg_precision; vgg.eval()
+    net = mm.StyleTransferNet().to(DEV); net.load_state_dict(p); net.train()
+    vgg = mv.VGG19().to(DEV); vgg.load_state_dict(vp); vgg.eval()
+    if precision is not None:                      # None: the modules' untouched defaults (what an unmodified train.py gets)
+        net.precision = precision
+    if vgg_precision is not None:
+        vgg.precision = vgg_precision
     content = O.make_image(b, h, w, seed=5, normalized=True)
     sty = O.make_image(1, h, w, seed=6, normalized=True)
     with torch.no_grad():
@@ -122,6 +126,23 @@ def test_training_step_tensor_core_path(dropin):
     got, grads, rl, rg = _step(dropin, "fp16", "bf16", 2, 64, 64)
     assert rel_l2(got["stylized"], rl["stylized"]) < 1e-2
     _check(got, grads, rl, rg, tol_loss=1e-2, tol_grad=1.2e-1, label="tc 2x64x64")
+
+
+def test_training_step_with_untouched_module_defaults(dropin):
+    """What an unmodified train.py gets: StyleTransferNet() and VGG19() with their default precisions (fp16 network, bf16
+    loss network, bf16 gradients) -- finite, within the tensor-core tolerances, no overflow in the style gradients."""
+    got, grads, rl, rg = _step(dropin, None, None, 2, 64, 64)
+    assert all(torch.isfinite(g).all() for g in grads.values())
+    assert rel_l2(got["stylized"], rl["stylized"]) < 1e-2
+    _check(got, grads, rl, rg, tol_loss=1e-2, tol_grad=1.2e-1, label="defaults 2x64x64")
+
+
+def test_training_step_fp16x3_forward_bf16_backward(dropin):
+    """precision='fp16x3' with a tape: fp32-class forward on tensor cores (error-compensated fp16 pairs) + the ordinary bf16
+    tensor-core backward.  Removes the mask-flip gradient error of a 16-bit forward (tools/exp_grad_rounding_points.py)."""
+    got, grads, rl, rg = _step(dropin, "fp16x3", "fp16", 2, 64, 64)
+    assert rel_l2(got["stylized"], rl["stylized"]) < 1e-4
+    _check(got, grads, rl, rg, tol_loss=2e-3, tol_grad=3e-2, label="x3 2x64x64")
 
 
 def test_training_step_tensor_core_path_odd_size(dropin):

@@ -20,8 +20,11 @@ def _oracle_net_grads(p, x, drop, dy):
     return {k: v.grad for k, v in q.items()}
 
 
-@pytest.mark.parametrize("precision,shape", [("fp32", (2, 24, 24)), ("fp32", (1, 20, 28)), ("fp16", (2, 24, 24)), ("fp16", (1, 36, 20))])
+@pytest.mark.parametrize("precision,shape", [("fp32", (2, 24, 24)), ("fp32", (1, 20, 28)), ("fp16", (2, 24, 24)), ("fp16", (1, 36, 20)),
+                                             ("fp16x3", (2, 24, 24)), ("fp16x3", (1, 36, 20))])
 def test_stylenet_backward_matches_autograd(monkeypatch, precision, shape):
+    """fp16x3: the split forward keeps its own fp16 (hi, lo) arithmetic and its bf16 activation twins here, so the bound is
+    that of bf16 weight-gradient operands (the structure of the tape -- split buffers, twins, window views -- is what is checked)."""
     emu_ops.install_backward(monkeypatch, ops)
     monkeypatch.setattr(backward, "grad_dtype", lambda precision: torch.float32)      # plan structure in fp32 arithmetic
     p = O.make_net_params(seed=3, random_affine=True)
@@ -29,10 +32,14 @@ def test_stylenet_backward_matches_autograd(monkeypatch, precision, shape):
     x = O.make_image(b, h, w, seed=11)
     drop = O.make_dropout_scales(b, seed=9)
     plan = engine.StyleNetPlan(precision)
-    plan.dtype = torch.float32
+    if precision != "fp16x3":
+        plan.dtype = torch.float32
     plan.pack(p)
     tape = {}
     y = plan.forward(x, drop, tape)
+    if precision == "fp16x3":
+        with torch.no_grad():
+            assert rel_l2(y, O.stylenet_forward(p, x, drop)) < 1e-4
     dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
     grads = backward.stylenet_backward(plan, tape, dy)
     ref = _oracle_net_grads(p, x, drop, dy)
@@ -44,7 +51,7 @@ def test_stylenet_backward_matches_autograd(monkeypatch, precision, shape):
             # a bias in front of InstanceNorm has zero gradient; autograd returns fp32 noise there (SURVEY 8c hazard i)
             assert float(grads[k].abs().max()) == 0.0 and float(g.abs().max()) < 1e-4 * scale, k
         else:
-            assert rel_l2(grads[k], g) < 2e-4, (k, rel_l2(grads[k], g))
+            assert rel_l2(grads[k], g) < (2e-4 if precision != "fp16x3" else 1e-2), (k, rel_l2(grads[k], g))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
