@@ -55,7 +55,9 @@ def run(args, wl, net, rank, world, dev, peaks):
         s_loss = L.style_loss(sf, targets)
         tv_loss = L.total_variation_loss(stylized)
         total = 1000.0 * c_loss + 1 * s_loss + 10 * tv_scale * tv_loss
-        if torch.isnan(total) or torch.isinf(total):                                    # train.py:193 (host sync)
+        # train.py:193 (host sync); with several ranks the decision is taken on a MIN-reduced flag so that all ranks skip together
+        ok = parallel.all_finite(total, world) if world > 1 else not (torch.isnan(total) or torch.isinf(total))
+        if not ok:
             raise RuntimeError("invalid loss in benchmark step")
         opt.zero_grad()
         total.backward()

@@ -1,0 +1,89 @@
+"""Data-parallel training on real NCCL ranks: every rank runs the CUDA path on its shard of the batch, the
+gradients meet in ONE SUM all-reduce of the flat bucket (TV term scaled by 1/world), and the result must equal the oracle's
+gradient of the single-process step on the concatenated batch (train.py:168-206); the NaN/Inf skip of train.py:193 is taken on
+a reduced flag.  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped otherwise."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import stylenet_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "fast_neural_style_transfer_b200", "dropin")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir, precision, vgg_precision, per_rank, size):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), FNST_VGG19_RANDOM_INIT="1")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, DROPIN)
+        from fast_neural_style_transfer_b200 import parallel
+        import models.model as mm
+        import models.vgg19_net as mv
+        import losses.losses as ll
+        p = O.make_net_params(seed=0, random_affine=True)
+        vp = O.make_vgg_params(seed=1)
+        net = mm.StyleTransferNet().to(dev); net.load_state_dict(p); net.precision = precision; net.eval()     # eval: no dropout, grads on
+        vgg = mv.VGG19().to(dev); vgg.load_state_dict(vp); vgg.precision = vgg_precision; vgg.eval()
+        content = O.make_image(per_rank * world, size, size, seed=5, normalized=True)
+        sty = O.make_image(1, size, size, seed=6, normalized=True)
+        with torch.no_grad():
+            targets = [ll.gram_matrix(f).squeeze(0) for f in vgg(sty.to(dev))]
+        x = parallel.shard_batch(content, rank, world).to(dev)
+        dp = parallel.GradientAllReduce(net, world)
+        for it in range(2):                                           # second iteration: the CUDA-graph replay path
+            y = torch.clamp(net(x), -3, 3)
+            with torch.no_grad():
+                cf = vgg(x)
+            sf = vgg(y)
+            total = 1000.0 * ll.content_loss(sf, cf) + ll.style_loss(sf, targets) + 10 * parallel.tv_weight_scale(world) * ll.total_variation_loss(y)
+            assert parallel.all_finite(total, world)
+            net.zero_grad()
+            total.backward()
+            flat = dp.all_reduce()
+            assert flat.numel() == 6243843
+        # NaN / Inf skip: one rank with a bad loss makes EVERY rank skip (train.py:193 on a reduced flag)
+        bad = torch.tensor(float("inf") if rank == world - 1 else 1.0, device=dev)
+        assert not parallel.all_finite(bad, world)
+        assert parallel.all_finite(torch.tensor(2.0, device=dev), world)
+        if rank == 0:
+            torch.save({k: v.grad.detach().cpu() for k, v in net.named_parameters()}, os.path.join(out_dir, "dp.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("precision,vgg_precision,tol", [("fp32", "fp32", 5e-3), ("fp16", "bf16", 1.5e-1)])
+def test_two_rank_nccl_step_equals_the_global_batch_gradient(tmp_path, precision, vgg_precision, tol):
+    world, per_rank, size = 2, 2, 64
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), precision, vgg_precision, per_rank, size), nprocs=world, join=True)
+    dp = torch.load(os.path.join(tmp_path, "dp.pt"))
+    p = O.make_net_params(seed=0, random_affine=True)
+    vp = O.make_vgg_params(seed=1)
+    content = O.make_image(per_rank * world, size, size, seed=5, normalized=True)
+    targets = O.style_targets(vp, O.make_image(1, size, size, seed=6, normalized=True))
+    _, ref = O.loss_and_grads(p, vp, content, targets, None)           # ONE process, global batch: the reference semantics
+    gn = float(torch.sqrt(sum((g.double() ** 2).sum() for g in ref.values())))
+    worst = 0.0
+    for k in ref:
+        err = float((dp[k].double() - ref[k].double()).norm()) / max(float(ref[k].double().norm()), 1e-4 * gn)
+        worst = max(worst, err)
+        assert err < tol, (k, err)
+    gn_dp = float(torch.sqrt(sum((g.double() ** 2).sum() for g in dp.values())))
+    print(f"[{precision}] 2-rank NCCL gradient vs global-batch oracle: worst tensor {worst:.3e}, norm {gn_dp:.6g} vs {gn:.6g}")
+    assert abs(gn_dp / gn - 1) < min(tol, 5e-3)
