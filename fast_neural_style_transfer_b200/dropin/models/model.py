@@ -2,13 +2,19 @@
 child-module names and 58 state-dict keys (models/model.py:7-90), forward executed by libfnst
 (hand-written sm_100a kernels) instead of ATen/cuDNN.
 
-The nn.Conv2d / nn.ConvTranspose2d / nn.InstanceNorm2d children are parameter containers only
-(identical default initialisation and construction order as the reference, so the same seed gives
-the same weights); their own forward is never called.  There is no CPU or library fallback:
+The nn.Conv2d / nn.ConvTranspose2d / nn.InstanceNorm2d children hold the parameters (identical
+default initialisation and construction order as the reference, so the same seed gives the same
+weights); their own stock forwards run only while the module is being exported (torch.jit.trace /
+torch.onnx.export cannot trace ctypes calls).  There is no CPU or library fallback at run time:
 non-CUDA inputs raise.
 
-Precision: `net.precision` in {"fp16" (default; tcgen05 tensor cores), "bf16", "fp32" (CUDA
-cores, 1e-4 parity path)}, or environment variable FNST_PRECISION.
+Precision: `net.precision`, or environment variable FNST_PRECISION:
+  "auto" (default)  inference: "fp16x3"; training: "fp16"
+  "fp16"            tcgen05 tensor cores, fp16 activations (bf16 gradients in training): 2e-3 on outputs
+  "fp16x3"          tcgen05 tensor cores, error-compensated fp16 (hi, lo) pairs: 1e-5 on outputs (the
+                    reference's fp32 class); in training an fp32-class forward + bf16 backward
+  "bf16"            tcgen05 tensor cores, bf16 activations (1.5e-2 on outputs at random init)
+  "fp32"            CUDA cores end to end (4e-6)
 """
 import os
 import sys
@@ -23,11 +29,82 @@ if _PKG_PARENT not in sys.path:
 
 from fast_neural_style_transfer_b200 import engine, graphs, ops   # noqa: E402
 from fast_neural_style_transfer_b200 import autograd_fns      # noqa: E402
+from fast_neural_style_transfer_b200._lib import PAD_REFLECT    # noqa: E402
 
 
-def _standalone(name):
-    raise RuntimeError(f"{name}.forward is not a separate operator in the B200 path; call StyleTransferNet.forward "
-                       "(conv + InstanceNorm + ReLU are fused across these module boundaries)")
+def _exporting(x=None) -> bool:
+    """torch.jit.trace / torch.onnx.export in progress (model_scripting/torchscript_model.py:25, onnx_version/onnx_model.py:24):
+    ctypes calls into libfnst cannot be traced, so during an export -- and only then -- the modules evaluate themselves with the
+    stock torch operators of their own parameter-holding children (the traced graph is the reference's graph, 58 shared tensors)."""
+    if torch.jit.is_tracing() or torch.onnx.is_in_onnx_export():
+        return True
+    if x is not None and x.is_cuda:
+        return False                                        # run time: nothing below is on the hot path
+    # torch.jit.trace(check_trace=True, the default the reference script uses) re-runs the Python module once, eagerly, to
+    # compare it with the trace: that call belongs to the export too
+    f = sys._getframe(1)
+    while f is not None:
+        if f.f_code.co_name == "_check_trace" and f.f_globals.get("__name__", "").startswith("torch.jit"):
+            return True
+        f = f.f_back
+    return False
+
+
+def _need_cuda_nograd(x, params, what):
+    if not x.is_cuda:
+        raise RuntimeError(f"{what} (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+        raise RuntimeError(f"{what}.forward on its own is an inference-time operator here; gradients flow through "
+                           "StyleTransferNet.forward (whole-network autograd node).  Wrap the call in torch.no_grad().")
+
+
+def _ceil16(v: int) -> int:
+    return (v + 15) // 16 * 16
+
+
+def _reflect_halo(x_nhwc: torch.Tensor, pad: int) -> torch.Tensor:
+    """ReflectionPad2d(pad) on an NHWC tensor (index gather: data movement only)."""
+    if pad == 0:
+        return x_nhwc
+    n, h, w, c = x_nhwc.shape
+    if h <= pad or w <= pad:
+        raise RuntimeError(f"ReflectionPad2d({pad}) needs H, W > {pad}")
+    def idx(extent):
+        i = torch.arange(-pad, extent + pad, device=x_nhwc.device).abs()
+        return torch.where(i >= extent, 2 * (extent - 1) - i, i)
+    return x_nhwc.index_select(1, idx(h)).index_select(2, idx(w)).contiguous()
+
+
+def _conv_nhwc(xp: torch.Tensor, weight: torch.Tensor, bias, stride: int, stats=None) -> torch.Tensor:
+    """'valid' Conv2d of an already padded fp32 NHWC tensor (channels padded to a multiple of 16) as a libfnst gather-GEMM on
+    the fp32 path: stride 1 directly, stride 2 through the space-to-depth view (tap (kh,kw) -> spatial offset (kh>>1, kw>>1)
+    of phase (kh&1, kw&1))."""
+    o, c, k, _ = weight.shape
+    n, hp, wp, cp = xp.shape
+    ng = _ceil16(o)
+    wk = torch.zeros((ng, k, k, cp), dtype=torch.float32, device=xp.device)
+    wk[:o, :, :, :c] = weight.detach().float().permute(0, 2, 3, 1)
+    b = None
+    if bias is not None:
+        b = torch.zeros(ng, dtype=torch.float32, device=xp.device)
+        b[:o] = bias.detach().float()
+    ho, wo = (hp - k) // stride + 1, (wp - k) // stride + 1
+    out = torch.empty((n, ho, wo, o), dtype=torch.float32, device=xp.device)
+    if stride == 1:
+        taps = engine.taps_kxk(k)
+        a, a_dims = xp, (n, hp, wp, cp)
+    elif stride == 2:
+        he, we = (hp + 1) // 2 * 2, (wp + 1) // 2 * 2
+        xe = torch.zeros((n, he, we, cp), dtype=torch.float32, device=xp.device)
+        xe[:, :hp, :wp] = xp
+        a = xe.view(n, he // 2, 2, we // 2, 2, cp).permute(0, 1, 3, 2, 4, 5).reshape(n, he // 2, we // 2, 4 * cp).contiguous()
+        a_dims = tuple(a.shape)
+        taps = [(kh >> 1, kw >> 1, ((kh & 1) * 2 + (kw & 1)) * cp) for kh in range(k) for kw in range(k)]
+    else:
+        raise RuntimeError("ConvLayer (B200 drop-in): stride must be 1 or 2")
+    spec = ops.ConvSpec(taps, cp, wk.reshape(ng, k * k * cp).contiguous(), ng, o, bias=b)
+    ops.conv_gather(spec, a, a_dims, engine._nhwc_strides(a), out, (ho, wo), stats, False)
+    return out
 
 
 class UpsampleConv(nn.Module):
@@ -38,7 +115,25 @@ class UpsampleConv(nn.Module):
                                                 output_padding=scale - 1)
 
     def forward(self, x):
-        _standalone("UpsampleConv")
+        """ConvTranspose2d(k=3, s=2, p=1, op=1) (models/model.py:21-22) as the sub-pixel 2x2-tap gather-GEMM with the
+        depth-to-space epilogue -- the same operator the fused network forward uses, on the fp32 path, unfused."""
+        if _exporting(x):
+            return self.upsample_conv(x)
+        ct = self.upsample_conv
+        _need_cuda_nograd(x, list(self.parameters()), "UpsampleConv")
+        if ct.kernel_size != (3, 3) or self.scale != 2:
+            raise RuntimeError("UpsampleConv (B200 drop-in): only the reference's kernel=3, scale=2 configuration is implemented")
+        cin, cout = ct.weight.shape[0], ct.weight.shape[1]
+        if cin % 16 or cout % 4:
+            raise RuntimeError("UpsampleConv (B200 drop-in): needs in_ch % 16 == 0 and out_ch % 4 == 0")
+        n, _, h, w = x.shape
+        a = ops.nchw_to_nhwc(x.detach().float().contiguous(), torch.float32)
+        bias4 = ct.bias.detach().float().repeat(4).contiguous() if ct.bias is not None else None
+        spec = ops.ConvSpec(engine.TAPS_2X2, cin, engine.pack_conv_transpose(ct.weight.detach().float(), torch.float32), 4 * cout, cout,
+                            epilogue=engine.EPI_D2S, bias=bias4)
+        out = torch.empty((n, 2 * h, 2 * w, cout), dtype=torch.float32, device=x.device)
+        ops.conv_gather(spec, a, (n, h, w, cin), engine._nhwc_strides(a), out, (h, w), None, False)
+        return ops.nhwc_to_nchw(out)
 
 
 class ConvLayer(nn.Module):
@@ -48,7 +143,17 @@ class ConvLayer(nn.Module):
         self.conv = nn.Conv2d(in_ch, out_ch, kernel_size=kernel, stride=stride)
 
     def forward(self, x):
-        _standalone("ConvLayer")
+        """conv(reflection_pad(x)) (models/model.py:74-75) as one libfnst gather-GEMM on the fp32 path, unfused."""
+        if _exporting(x):
+            return self.conv(self.reflection_pad(x))
+        _need_cuda_nograd(x, list(self.parameters()), "ConvLayer")
+        conv = self.conv
+        k, stride = conv.kernel_size[0], conv.stride[0]
+        if k * k > 81 or conv.kernel_size[0] != conv.kernel_size[1]:
+            raise RuntimeError("ConvLayer (B200 drop-in): square kernels up to 9x9")
+        a = ops.nchw_to_nhwc(x.detach().float().contiguous(), torch.float32, c_pad=_ceil16(x.shape[1]))
+        out = _conv_nhwc(_reflect_halo(a, k // 2), conv.weight, conv.bias, stride)
+        return ops.nhwc_to_nchw(out)
 
 
 class ResidualBlock(nn.Module):
@@ -61,7 +166,33 @@ class ResidualBlock(nn.Module):
         self.dropout = nn.Dropout2d(0.1)
 
     def forward(self, x):
-        _standalone("ResidualBlock")
+        """x + in2(conv2(dropout(relu(in1(conv1(x)))))) (models/model.py:86-90) on the libfnst operators of the fused forward
+        (gather-GEMM with InstanceNorm statistics in its epilogue, inorm_apply writing the next reflect-halo buffer), fp32 path."""
+        if _exporting(x):
+            y = F.relu(self.in1(self.conv1(x)))
+            y = self.dropout(y)
+            return x + self.in2(self.conv2(y))
+        _need_cuda_nograd(x, list(self.parameters()), "ResidualBlock")
+        n, c, h, w = x.shape
+        if c % 16 or 256 % (c // 8) or h < 2 or w < 2:
+            raise RuntimeError("ResidualBlock (B200 drop-in): channel count must be 16, 32, 64, 128, 256, ... (a divisor pattern of the norm kernel)")
+        f32 = torch.float32
+        xp = _reflect_halo(ops.nchw_to_nhwc(x.detach().float().contiguous(), f32), 1)
+        affine = lambda m: (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
+        st = torch.zeros((n, c, 2), dtype=f32, device=x.device)
+        raw = _conv_nhwc(xp, self.conv1.conv.weight, None, 1, stats=st)            # the conv bias is cancelled by the InstanceNorm mean
+        drop = None
+        if self.training:
+            drop = torch.empty((n, c, 1, 1), dtype=f32, device=x.device).bernoulli_(1.0 - self.dropout.p).div_(1.0 - self.dropout.p).view(n, c)
+        mid = torch.empty((n, h + 2, w + 2, c), dtype=f32, device=x.device)
+        g, b = affine(self.in1)
+        ops.inorm_apply(raw, st, g, b, mid, relu=True, pad=1, pad_mode=PAD_REFLECT, drop=drop)
+        st2 = torch.zeros((n, c, 2), dtype=f32, device=x.device)
+        raw2 = _conv_nhwc(mid, self.conv2.conv.weight, None, 1, stats=st2)
+        out = torch.empty((n, h, w, c), dtype=f32, device=x.device)
+        g, b = affine(self.in2)
+        ops.inorm_apply(raw2, st2, g, b, out, relu=False, res=xp, res_pad=1)
+        return ops.nhwc_to_nchw(out)
 
 
 class StyleTransferNet(nn.Module):
@@ -77,7 +208,7 @@ class StyleTransferNet(nn.Module):
         self.up2 = UpsampleConv(64, 32, kernel=3, scale=2)
         self.norm4 = nn.InstanceNorm2d(32, affine=True)
         self.final_conv = ConvLayer(32, 3, kernel=9, stride=1)
-        self.precision = os.environ.get("FNST_PRECISION", "fp16")
+        self.precision = os.environ.get("FNST_PRECISION", "auto")
 
     # plan cache (packed weights) is derived state: never pickled, rebuilt when parameters change
     def __getstate__(self):
@@ -86,12 +217,21 @@ class StyleTransferNet(nn.Module):
             state.pop(k, None)
         return state
 
-    def _plan(self) -> "engine.StyleNetPlan":
+    def _resolved_precision(self, need_grad: bool) -> str:
+        """"auto" (default): inference in the reference's own fp32 class (fp16x3: error-compensated fp16 pairs on tensor cores,
+        1e-5 relative L2), training on the fast tensor-core path (fp16 forward / bf16 backward: the class of PyTorch's default
+        TF32 convolutions, which is what the reference itself trains in on a GPU)."""
+        if self.precision != "auto":
+            return self.precision
+        return "fp16" if need_grad else "fp16x3"
+
+    def _plan(self, need_grad: bool = False) -> "engine.StyleNetPlan":
         params = dict(self.named_parameters())
-        key = (self.precision, tuple((p.data_ptr(), p._version) for p in params.values()))
+        precision = self._resolved_precision(need_grad)
+        key = (precision, tuple((p.data_ptr(), p._version) for p in params.values()))
         cache = self.__dict__.get("_plan_cache")
         if cache is None or cache[0] != key:
-            cache = (key, engine.StyleNetPlan(self.precision).pack(params))
+            cache = (key, engine.StyleNetPlan(precision).pack(params))
             self.__dict__["_plan_cache"] = cache
         return cache[1]
 
@@ -157,7 +297,25 @@ class StyleTransferNet(nn.Module):
         y = self.forward(x)
         return ops.nchw_to_u8(y.contiguous(), self.IMAGENET_MEAN, self.IMAGENET_STD)
 
+    def to_reference_module(self) -> "StyleTransferNet":
+        """The module itself: its children are stock nn.Conv2d / ConvTranspose2d / InstanceNorm2d / ReflectionPad2d objects
+        holding the 58 tensors, and under torch.jit.trace / torch.onnx.export every forward in this file evaluates through
+        them (see _exporting) -- so the reference's export scripts work on the drop-in unchanged."""
+        return self
+
+    def _stock_forward(self, x):
+        # models/model.py:49-65 on the children's own stock forwards (export only)
+        h = F.relu(self.norm1(self.conv1(x)))
+        h = F.relu(self.norm2(self.conv2(h)))
+        for blk in self.res_blocks:
+            h = blk(h)
+        h = F.relu(self.norm3(self.up1(h)))
+        h = F.relu(self.norm4(self.up2(h)))
+        return self.final_conv(h)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if _exporting(x):
+            return self._stock_forward(x)
         if not x.is_cuda:
             raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
         params = list(self.parameters())
@@ -167,7 +325,8 @@ class StyleTransferNet(nn.Module):
                 cache = self.__dict__.setdefault("_train_graphs", {})
                 # (every parameter address is part of the key: the captured graphs read the weights in place, so a parameter
                 #  whose storage was replaced -- `.to()`, `p.data = ...` -- must not hit a stale capture)
-                key = (self.precision, tuple(x.shape), x.device.index, self.training, tuple(p.data_ptr() for p in params))
+                precision = self._resolved_precision(True)
+                key = (precision, tuple(x.shape), x.device.index, self.training, tuple(p.data_ptr() for p in params))
                 state = cache.get(key)
                 busy = state is not None and state.in_flight.busy()
                 # the Dropout2d scales are drawn straight into the captured graph's input buffer (unless that graph is in flight)
@@ -175,7 +334,7 @@ class StyleTransferNet(nn.Module):
                 if state is None:
                     if len(cache) >= 4:
                         cache.clear()
-                    state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(self.named_parameters()), self.precision, x, drops)
+                    state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(self.named_parameters()), precision, x, drops)
                 if not busy:
                     return autograd_fns.stylenet_graphed_apply(state, x, drops, params)
                 # an earlier forward of this graph still waits for its backward (gradient accumulation, two losses on two
@@ -183,7 +342,7 @@ class StyleTransferNet(nn.Module):
             else:
                 drops = self._dropout_scales(x)
             names = [n for n, _ in self.named_parameters()]
-            return autograd_fns.stylenet_apply(self._plan(), names, x, drops, params)
+            return autograd_fns.stylenet_apply(self._plan(need_grad=True), names, x, drops, params)
         plan = self._plan()
         use_graph = (not self.training and os.environ.get("FNST_CUDA_GRAPH", "1") != "0"
                      and x.shape[0] * x.shape[2] * x.shape[3] <= self.GRAPH_MAX_PIXELS

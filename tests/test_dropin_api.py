@@ -140,3 +140,29 @@ def test_same_seed_gives_the_reference_weights(dropin):
     assert list(ref) == list(got) and len(ref) == 58
     for k in ref:
         assert torch.equal(ref[k], got[k]), k
+
+
+def test_export_switch_traces_the_reference_graph(dropin, tmp_path):
+    """model_scripting/torchscript_model.py:25 (`torch.jit.trace(net, torch.rand(1,3,256,256), strict=False)`) on the drop-in:
+    ctypes calls cannot be traced, so while an export runs the modules evaluate through their own stock children -- the traced
+    module computes the reference function (here: equal to the oracle on CPU) and loads without the package."""
+    mm, _, _ = dropin
+    torch.manual_seed(3)
+    net = mm.StyleTransferNet().eval()
+    x = torch.rand(1, 3, 64, 64)
+    traced = torch.jit.trace(net, x, strict=False)
+    path = tmp_path / "model_traced.pt"
+    traced.save(str(path))
+    again = torch.jit.load(str(path), map_location="cpu")
+    x2 = torch.rand(1, 3, 64, 64)
+    with torch.no_grad():
+        ref = O.stylenet_forward({k: v.detach() for k, v in net.state_dict().items()}, x2)
+        got = again(x2)
+    assert float((got - ref).norm() / ref.norm()) < 1e-5
+    assert net.to_reference_module() is net
+    # outside an export the same call refuses CPU tensors (no CPU fallback at run time)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(x)
+    for sub in (net.conv1, net.res_blocks[0], net.up1):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            sub(torch.rand(1, sub.conv.in_channels if hasattr(sub, "conv") else 256, 16, 16))
