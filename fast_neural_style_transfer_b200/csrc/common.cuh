@@ -76,6 +76,7 @@ struct Tuning {
   int wgrad_waves_x2 = 2;      // wgrad_tc split-K target: tasks <= waves_x2/2 * SM count (one wave measured best: fewer L2 atomics)
   int wgrad_bn = 0;            // 0 = widest column block that divides kc; else force 64/128/256
   int pdl = 1;
+  int conv_stage_out = 1;      // conv_tc epilogue: 1 = shared-memory tile + TMA store + per-column statistics where applicable, 0 = never
   int conv_pair = 1;           // 1: CTA pairs (cta_group::2) where measured faster; 0: never; 2: whenever the column tile is >= 128
   int inorm_bwd_blocks = 2;    // resident blocks per SM the InstanceNorm-backward reduce kernel is compiled for (16-bit types): 1 or 2
   int resize_staged = 0;       // fnst_resize_to_tensor: 1 = stage the tile's input span in shared memory with 32-bit loads

@@ -70,6 +70,7 @@ struct ConvTcParams {
   int32_t num_kblocks, chunks_per_tap;
   int32_t h0, w0;
   int32_t epilogue, c_out, n_gemm, relu, out_is_bf16, out_is_f32, b_image_rows;
+  int32_t stage_out;             // 1: epilogue stages the tile in shared memory (swizzled) and stores it with TMA (one tile per CTA)
   uint32_t idesc;
   int32_t out_dtype, mask_dtype;
   void* out;
@@ -120,7 +121,7 @@ __device__ __forceinline__ void store_chunk(TOut* p, const float (&v)[32], int c
 template <int BLOCK_N, bool PAIR>
 __global__ void __launch_bounds__((TcCfg<BLOCK_N, PAIR>::THREADS), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ ConvTcParams p) {
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N, PAIR>;
   static_assert(!PAIR || BLOCK_N >= 64, "CTA pairs need at least 32 weight rows per CTA");
   constexpr int STAGES = Cfg::STAGES;
@@ -284,6 +285,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N);
 
+      if (BLOCK_N >= 64 && p.stage_out) {
+        // ---- staged epilogue (one tile per CTA: the operand ring is idle once the accumulator is complete) ----------------
+        // TMEM -> registers -> 16-bit tile in shared memory, [BLOCK_N/64 column blocks][128 pixel rows][128 B] in the 128-byte
+        // swizzle TMA expects -> (a) InstanceNorm column sums with ONE THREAD PER COLUMN walking the 128 staged rows (no
+        // transposition, no shuffles; statistics of exactly the values that are stored), (b) TMA tile stores (full 128-byte
+        // lines, ragged edges clipped by the tensor map) instead of 16-byte stores at a 512-byte stride per lane.
+        uint8_t* stage = smem;
+#pragma unroll 1
+        for (int cb = col_begin; cb < col_end; cb += 32) {
+          uint32_t raw[32];
+          tmem_ld_x32(t_row + cb, raw);
+          tmem_ld_wait();
+          const int col0 = n_tile * BLOCK_N + cb;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) : 0.f;      // rows outside the image: zeros (statistics)
+          if (p.bias && valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += p.bias[col0 + i];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          uint8_t* rowp = stage + (cb >> 6) * (TC_BLOCK_M * 128) + r * 128;
+          const int j0 = (cb & 63) >> 3;                       // first 16-byte chunk of these 32 columns inside the 128-byte row
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            if (p.out_is_bf16) {
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[8 * k + 2 * e], v[8 * k + 2 * e + 1]);
+            } else {
+              __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[8 * k + 2 * e], v[8 * k + 2 * e + 1]);
+            }
+            *reinterpret_cast<uint4*>(rowp + (((j0 + k) ^ (r & 7)) << 4)) = u;
+          }
+        }
+        // generic-proxy writes -> visible to the async proxy (TMA), then all epilogue warps meet
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (et == 0 && tile_live) {
+#pragma unroll 1
+          for (int b = 0; b < BLOCK_N / 64; ++b) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&map_out)), "r"(smem_u32(stage + b * (TC_BLOCK_M * 128))),
+                           "r"(n_tile * BLOCK_N + b * 64), "r"(tw * TW), "r"(th * p.h_step), "r"(n) : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.stats && tile_live) {
+          for (int c = et; c < BLOCK_N; c += EPI_THREADS) {
+            const uint8_t* colp = stage + (c >> 6) * (TC_BLOCK_M * 128) + ((c & 7) << 1);
+            const int j = (c & 63) >> 3;
+            float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int rr = 0; rr < TC_BLOCK_M; ++rr) {
+              const unsigned short bits = *reinterpret_cast<const unsigned short*>(colp + rr * 128 + ((j ^ (rr & 7)) << 4));
+              const float x = p.out_is_bf16 ? __uint_as_float((uint32_t)bits << 16) : __half2float(__ushort_as_half(bits));
+              s1[rr & 3] += x;
+              s2[rr & 3] = fmaf(x, x, s2[rr & 3]);
+            }
+            const int col = n_tile * BLOCK_N + c;
+            atomicAdd(&p.stats[((size_t)n * p.c_out + col) * 2 + 0], (s1[0] + s1[1]) + (s1[2] + s1[3]));
+            atomicAdd(&p.stats[((size_t)n * p.c_out + col) * 2 + 1], (s2[0] + s2[1]) + (s2[2] + s2[3]));
+          }
+        }
+        if (et == 0 && tile_live) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // accumulator fully read long ago: hand the TMEM stage back (keeps the barrier protocol of the generic path)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]); }
+        continue;
+      }
+
 #pragma unroll 1
       for (int cb = col_begin; cb < col_end; cb += CHUNK) {
         uint32_t raw[32];
@@ -427,7 +506,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 int validate_conv_desc(const fnst_conv_desc* d);
 
 template <int BLOCK_N, bool PAIR>
-static int launch_conv_tc(const CUtensorMap& ma, const CUtensorMap& mb, const ConvTcParams& p, int num_sms, cudaStream_t st) {
+static int launch_conv_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const ConvTcParams& p, int num_sms,
+                          cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, PAIR>;
   auto kern = conv_tc_kernel<BLOCK_N, PAIR>;
   FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -435,11 +515,11 @@ static int launch_conv_tc(const CUtensorMap& ma, const CUtensorMap& mb, const Co
     // persistent CTA pairs: one cluster of 2 per TPC; a unit = two adjacent pixel tiles x one column tile
     const int units = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     const int pairs = units < num_sms / 2 ? units : num_sms / 2;
-    launch_pdl_cluster(kern, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 2, ma, mb, p);
+    launch_pdl_cluster(kern, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, 2, ma, mb, mo, p);
     return launch_status("conv_tc (CTA pair)");
   }
   const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, ma, mb, p);
+  launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, ma, mb, mo, p);
   return launch_status("conv_tc");
 }
 
@@ -547,13 +627,26 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
     const uint32_t box[2] = {TC_BLOCK_K, (uint32_t)(pair ? block_n / 2 : block_n)};     // a pair's CTAs load half the rows each
     if (int r = encode_tensor_map_2b(&mb, d->b, 2, dims, str, box)) return r;
   }
+  // Staged epilogue (shared-memory tile + TMA store + per-column statistics): plain NHWC 16-bit outputs of full 64-column
+  // blocks, one tile per CTA (the operand ring doubles as the staging buffer, so no next tile may be loading into it).
+  CUtensorMap mo;
+  memset(&mo, 0, sizeof(mo));
+  p.stage_out = 0;
+  if (tuning().conv_stage_out && d->epilogue == FNST_EPI_NHWC && !p.out_is_f32 && block_n >= 64 && d->c_out == d->n_gemm &&
+      d->n_gemm % 64 == 0 && !p.addend && !p.mask && !pair && p.num_tiles <= num_sms && !p.dbg_mode) {
+    const uint64_t dims[4] = {(uint64_t)d->c_out, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->out_n};
+    const uint64_t str[3] = {(uint64_t)d->c_out * 2, (uint64_t)d->c_out * 2 * d->out_w, (uint64_t)d->c_out * 2 * d->out_w * d->out_h};
+    const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    if (int r = encode_tensor_map_2b(&mo, d->out, 4, dims, str, box)) return r;
+    p.stage_out = 1;
+  }
   if (d->stats && !(d->flags & FNST_DESC_PREZEROED))
     FNST_CUDA(cudaMemsetAsync(d->stats, 0, sizeof(float) * 2 * (size_t)d->out_n * d->c_out, st));
   switch (block_n) {
-    case 16: return launch_conv_tc<16, false>(ma, mb, p, num_sms, st);
-    case 32: return launch_conv_tc<32, false>(ma, mb, p, num_sms, st);
-    case 64: return launch_conv_tc<64, false>(ma, mb, p, num_sms, st);
-    case 128: return pair ? launch_conv_tc<128, true>(ma, mb, p, num_sms, st) : launch_conv_tc<128, false>(ma, mb, p, num_sms, st);
-    default: return pair ? launch_conv_tc<256, true>(ma, mb, p, num_sms, st) : launch_conv_tc<256, false>(ma, mb, p, num_sms, st);
+    case 16: return launch_conv_tc<16, false>(ma, mb, mo, p, num_sms, st);
+    case 32: return launch_conv_tc<32, false>(ma, mb, mo, p, num_sms, st);
+    case 64: return launch_conv_tc<64, false>(ma, mb, mo, p, num_sms, st);
+    case 128: return pair ? launch_conv_tc<128, true>(ma, mb, mo, p, num_sms, st) : launch_conv_tc<128, false>(ma, mb, mo, p, num_sms, st);
+    default: return pair ? launch_conv_tc<256, true>(ma, mb, mo, p, num_sms, st) : launch_conv_tc<256, false>(ma, mb, mo, p, num_sms, st);
   }
 }

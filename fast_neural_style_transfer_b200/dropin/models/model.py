@@ -313,11 +313,65 @@ class StyleTransferNet(nn.Module):
         h = F.relu(self.norm4(self.up2(h)))
         return self.final_conv(h)
 
+    HOST_CHUNK_PIXELS = 32 * 256 * 256          # images per pipeline chunk = this many pixels (32 images at 256x256, 1 at 1080p)
+
+    @torch.no_grad()
+    def _forward_pinned_host(self, x_host: torch.Tensor) -> torch.Tensor:
+        """Extension beyond the reference API (where a CPU input to a CUDA module is an error): a PINNED host batch is stylised
+        on the module's GPU as a three-stage pipeline -- host->device copy of chunk i+1 (copy stream), network forward of chunk
+        i (current stream), device->host copy of chunk i-1 (second copy stream) -- and comes back as a pinned host tensor.
+        The PCIe transfers of a large batch (2 x 100 MB for 256 images) then hide under the forward instead of bracketing it."""
+        dev = next(self.parameters()).device
+        B, _, H, W = x_host.shape
+        per = max(1, min(B, self.HOST_CHUNK_PIXELS // (H * W)))
+        if per >= B:                             # one chunk: nothing to overlap -- the ordinary (CUDA-graph) forward between two copies
+            y = self.forward(x_host.to(dev, non_blocking=True))
+            out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+            out.copy_(y, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return out
+        plan = self._plan()
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = (self.__dict__.get("_host_streams") or (None, None))
+        if s_in is None or s_in.device != dev:
+            s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            self.__dict__["_host_streams"] = (s_in, s_out)
+        x32 = x_host if x_host.dtype == torch.float32 else x_host.float().pin_memory()
+        xd = [torch.empty((per, 3, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+        free = [None, None]                      # event: the forward that read xd[j] has finished
+        out_host, keep = None, []
+        s_in.wait_stream(cur)
+        bounds = [(lo, min(B, lo + per)) for lo in range(0, B, per)]
+        for i, (lo, hi) in enumerate(bounds):
+            j = i & 1
+            with torch.cuda.stream(s_in):
+                if free[j] is not None:
+                    s_in.wait_event(free[j])
+                xd[j][:hi - lo].copy_(x32[lo:hi], non_blocking=True)
+                ready = torch.cuda.Event(); ready.record(s_in)
+            cur.wait_event(ready)
+            y = plan.forward(xd[j][:hi - lo])
+            done = torch.cuda.Event(); done.record(cur)
+            free[j] = done
+            if out_host is None:
+                out_host = torch.empty((B,) + tuple(y.shape[1:]), dtype=y.dtype, pin_memory=True)      # cached pinned block
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                out_host[lo:hi].copy_(y, non_blocking=True)
+            keep.append(y)                        # keep device outputs alive until their copies have drained
+        s_out.synchronize()                       # the caller receives a host tensor: its bytes must have landed
+        cur.wait_stream(s_in)
+        return out_host
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if _exporting(x):
             return self._stock_forward(x)
         if not x.is_cuda:
-            raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
+            if x.is_pinned() and x.dim() == 4 and x.shape[1] == 3 and not (torch.is_grad_enabled() and self.training) \
+                    and next(self.parameters()).is_cuda:
+                return self._forward_pinned_host(x)
+            raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback "
+                               "(pinned host batches are accepted for inference and are pipelined through the GPU)")
         params = list(self.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             if graphs.enabled() and not torch.cuda.is_current_stream_capturing():

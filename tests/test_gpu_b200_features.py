@@ -51,14 +51,16 @@ def _conv(B, hw, cin, cout, block_n, pair, epilogue=0, taps=None, n_gemm=None, d
 ])
 def test_cta_pair_matches_single_cta(cfg, restore_knobs):
     """cta_group::2 (two SMs, M = 256) and cta_group::1 run the same K order per output element: outputs agree bit for bit;
-    the InstanceNorm statistics differ only by the order of their fp32 atomics."""
+    the InstanceNorm statistics differ by the order of their fp32 atomics and -- where the single-CTA launch takes the staged
+    epilogue -- by being taken from the stored 16-bit values instead of the fp32 accumulators."""
     cfg = dict(cfg)
     if cfg.get("epilogue") == 1:
         cfg["taps"] = engine.TAPS_2X2
     o0, s0 = _conv(pair=0, **cfg)
     o1, s1 = _conv(pair=2, **cfg)
     assert torch.equal(o0, o1)
-    assert float(((s0 - s1).abs() / (s0.abs() + 1)).max()) < 1e-4
+    assert float(((s0[..., 1] - s1[..., 1]).abs() / (s0[..., 1].abs() + 1)).max()) < (3e-3 if cfg.get("dt") == torch.bfloat16 else 2e-4)
+    assert float((s0[..., 0] - s1[..., 0]).abs().max()) < 2e-3 * float(s0[..., 1].max()) ** 0.5
 
 
 @pytest.mark.parametrize("shape", [(1, 256, 256), (3, 100, 131), (5, 17, 9), (1, 270, 480)])

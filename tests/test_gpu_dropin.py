@@ -140,3 +140,26 @@ def test_stylize_uint8_matches_reference_postprocessing(dropin):
     # values within fp32 noise of an integer boundary may land on either side; a rounding implementation would be off by
     # one on about half of the pixels
     assert float(diff.max()) <= 1.0 and float((diff > 0).float().mean()) < 0.01
+
+
+def test_pinned_host_batch_is_pipelined_and_equal_to_the_device_path(dropin):
+    """net(pinned host batch) (extension: a CPU input is an error in the reference): chunked H2D / forward / D2H on three
+    streams; the result must be the device path's result, for a batch that spans several chunks with a ragged last one."""
+    mm, _, _ = dropin
+    p = O.make_net_params(seed=0)
+    net = mm.StyleTransferNet().to(DEV); net.load_state_dict(p); net.precision = "fp16"; net.eval()
+    net.HOST_CHUNK_PIXELS = 3 * 64 * 64                                   # 3 images per chunk -> chunks of 3, 3, 1
+    x = O.make_image(7, 64, 64, seed=21)
+    with torch.no_grad():
+        want = net(x.to(DEV)).cpu()
+        got = net(x.pin_memory())
+        one = net(x[:2].pin_memory())                                      # single chunk
+    assert not got.is_cuda and got.is_pinned() and got.shape == want.shape
+    # (not bit-equal: the InstanceNorm statistics of a tile-parallel launch are accumulated in a batch-dependent order, and
+    #  from the stored fp16 values or the fp32 accumulators depending on the launch shape -- both inside the fp16 path's 2e-3 class)
+    assert rel_l2(got, want) < 5e-3 and rel_l2(one, want[:2]) < 5e-3
+    with torch.no_grad():
+        ref = O.stylenet_forward(p, x)
+    assert rel_l2(got, ref) < 1e-2 and rel_l2(want, ref) < 1e-2
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(x)                                                             # pageable host memory is still refused

@@ -143,9 +143,16 @@ def test_conv_tc(name, dtype):
     assert not torch.isnan(got.float()).any()
     tol = 2e-5 if got.dtype == torch.float32 else (1e-3 if dtype == torch.float16 else 6e-3)   # output rounding
     assert rel_l2(got, ref) < tol
-    if with_stats:   # statistics are taken from the fp32 accumulators, before output rounding
-        assert rel_l2(st[:, :, 1], st_ref[:, :, 1]) < 1e-4
-        assert float((st[:, :, 0].cpu() - st_ref[:, :, 0]).abs().max()) < 2e-3 * float(st_ref[:, :, 1].max()) ** 0.5
+    if with_stats:
+        # statistics are those of the fp32 accumulators (generic epilogue) or of exactly the stored, rounded values (staged
+        # shared-memory epilogue of one-tile-per-CTA launches): either is a valid InstanceNorm statistic of its tensor
+        g64 = got.double().cpu()
+        st_got = torch.stack([g64.sum(dim=(1, 2)), (g64 ** 2).sum(dim=(1, 2))], dim=-1)
+        exact = rel_l2(st[:, :, 1], st_ref[:, :, 1]) < 1e-4 and \
+            float((st[:, :, 0].cpu() - st_ref[:, :, 0]).abs().max()) < 2e-3 * float(st_ref[:, :, 1].max()) ** 0.5
+        stored = rel_l2(st[:, :, 1], st_got[:, :, 1]) < 2e-5 and \
+            float((st[:, :, 0].cpu().double() - st_got[:, :, 0]).abs().max()) < 1e-4 * float(st_got[:, :, 1].max()) ** 0.5
+        assert exact or stored
 
 
 def test_conv_tc_fp32_out():
