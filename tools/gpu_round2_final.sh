@@ -24,9 +24,12 @@ export FNST_BENCH_NO_ROOFLINE=1
 CMD="python bench.py --workload train --steps 3 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/r02_plain_train.log 2>&1 && {
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 800 --csv --log-file gpurun_out/r02_launches_train.csv $CMD > gpurun_out/r02_ncu_list.log 2>&1; echo "ncu list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel<256|inorm_apply_kernel|wgrad_tc_kernel<256|inorm_bwd_reduce" -s 40 -c 8 -f -o gpurun_out/r02_prof_train_kernels $CMD > gpurun_out/r02_ncu_full.log 2>&1; echo "ncu full rc=$?"
+for K in conv_tc_kernel wgrad_tc_kernel "inorm_apply_kernel|inorm_bwd_reduce_kernel|inorm_bwd_apply_kernel"; do
+  N=$(echo $K | cut -d'|' -f1)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K" -s 24 -c 5 -f -o gpurun_out/r02_prof_$N $CMD > gpurun_out/r02_ncu_full_$N.log 2>&1; echo "ncu full $N rc=$?"
+done
 }
 python tools/summarize_launches.py gpurun_out/r02_launches_train.csv "Round 2: launches 1800..2600 of FNST_BENCH_NO_ROOFLINE=1 bench.py --workload train --steps 3 --warmup 3" > gpurun_out/r02_train_launches.md 2>/dev/null
-[ -f gpurun_out/r02_prof_train_kernels.ncu-rep ] && python tools/ncu_summary.py gpurun_out/r02_prof_train_kernels.ncu-rep > gpurun_out/r02_ncu_train_kernels.json 2> gpurun_out/r02_ncu_summary.err
+python tools/ncu_summary.py gpurun_out/r02_prof_*.ncu-rep > gpurun_out/r02_ncu_train_kernels.json 2> gpurun_out/r02_ncu_summary.err
 find gpurun_out -name '*.ncu-rep' -size +20M -delete
 du -sh gpurun_out | tail -1
