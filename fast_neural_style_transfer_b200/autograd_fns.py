@@ -332,15 +332,27 @@ class VGGGraph:
         self.in_flight = _InFlight()
 
         def fwd(x_):
+            # the five feature maps live in ONE flat static buffer, so handing them to the caller is one device copy, not five
             self.tape.clear()
-            feats = plan.forward(x_, self.tape if with_tape else None)
-            return _grad_interface(feats) if with_tape else tuple(feats)
+            B, _, H, W = x_.shape
+            self.shapes = plan.feature_shapes(B, H, W)
+            self.numels = [s[0] * s[1] * s[2] * s[3] for s in self.shapes]
+            iface = torch.bfloat16 if (with_tape and plan.dtype == torch.float16) else plan.dtype       # see _grad_interface
+            flat = torch.empty(sum(self.numels), dtype=iface, device=x_.device)
+            views = [v.view(s) for v, s in zip(torch.split(flat, self.numels), self.shapes)]
+            if iface == plan.dtype:
+                plan.forward(x_, self.tape if with_tape else None, out_buffers=dict(zip(plan.FEATURE_LAYERS, views)))
+            else:
+                for f, v in zip(plan.forward(x_, self.tape), views):
+                    ops.cast(f, iface, out=v)
+            return flat
 
         self.fwd = graphs.GraphedPlan(fwd, [x.float().contiguous()])
         self.bwd = {}
 
     def forward(self, x):
-        return tuple(f.clone() for f in self.fwd(x))
+        flat = self.fwd(x).clone()
+        return tuple(v.view(s) for v, s in zip(torch.split(flat, self.numels), self.shapes))
 
     def backward(self, dfeats):
         from . import backward, graphs

@@ -213,9 +213,27 @@ class StyleTransferNet(nn.Module):
     # plan cache (packed weights) is derived state: never pickled, rebuilt when parameters change
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ("_plan_cache", "_graphs", "_train_graphs"):
+        for k in ("_plan_cache", "_graphs", "_train_graphs", "_named_cache", "_host_streams"):
             state.pop(k, None)
         return state
+
+    def _named(self):
+        """dict(self.named_parameters()), cached: the module-tree walk costs ~0.1 ms per call and the forward needs it several
+        times per step.  Parameter OBJECTS are stable under .to() / load_state_dict() (nn.Module swaps `.data`); anything
+        that replaces them (register_parameter, parametrizations) changes `_parameters` of some child, which the cheap check
+        below -- object identity of every cached parameter in its owner's dict -- catches."""
+        cache = self.__dict__.get("_named_cache")
+        if cache is not None:
+            owners, named = cache
+            if all(owner.get(attr) is p for owner, attr, p in owners):
+                return named
+        named = dict(self.named_parameters())
+        owners = []
+        for name, p in named.items():
+            mod_path, _, attr = name.rpartition(".")
+            owners.append((self.get_submodule(mod_path)._parameters, attr, p))
+        self.__dict__["_named_cache"] = (owners, named)
+        return named
 
     def _resolved_precision(self, need_grad: bool) -> str:
         """"auto" (default): inference in the reference's own fp32 class (fp16x3: error-compensated fp16 pairs on tensor cores,
@@ -226,7 +244,7 @@ class StyleTransferNet(nn.Module):
         return "fp16" if need_grad else "fp16x3"
 
     def _plan(self, need_grad: bool = False) -> "engine.StyleNetPlan":
-        params = dict(self.named_parameters())
+        params = self._named()
         precision = self._resolved_precision(need_grad)
         key = (precision, tuple((p.data_ptr(), p._version) for p in params.values()))
         cache = self.__dict__.get("_plan_cache")
@@ -321,7 +339,7 @@ class StyleTransferNet(nn.Module):
         on the module's GPU as a three-stage pipeline -- host->device copy of chunk i+1 (copy stream), network forward of chunk
         i (current stream), device->host copy of chunk i-1 (second copy stream) -- and comes back as a pinned host tensor.
         The PCIe transfers of a large batch (2 x 100 MB for 256 images) then hide under the forward instead of bracketing it."""
-        dev = next(self.parameters()).device
+        dev = self.conv1.conv.weight.device
         B, _, H, W = x_host.shape
         per = max(1, min(B, self.HOST_CHUNK_PIXELS // (H * W)))
         if per >= B:                             # one chunk: nothing to overlap -- the ordinary (CUDA-graph) forward between two copies
@@ -368,11 +386,12 @@ class StyleTransferNet(nn.Module):
             return self._stock_forward(x)
         if not x.is_cuda:
             if x.is_pinned() and x.dim() == 4 and x.shape[1] == 3 and not (torch.is_grad_enabled() and self.training) \
-                    and next(self.parameters()).is_cuda:
+                    and self.conv1.conv.weight.is_cuda:
                 return self._forward_pinned_host(x)
             raise RuntimeError("StyleTransferNet (B200 drop-in) needs CUDA tensors: there is no CPU fallback "
                                "(pinned host batches are accepted for inference and are pipelined through the GPU)")
-        params = list(self.parameters())
+        named = self._named()
+        params = list(named.values())
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             if graphs.enabled() and not torch.cuda.is_current_stream_capturing():
                 # training step as two CUDA-graph replays (forward incl. weight re-pack, backward) per input shape
@@ -388,14 +407,14 @@ class StyleTransferNet(nn.Module):
                 if state is None:
                     if len(cache) >= 4:
                         cache.clear()
-                    state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(self.named_parameters()), precision, x, drops)
+                    state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(named), precision, x, drops)
                 if not busy:
                     return autograd_fns.stylenet_graphed_apply(state, x, drops, params)
                 # an earlier forward of this graph still waits for its backward (gradient accumulation, two losses on two
                 # inputs): the captured tape holds ONE forward, so this call takes the eager per-call-tape path below
             else:
                 drops = self._dropout_scales(x)
-            names = [n for n, _ in self.named_parameters()]
+            names = list(named)
             return autograd_fns.stylenet_apply(self._plan(need_grad=True), names, x, drops, params)
         plan = self._plan()
         use_graph = (not self.training and os.environ.get("FNST_CUDA_GRAPH", "1") != "0"

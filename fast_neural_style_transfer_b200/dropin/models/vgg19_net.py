@@ -65,10 +65,26 @@ class VGG19(nn.Module):
         state = self.__dict__.copy()
         state.pop("_plan_cache", None)
         state.pop("_graphs", None)
+        state.pop("_named_cache", None)
         return state
 
+    def _named(self):
+        """dict(self.named_parameters()), cached (see StyleTransferNet._named)."""
+        cache = self.__dict__.get("_named_cache")
+        if cache is not None:
+            owners, named = cache
+            if all(owner.get(attr) is p for owner, attr, p in owners):
+                return named
+        named = dict(self.named_parameters())
+        owners = []
+        for name, p in named.items():
+            mod_path, _, attr = name.rpartition(".")
+            owners.append((self.get_submodule(mod_path)._parameters, attr, p))
+        self.__dict__["_named_cache"] = (owners, named)
+        return named
+
     def _plan(self) -> "engine.VGGPlan":
-        params = dict(self.named_parameters())
+        params = self._named()
         key = (self.precision, tuple((p.data_ptr(), p._version) for p in params.values()))
         cache = self.__dict__.get("_plan_cache")
         if cache is None or cache[0] != key:

@@ -522,6 +522,7 @@ class VGGPlan:
         self.precision = precision
         self.dtype = act_dtype(precision)
         self.use_tc = precision != "fp32"
+        self._out_buffers = None
         self.w: Dict[str, torch.Tensor] = {}
         self.b: Dict[str, torch.Tensor] = {}
 
@@ -540,17 +541,29 @@ class VGGPlan:
     def _conv(self, name: str, a: torch.Tensor, tape: Optional[dict]) -> torch.Tensor:
         B, H, W, C = a.shape
         cout = self.w[name].shape[0]
-        out = torch.empty((B, H, W, cout), dtype=self.dtype, device=a.device)
+        out = (self._out_buffers or {}).get(name)           # caller-provided output (the five feature maps in one flat buffer)
+        if out is None:
+            out = torch.empty((B, H, W, cout), dtype=self.dtype, device=a.device)
+        assert tuple(out.shape) == (B, H, W, cout) and out.dtype == self.dtype and out.is_contiguous()
         spec = ConvSpec(taps_kxk(3), C, self.w[name], cout, cout, h0=-1, w0=-1, bias=self.b[name], relu=True)
         ops.conv_gather(spec, a, (B, H, W, C), _nhwc_strides(a), out, (H, W), None, self.use_tc)
         if tape is not None:
             tape[name] = (a, out)
         return out
 
-    def forward(self, x: torch.Tensor, tape: Optional[dict] = None) -> List[torch.Tensor]:
+    FEATURE_LAYERS = ("slice1.2", "slice2.7", "slice3.14", "slice4.21", "slice5.23")
+
+    @staticmethod
+    def feature_shapes(B: int, H: int, W: int):
+        """NHWC shapes of the five returned feature maps for a (B,3,H,W) input."""
+        return [(B, H, W, 64), (B, H // 2, W // 2, 128), (B, H // 4, W // 4, 256), (B, H // 8, W // 8, 512), (B, H // 8, W // 8, 512)]
+
+    def forward(self, x: torch.Tensor, tape: Optional[dict] = None, out_buffers: Optional[Dict[str, torch.Tensor]] = None) -> List[torch.Tensor]:
+        """out_buffers: optional {layer name in FEATURE_LAYERS: preallocated NHWC output} (e.g. views of one flat buffer)."""
         assert x.dim() == 4 and x.shape[1] == 3
         x = x.contiguous().float()
         B, _, H, W = x.shape
+        self._out_buffers = out_buffers
         if H < 8 or W < 8:
             raise RuntimeError("VGG19 feature stack needs H, W >= 8 (three 2x2 max-pools)")
         if self.use_tc:

@@ -459,9 +459,11 @@ def relu_mask(g, extra, act):
     return out
 
 
-def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def cast(x: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert x.is_contiguous()
-    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    assert out.dtype == dtype and out.is_contiguous() and out.numel() == x.numel()
     dev, st = _ctx(x)
     check(lib.fnst_cast(_ptr(x), _ptr(out), x.numel(), dt(x.dtype), dt(dtype), dev, st), "cast")
     _count()
