@@ -177,12 +177,20 @@ def assemble_gradients(core: dict, names: Sequence[str], params: Dict[str, torch
     return flat
 
 
-def _final_dgrad_layout(wt):                                              # (3, 32, 9, 9) -> (32, 18*64)
-    wd = torch.zeros((32, 9, 2, 8, 8), dtype=wt.dtype)                # (c, kh, a, i, j)
+def _final_dgrad_layout(wt):                                              # (3, 32, 9, 9) -> (64, 9*64)
+    """final_conv data-gradient operand for the PIXEL-PAIR form: one GEMM row computes the two neighbouring pixels (2m, 2m+1)
+    of d_act4 (64 columns = parity x 32 channels = exactly two NHWC pixels) from ONE 128-byte window of the 4-channel
+    zero-halo gradient image, 16 pixels x 4 channels starting at pixel 2m: window pixel i holds dy column u - kw + 8 for
+    kw = parity + 8 - i.  Nine taps (kernel rows) instead of the 18 of the 8-channel single-pixel form: half the executed
+    FLOPs and a quarter of the L2 -> shared-memory traffic."""
+    wd = torch.zeros((2, 32, 9, 16, 4), dtype=wt.dtype)               # (parity, c, kh, i, j)
     wperm = wt.permute(1, 2, 3, 0)                                    # (c, kh, kw, j)
-    wd[:, :, 0, :, :3] = wperm[:, :, _FINAL_KW[:8], :]                # a = 0: pixel i <-> kw = 8 - i
-    wd[:, :, 1, 0, :3] = wperm[:, :, 0, :]                            # a = 1: pixel 0 <-> kw = 0
-    return wd.reshape(32, 18 * 64)
+    for par in (0, 1):
+        for i in range(16):
+            kw = par + 8 - i
+            if 0 <= kw <= 8:
+                wd[par, :, :, i, :3] = wperm[:, :, kw, :]
+    return wd.reshape(64, 9 * 64)
 
 
 def pack_dgrad_operands(plan: "engine.StyleNetPlan") -> Dict[str, torch.Tensor]:
@@ -304,9 +312,8 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
     taps81 = taps_kxk(9)
     wfin = p["final_conv.conv.weight"]
     if tc:
-        # Tensor-core forms on an 8-channel zero-halo copy of dy (halo 8; one pixel = 16 bytes, 8 pixels = one 128-byte row):
-        #  dgrad: window at halo position (y+8-kh, x[+8]) covers dy pixels x-kw for kw = 8..1 [and kw = 0]: 18 taps, K = 1152
-        #  wgrad: contraction over halo positions p; M side = 16-pixel dy window (128 = 16 px x 8 ch) at p, N side = act4
+        # Tensor-core forms on zero-halo copies of dy (halo 8):
+        #  wgrad (8-channel copy: one pixel = 16 bytes, 8 pixels = one 128-byte row): contraction over halo positions p; M side = 16-pixel dy window (128 = 16 px x 8 ch) at p, N side = act4
         #         pixel-pair window at p + (kh-8, 0): D[(i,j)][kh*64 + jj*32 + c] = dW[j][c][kh][jj+8-i]  (9 taps)
         rows_g, pitch_g = H4 + 16, W4 + 16
         g8 = ops.image_to_halo(dy, 8, PAD_ZERO, 8, rows_g, pitch_g, gdt)
@@ -321,10 +328,12 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
                       (rows_g, pitch_g), use_tc=True, g_strides=g_str, out=slot("final"), out_zeroed=True)
             keep_alive.append(a_g)
 
-        taps18 = [(8 - kh, a * 8, 0) for kh in range(9) for a in (0, 1)]
+        # dgrad, pixel-pair form (see _final_dgrad_layout): 4-channel zero-halo image, windows start at every second pixel
+        g4 = ops.image_to_halo(dy, 8, PAD_ZERO, 4, rows_g, pitch_g, gdt)
         d_act4 = torch.empty((B, Hq, Wq, 32), dtype=gdt, device=dev)
-        ops.conv_gather(ConvSpec(taps18, 64, wd_all["final"], 32, 32), g8,
-                        (B, rows_g, pitch_g, 64), g_str, d_act4, (Hq, Wq), None, True)
+        ops.conv_gather(ConvSpec([(8 - kh, 0, 0) for kh in range(9)], 64, wd_all["final"], 64, 64), g4,
+                        (B, rows_g, pitch_g // 2, 64), (rows_g * pitch_g * 4, pitch_g * 4, 8), d_act4.view(B, Hq, Wq // 2, 64),
+                        (Hq, Wq // 2), None, True)
     else:
         g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
         wgrad(ConvSpec(taps81, 32, None, 16, 3), act4, None, (B, Hq, Wq, 32), g16, (H4, W4), slot("final"))
