@@ -14,6 +14,7 @@ F32, F16, BF16 = 0, 1, 2
 EPI_NHWC, EPI_D2S, EPI_NCHW_F32, EPI_ROWSUM9 = 0, 1, 2, 3
 PAD_NONE, PAD_REFLECT, PAD_ZERO = 0, 1, 2
 DESC_PREZEROED = 1
+DESC_LINEAR = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FNST_LIB", os.path.join(_HERE, "libfnst.so"))
@@ -78,8 +79,8 @@ EXPORTS = {
     "fnst_wgrad_tc": (C.c_int, [C.POINTER(ConvDesc), C.c_int, C.c_int, C.c_void_p]),
     "fnst_conv_first_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
-    "fnst_inorm_bwd_reduce": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "fnst_inorm_bwd_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_inorm_bwd_reduce": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fnst_inorm_bwd_apply": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 6 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fnst_inorm_bwd_fused_parts": (C.c_int, [C.c_int] * 9),
     "fnst_inorm_bwd_fused": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 7 + [C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fnst_affine_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),

@@ -91,6 +91,12 @@ def _tc_ok(use_tc: bool, kc: int, n_gemm: int) -> bool:
 # side stream the way the small two-pass kernels do.
 FUSED_INORM_BWD = os.environ.get("FNST_INORM_BWD_FUSED", "0") not in ("", "0")
 
+# Pixel-stream data gradients (fnst.h FNST_DESC_LINEAR) for the residual trunk: the InstanceNorm backward writes d_raw into a
+# buffer with a 2-pixel ZERO halo, and the data gradient of the 3x3 convolution behind ReflectionPad2d(1) runs over the linear
+# pixel stream of that buffer -- 145 full tiles at 4 x 64 x 64 (one wave on 148 SMs; 21 us) instead of 180 ragged 8 x 16 boxes
+# on the 66 x 66 domain (two waves; 35.5 us).  FNST_LINEAR_DGRAD=0 restores the box form.
+LINEAR_DGRAD = os.environ.get("FNST_LINEAR_DGRAD", "1") not in ("", "0")
+
 NORM_LAYERS = (["norm1", "norm2"] + [f"res_blocks.{i}.{n}" for i in range(5) for n in ("in1", "in2")] + ["norm3", "norm4"])
 
 
@@ -247,17 +253,19 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
     norm_sums: Dict[str, tuple] = {}
     wtw = tape.get("w") or {}                    # bf16 twins of the saved activations (None entries: use the activation itself)
 
-    def inorm_backward(layer, gsrc, extra, raw, stats, drop, relu, pad=0, pad_mode=PAD_NONE, s2d=False, out_s2d=False, want_gy=False):
-        """d_raw (and gy when asked) of one InstanceNorm layer; its sums slice is registered for the affine gradients."""
+    def inorm_backward(layer, gsrc, extra, raw, stats, drop, relu, pad=0, pad_mode=PAD_NONE, s2d=False, out_s2d=False, want_gy=False,
+                       gsrc_slack=0, out_pad=0):
+        """d_raw (and gy when asked) of one InstanceNorm layer; its sums slice is registered for the affine gradients.
+        gsrc_slack / out_pad: geometry of the pixel-stream data gradients (see LINEAR_DGRAD)."""
         ga, ba = plan._affine(layer)
         src_off = arena.used
         sums = arena.take(B, raw.shape[-1], 2)
         norm_sums[layer] = (src_off, raw.shape[-1])
-        if FUSED_INORM_BWD and ops.inorm_bwd_fused_parts(raw, gdt, gsrc is not None, extra is not None, s2d) > 0:
+        if FUSED_INORM_BWD and not (gsrc_slack or out_pad) and ops.inorm_bwd_fused_parts(raw, gdt, gsrc is not None, extra is not None, s2d) > 0:
             d_raw, gy, _ = ops.inorm_bwd_fused(gsrc, extra, raw, stats, ga, ba, drop, gdt, relu, pad, pad_mode, s2d, out_s2d, want_gy, sums)
             return d_raw, gy
-        gy, _ = ops.inorm_bwd_reduce(gsrc, extra, raw, stats, ga, ba, drop, gdt, relu, pad, pad_mode, s2d, sums=sums)
-        d_raw, _ = ops.inorm_bwd_apply(gy, raw, stats, sums, ga, out_s2d=out_s2d, want_dgb=False)
+        gy, _ = ops.inorm_bwd_reduce(gsrc, extra, raw, stats, ga, ba, drop, gdt, relu, pad, pad_mode, s2d, sums=sums, gsrc_slack=gsrc_slack)
+        d_raw, _ = ops.inorm_bwd_apply(gy, raw, stats, sums, ga, out_s2d=out_s2d, want_dgb=False, out_pad=out_pad)
         return d_raw, gy
 
     # Weight gradients are off the critical path (nothing downstream in this backward consumes them): they run on a
@@ -285,14 +293,18 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
         keep_alive.extend(tensors)
         return _Side()
 
-    def wgrad(spec, a, a_twin, a_dims, g, out_hw, out):
+    def wgrad(spec, a, a_twin, a_dims, g, out_hw, out, g_pad=0):
         """Weight gradient of `spec` into a staging slice; tensor cores whenever the channel window is a multiple of 64
-        (operand = the activation's bf16 twin when the forward wrote one, else a cast)."""
+        (operand = the activation's bf16 twin when the forward wrote one, else a cast).  g_pad: g carries a halo of that width."""
         use_tc = tc and spec.kc % 64 == 0
         if use_tc and a.dtype != g.dtype:
             a = a_twin if a_twin is not None else ops.cast(a, g.dtype)
             keep_alive.append(a)
-        ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, out=out, out_zeroed=True)
+        g_strides = None
+        if g_pad:
+            g_strides = (g.stride(0), g.stride(1), g.stride(2))
+            g = g[:, g_pad:g.shape[1] - g_pad, g_pad:g.shape[2] - g_pad, :]
+        ops.wgrad(spec, a, a_dims, _nhwc_strides(a), g, out_hw, use_tc=use_tc, g_strides=g_strides, out=out, out_zeroed=True)
 
     wd_all = getattr(plan, "wd", None) or pack_dgrad_operands(plan)     # packed by the training forward (side stream) when it ran
 
@@ -365,7 +377,19 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
     res_dg = wd_all["res"]                      # (10, 256, 9*256): the ten 3x3 data-gradient operands as one stacked tensor
     res_db = slot("res")
 
+    lin = tc and LINEAR_DGRAD and not FUSED_INORM_BWD
+    Z = 2 if lin else 0                         # zero halo of the trunk's d_raw buffers = slack of the gradients computed from them
+    Hz, Wz = H2 + 2 * Z, W2 + 2 * Z
+
     def res_dgrad(g, idx):
+        """Gradient w.r.t. the reflect-padded input of a trunk convolution from d_raw: (B, H2+2, W2+2, 256), or, in the
+        pixel-stream form, (B, H2+4, W2+4, 256) whose [:, :H2+2, :W2+2] corner holds it (g then has a 2-pixel zero halo)."""
+        if lin:
+            m = B * Hz * Wz
+            out = torch.empty((B, Hz, Wz, 256), dtype=gdt, device=dev)
+            ops.conv_gather(ConvSpec([(Z - dh, Z - dw, 0) for dh, dw, _ in taps9], 256, res_dg[idx], 256, 256), g, (1, 1, m, 256),
+                            (m * 256, Wz * 256, 256), out, (1, m), None, True, linear=True)
+            return out
         out = torch.empty(pdims, dtype=gdt, device=dev)
         ops.conv_gather(ConvSpec(_neg(taps9), 256, res_dg[idx], 256, 256), g, (B, H2, W2, 256), _nhwc_strides(g), out,
                         (H2 + 2, W2 + 2), None, tc)
@@ -376,21 +400,23 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
         pre = f"res_blocks.{i}"
         # in2 (no ReLU); the total output gradient also feeds the skip connection
         d_raw_b, g_out = inorm_backward(pre + ".in2", gsrc, extra, blk["raw_b"], blk["st_b"], None, False,
-                                        1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE, want_gy=True)
+                                        1 if gsrc is not None else 0, PAD_REFLECT if gsrc is not None else PAD_NONE, want_gy=True,
+                                        gsrc_slack=Z if gsrc is not None else 0, out_pad=Z)
         mid = blk["mid"]
         with on_side(mid, d_raw_b):
-            wgrad(ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, mid_w[i], pdims, d_raw_b, (H2, W2), res_db[2 * i + 1])
+            wgrad(ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}b"), mid, mid_w[i], pdims, d_raw_b, (H2, W2), res_db[2 * i + 1], g_pad=Z)
         d_mid = res_dgrad(d_raw_b, 2 * i + 1)
         # in1 + ReLU + Dropout2d
-        d_raw_a, _ = inorm_backward(pre + ".in1", d_mid, None, blk["raw_a"], blk["st_a"], blk["drop"], True, 1, PAD_REFLECT)
+        d_raw_a, _ = inorm_backward(pre + ".in1", d_mid, None, blk["raw_a"], blk["st_a"], blk["drop"], True, 1, PAD_REFLECT,
+                                    gsrc_slack=Z, out_pad=Z)
         cur = trunk[i]
         with on_side(cur, d_raw_a):
-            wgrad(ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, trunk_w[i], pdims, d_raw_a, (H2, W2), res_db[2 * i])
+            wgrad(ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, trunk_w[i], pdims, d_raw_a, (H2, W2), res_db[2 * i], g_pad=Z)
         gsrc = res_dgrad(d_raw_a, 2 * i)
         extra = g_out
 
     # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
-    d_raw2, _ = inorm_backward("norm2", gsrc, extra, tape["raw2"], tape["st2"], None, True, 1, PAD_REFLECT)
+    d_raw2, _ = inorm_backward("norm2", gsrc, extra, tape["raw2"], tape["st2"], None, True, 1, PAD_REFLECT, gsrc_slack=Z)
     buf2 = tape["buf2"]
     Hs, Ws = buf2.shape[1], buf2.shape[2]
     with on_side(buf2, d_raw2):

@@ -159,10 +159,11 @@ __global__ void __launch_bounds__(256) conv_first_wgrad_kernel(const float* __re
 // ---------------------------------------------------------------------------------------------
 struct HaloLayout {
   int H, W, C, pad, reflect, s2d;
+  int slack;      // the buffer is allocated `slack` rows and columns larger than the halo extent (in its own pixel units)
   __device__ __forceinline__ size_t index(int n, int hp, int wp, int c) const {
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-    if (!s2d) return (((size_t)n * Hp + hp) * Wp + wp) * C + c;
-    const int Hs = (Hp + 1) >> 1, Ws = (Wp + 1) >> 1;
+    if (!s2d) return (((size_t)n * (Hp + slack) + hp) * (Wp + slack) + wp) * C + c;
+    const int Hs = ((Hp + 1) >> 1) + slack, Ws = ((Wp + 1) >> 1) + slack;
     return (((size_t)n * Hs + (hp >> 1)) * Ws + (wp >> 1)) * (4 * C) + ((hp & 1) * 2 + (wp & 1)) * C + c;
   }
   // padded coordinates whose value was copied from interior coordinate i (extent n): returns count (<= 3)
@@ -190,7 +191,6 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) inorm_bwd_reduce_kernel(const
                                                                float* __restrict__ sums, float* __restrict__ dgb, HaloLayout L,
                                                                int relu, float eps, int rows_per_block) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ float sm[];      // par[5][C] (a, b, mean, rstd, dropout scale) | part[PL][2C]
   const int n = blockIdx.y;
   const int C = L.C, CG = C >> 3, PL = 256 / CG;
@@ -208,6 +208,9 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) inorm_bwd_reduce_kernel(const
       par[4 * C + c] = drop ? drop[(size_t)n * C + c] : 1.f;
     }
   }
+  // The table above only reads tensors of the FORWARD pass (statistics, affine parameters, dropout scales): it is built while
+  // the predecessor (the data-gradient GEMM that produces gsrc) drains; gradients are touched only below this wait.
+  pdl_wait();
   __syncthreads();
   float a[8], b[8], mean[8], rstd[8], ds[8];
 #pragma unroll
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restri
                                                               const float* __restrict__ stats, const float* __restrict__ sums,
                                                               const float* __restrict__ gamma, TG* __restrict__ draw,
                                                               int H, int W, int C, float eps, int out_s2d, float* __restrict__ dgb,
-                                                              int rows_per_block) {
+                                                              int rows_per_block, int out_pad) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float par[];     // [5][C]: k0 = gamma*rstd, mean(gy), mean(gy*xhat), mean, rstd
@@ -358,9 +361,32 @@ __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restri
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = k0[i] * (g[i] - m1[i] - (x[i] - mean[i]) * rstd[i] * m2[i]);
         TG* dst = out_s2d ? draw + (((size_t)n * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * (4 * C) + ((h & 1) * 2 + (w & 1)) * C + c0
-                          : draw + idx;
+                 : out_pad ? draw + (((size_t)n * (H + 2 * out_pad) + h + out_pad) * (W + 2 * out_pad) + w + out_pad) * C + c0
+                           : draw + idx;
         store8<TG>(dst, g);
       }
+    }
+  }
+  if (out_pad) {
+    // zero halo of the padded output [n][H+2p][W+2p][C]: the 2p border pixels of this block's rows, and an equal share of
+    // the p top + p bottom rows (the consumer is a zero-padded gather-GEMM over the linear pixel stream of this buffer)
+    const int Wp = W + 2 * out_pad, Hp = H + 2 * out_pad;
+    float z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = 0.f;
+    TG* img = draw + (size_t)n * Hp * Wp * C;
+    const int h_lo = blockIdx.x * rows_per_block, h_hi = min(h_lo + rows_per_block, H);
+    for (int i = pl; i < (h_hi - h_lo) * 2 * out_pad; i += PL) {
+      const int h = h_lo + i / (2 * out_pad), k = i % (2 * out_pad);
+      const int wp = k < out_pad ? k : W + k;                       // left border [0,p), right border [W+p, W+2p)
+      store8<TG>(img + ((size_t)(h + out_pad) * Wp + wp) * C + c0, z);
+    }
+    const int frame = 2 * out_pad * Wp;                              // pixels of the top and bottom rows
+    const int per = (frame + gridDim.x - 1) / gridDim.x;
+    for (int i = blockIdx.x * per + pl; i < min(frame, (int)(blockIdx.x + 1) * per); i += PL) {
+      const int r = i / Wp, wp = i - r * Wp;
+      const int hp = r < out_pad ? r : H + r;                        // rows [0,p) and [H+p, H+2p)
+      store8<TG>(img + ((size_t)hp * Wp + wp) * C + c0, z);
     }
   }
 }
@@ -876,8 +902,9 @@ extern "C" int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const 
 extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
                                      const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
                                      float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
-                                     int pad, int pad_mode, int s2d, int prezeroed, int device, void* stream) {
+                                     int pad, int pad_mode, int s2d, int gsrc_slack, int prezeroed, int device, void* stream) {
   FNST_CHECK_ARG((gsrc || extra) && raw && stats && gamma && beta && gy && sums, "inorm_bwd_reduce: null pointer");
+  FNST_CHECK_ARG(gsrc_slack >= 0, "inorm_bwd_reduce: negative gsrc_slack");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 1024 && 256 % (c / 8) == 0, "inorm_bwd_reduce: unsupported channel count %d", c);
   FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -885,7 +912,7 @@ extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const 
     FNST_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)n * c, st));
     if (dgb) FNST_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * 2 * (size_t)c, st));
   }
-  HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d};
+  HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d, gsrc_slack};
   const int rpb = rows_per_block(h, n);
   dim3 grid((h + rpb - 1) / rpb, n);
   const size_t smem = sizeof(float) * (5 * (size_t)c + (size_t)(256 / (c / 8)) * 2 * c);
@@ -904,8 +931,9 @@ extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const 
 
 extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, const float* sums, const float* gamma,
                                     void* draw, float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps,
-                                    int out_s2d, int device, void* stream) {
+                                    int out_s2d, int out_pad, int device, void* stream) {
   FNST_CHECK_ARG(gy && raw && stats && sums && gamma && draw, "inorm_bwd_apply: null pointer");
+  FNST_CHECK_ARG(out_pad >= 0 && !(out_pad && out_s2d), "inorm_bwd_apply: out_pad is for the plain NHWC output only");
   FNST_CHECK_ARG(c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0, "inorm_bwd_apply: unsupported channel count %d", c);
   FNST_CHECK_ARG(!out_s2d || (h % 2 == 0 && w % 2 == 0), "inorm_bwd_apply: space-to-depth output needs even h, w");
   FNST_DEVICE(device);
@@ -915,7 +943,7 @@ extern "C" int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float
     FNST_DISPATCH_DTYPE(g_dtype, TG, {
       launch_pdl(inorm_bwd_apply_kernel<TA, TG>, dim3(grid), dim3(256), sizeof(float) * 5 * c, (cudaStream_t)stream,
           reinterpret_cast<const TG*>(gy), reinterpret_cast<const TA*>(raw), stats, sums, gamma, reinterpret_cast<TG*>(draw),
-          h, w, c, eps, out_s2d, dgb, rpb);
+          h, w, c, eps, out_s2d, dgb, rpb, out_pad);
     });
   });
   return launch_status("inorm_bwd_apply");

@@ -71,6 +71,7 @@ struct ConvTcParams {
   int32_t h0, w0;
   int32_t epilogue, c_out, n_gemm, relu, out_is_bf16, out_is_f32, b_image_rows;
   int32_t stage_out;             // 1: epilogue stages the tile in shared memory (swizzled) and stores it with TMA (one tile per CTA)
+  int32_t lin_pitch;             // > 0: pixel-stream form (FNST_DESC_LINEAR): tap (dh, dw) = pixel offset dh * lin_pitch + dw
   uint32_t idesc;
   int32_t out_dtype, mask_dtype;
   void* out;
@@ -197,17 +198,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int brow = n * p.b_image_rows + n_tile * BLOCK_N + rank * Cfg::B_ROWS;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           const int t = kb / p.chunks_per_tap, ch = kb - t * p.chunks_per_tap;
+          // pixel-stream form: the tile is 128 consecutive pixels of a linear stream and a tap is a linear shift
+          const int cw = wb + p.tap_dw[t] + p.tap_dh[t] * p.lin_pitch;
+          const int chh = p.lin_pitch ? 0 : hb + p.tap_dh[t];
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + TC_A_BYTES;
           if (PAIR) {
             // one arrival + the bytes of BOTH CTAs on the leader's barrier (the partner's loads are credited to it)
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            tma_load_4d_pair(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, wb + p.tap_dw[t], hb + p.tap_dh[t], n);
+            tma_load_4d_pair(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, cw, chh, n);
             tma_load_2d_pair(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, brow);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_4d(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, wb + p.tap_dw[t], hb + p.tap_dh[t], n);
+            tma_load_4d(sa, &map_a, &full_bar[stage], p.tap_c0[t] + ch * TC_BLOCK_K, cw, chh, n);
             tma_load_2d(sb, &map_b, &full_bar[stage], kb * TC_BLOCK_K, brow);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -554,6 +558,13 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   if (d->epilogue == FNST_EPI_NHWC) FNST_CHECK_ARG(d->c_out == d->n_gemm && (d->n_gemm == 16 || d->n_gemm % 32 == 0), "conv_tc: NHWC epilogue needs c_out == n_gemm, a multiple of 32 (or 16)");
   if (d->epilogue == FNST_EPI_NCHW_F32) FNST_CHECK_ARG(d->c_out <= 16 && !d->stats && !d->relu, "conv_tc: NCHW epilogue supports c_out <= 16, no stats/relu");
   const bool rowsum = d->epilogue == FNST_EPI_ROWSUM9;
+  const bool linear = (d->flags & FNST_DESC_LINEAR) != 0;
+  if (linear) {
+    // pixel-stream form: one row of a_w pixels; tap (dh, dw) is the linear pixel shift dh * pitch + dw, pitch = a_stride_h / a_stride_w
+    FNST_CHECK_ARG(d->a_h == 1 && d->a_n == 1 && d->out_h == 1 && d->out_n == 1, "conv_tc: the pixel-stream form needs a_h == a_n == out_h == out_n == 1");
+    FNST_CHECK_ARG(d->epilogue == FNST_EPI_NHWC && !d->stats && d->a_stride_w > 0 && d->a_stride_h % d->a_stride_w == 0,
+                   "conv_tc: the pixel-stream form needs the NHWC epilogue, no statistics and a row stride that is a multiple of the pixel stride");
+  }
   if (rowsum) {
     FNST_CHECK_ARG(d->n_gemm == 32 && 9 * d->c_out <= 27 && !d->stats && !d->relu, "conv_tc: ROWSUM9 needs n_gemm == 32, c_out <= 3, no stats/relu");
     for (int t = 0; t < d->ntaps; ++t) FNST_CHECK_ARG(d->tap_dh[t] == 0, "conv_tc: ROWSUM9 taps must have dh == 0");
@@ -566,7 +577,7 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   p.out_n = d->out_n; p.out_h = d->out_h; p.out_w = d->out_w;
   // pixel tile TH x TW = 128: wide tiles for wide images, never wider than needed
   // ROWSUM9: tall 4 x 32 T tiles advance by 24 output rows (8-row halo below): 75 % of the loaded rows are new
-  const int tw_log2 = rowsum ? 2 : (d->out_w <= 8 ? 3 : 4);
+  const int tw_log2 = linear ? 7 : rowsum ? 2 : (d->out_w <= 8 ? 3 : 4);
   p.tw_log2 = tw_log2;
   const int TW = 1 << tw_log2, TH = TC_BLOCK_M >> tw_log2;
   p.h_step = rowsum ? TH - 8 : TH;
@@ -595,6 +606,7 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   p.chunks_per_tap = d->kc / TC_BLOCK_K;
   p.num_kblocks = d->ntaps * p.chunks_per_tap;
   p.h0 = d->h0; p.w0 = d->w0;
+  p.lin_pitch = linear ? (int32_t)(d->a_stride_h / d->a_stride_w) : 0;
   p.epilogue = d->epilogue; p.c_out = d->c_out; p.n_gemm = d->n_gemm; p.relu = d->relu;
   p.out_is_bf16 = d->out_dtype == FNST_BF16; p.out_is_f32 = d->out_dtype == FNST_F32;
   // CTA pairs (M = 256 MMAs across two SMs) for the wide column tiles.  Measured (tools/exp_conv_fixed_cost.py): ~7 % less
@@ -616,7 +628,8 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   CUtensorMap ma, mb;
   {
     const uint64_t dims[4] = {(uint64_t)d->a_c, (uint64_t)d->a_w, (uint64_t)d->a_h, (uint64_t)d->a_n};
-    const uint64_t str[3] = {(uint64_t)d->a_stride_w * 2, (uint64_t)d->a_stride_h * 2, (uint64_t)d->a_stride_n * 2};
+    uint64_t str[3] = {(uint64_t)d->a_stride_w * 2, (uint64_t)d->a_stride_h * 2, (uint64_t)d->a_stride_n * 2};
+    if (linear) str[1] = str[2] = (uint64_t)d->a_stride_w * 2 * (uint64_t)d->a_w;       // extent-1 dimensions: any legal stride
     const uint32_t box[4] = {TC_BLOCK_K, (uint32_t)TW, (uint32_t)TH, 1};
     if (int r = encode_tensor_map_2b(&ma, d->a, 4, dims, str, box)) return r;
   }

@@ -150,12 +150,17 @@ class ZeroArena:
 
 def conv_gather(spec: ConvSpec, a: torch.Tensor, a_dims: Tuple[int, int, int, int], a_strides: Tuple[int, int, int],
                 out: torch.Tensor, out_hw: Tuple[int, int], stats: Optional[torch.Tensor], use_tc: bool,
-                stats_zeroed: bool = False) -> None:
+                stats_zeroed: bool = False, linear: bool = False) -> None:
     """a_dims = (n, h, w, c) logical extents of the activation view; a_strides = (n, h, w) element strides.
-    stats_zeroed: `stats` is already zero (slice of a ZeroArena); the call then issues no memset."""
+    stats_zeroed: `stats` is already zero (slice of a ZeroArena); the call then issues no memset.
+    linear: pixel-stream form (fnst.h FNST_DESC_LINEAR; tensor cores only): a_dims = (1, 1, pixels, c), out_hw = (1, pixels),
+    tap (dh, dw) = pixel shift dh * (a_strides[1] // a_strides[2]) + dw."""
     d = _fill_desc(spec, a, a_dims, a_strides, out_hw)
     if stats_zeroed:
         d.flags = _lib.DESC_PREZEROED
+    if linear:
+        assert use_tc, "the pixel-stream form exists on the tensor-core kernel only"
+        d.flags |= _lib.DESC_LINEAR
     wshape = (spec.n_gemm, len(spec.taps) * spec.kc)
     if spec.per_image_weights:
         wshape = (a_dims[0],) + wshape
@@ -326,9 +331,11 @@ def conv_first_wgrad(x: torch.Tensor, g: torch.Tensor, k: int, stride: int, pad:
 
 
 def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=_lib.PAD_NONE, s2d=False,
-                     eps: float = 1e-5, arena: Optional[ZeroArena] = None, sums: Optional[torch.Tensor] = None):
+                     eps: float = 1e-5, arena: Optional[ZeroArena] = None, sums: Optional[torch.Tensor] = None,
+                     gsrc_slack: int = 0):
     """arena / sums: take the (zeroed) reduction buffer from the arena, or use the given zeroed [n,c,2] tensor, instead of
-    having the call memset a fresh one."""
+    having the call memset a fresh one.  gsrc_slack: gsrc is allocated that many rows and columns larger than its halo
+    extent (output of a pixel-stream data-gradient GEMM)."""
     n, h, w, c = raw.shape
     gy = torch.empty((n, h, w, c), dtype=gdtype, device=raw.device)
     dgb = None                   # d gamma / d beta come out of pass 2 (inorm_bwd_apply): no same-address atomics in pass 1
@@ -344,20 +351,21 @@ def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, p
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_bwd_reduce(_ptr(gsrc), _ptr(extra), _ptr(raw), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(drop), _ptr(gy),
                                     _ptr(sums), _ptr(dgb), n, h, w, c, dt(raw.dtype), dt(gdtype), int(relu), eps, pad, pad_mode, int(s2d),
-                                    int(prezeroed), dev, st), "inorm_bwd_reduce")
+                                    int(gsrc_slack), int(prezeroed), dev, st), "inorm_bwd_reduce")
     _count(1 if prezeroed else 2)
     return gy, sums
 
 
-def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-5, want_dgb: bool = True):
-    """Returns (d_raw, dgb) with dgb = [d gamma; d beta] (2, c) fp32 (None unless want_dgb)."""
+def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps: float = 1e-5, want_dgb: bool = True, out_pad: int = 0):
+    """Returns (d_raw, dgb) with dgb = [d gamma; d beta] (2, c) fp32 (None unless want_dgb).
+    out_pad: d_raw is (n, h + 2*out_pad, w + 2*out_pad, c) with a zero halo written by the same launch."""
     n, h, w, c = raw.shape
-    shape = (n, h // 2, w // 2, 4 * c) if out_s2d else (n, h, w, c)
+    shape = (n, h // 2, w // 2, 4 * c) if out_s2d else (n, h + 2 * out_pad, w + 2 * out_pad, c)
     draw = torch.empty(shape, dtype=gy.dtype, device=raw.device)
     dgb = torch.empty((2, c), dtype=torch.float32, device=raw.device) if want_dgb else None
     dev, st = _ctx(raw)
     check(lib.fnst_inorm_bwd_apply(_ptr(gy), _ptr(raw), _ptr(stats), _ptr(sums), _ptr(gamma), _ptr(draw), _ptr(dgb), n, h, w, c,
-                                   dt(raw.dtype), dt(gy.dtype), eps, int(out_s2d), dev, st), "inorm_bwd_apply")
+                                   dt(raw.dtype), dt(gy.dtype), eps, int(out_s2d), int(out_pad), dev, st), "inorm_bwd_apply")
     _count()
     return draw, dgb
 

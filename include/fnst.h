@@ -86,6 +86,13 @@ typedef struct fnst_conv_desc {
  * caller (e.g. one arena memset per forward), so the call issues no memset in front of the kernel and the kernel can
  * be chained to its predecessor by programmatic dependent launch. */
 #define FNST_DESC_PREZEROED 1
+/* fnst_conv_tc only: PIXEL-STREAM form.  The activation view is ONE row of a_w pixels (a_h == a_n == out_h == out_n == 1, NHWC
+ * epilogue, no statistics) and tap (dh, dw) addresses pixel  w + dh * pitch + dw  with pitch = a_stride_h / a_stride_w; GEMM
+ * tiles are 128 consecutive pixels.  A zero-haloed image batch [n][H+2z][W+2z][c] presented this way turns a zero-padded
+ * convolution over the (H+2z) x (W+2z) domain into n*(H+2z)*(W+2z)/128 full tiles -- the data gradient of a 3x3 convolution
+ * behind ReflectionPad2d(1) on 4 x 64 x 64 images is 145 tiles (one wave of a 148-SM GPU) instead of the 180 of 8 x 16 pixel
+ * boxes on the 66 x 66 domain.  Columns beyond the image in each row of the output are don't-care values. */
+#define FNST_DESC_LINEAR 2
 
 int fnst_version(void);
 const char* fnst_last_error(void);
@@ -240,13 +247,17 @@ int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const void* g, in
 int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
                           const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
                           float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
-                          int pad, int pad_mode, int s2d, int prezeroed, int device, void* stream);
-/* Pass 2: draw = gamma*rstd*(gy - mean(gy) - xhat*mean(gy*xhat)), written NHWC [n,h,w,c] or, if out_s2d,
+                          int pad, int pad_mode, int s2d, int gsrc_slack, int prezeroed, int device, void* stream);
+/* gsrc_slack: gsrc is allocated gsrc_slack rows and columns larger than its halo extent ([n][h+2pad+slack][w+2pad+slack][c];
+ * space-to-depth: slack in space-to-depth pixels) -- the output of a pixel-stream data-gradient GEMM (FNST_DESC_LINEAR).
+ * Pass 2: draw = gamma*rstd*(gy - mean(gy) - xhat*mean(gy*xhat)), written NHWC [n,h,w,c] or, if out_s2d,
  * space-to-depth [n,h/2,w/2,4c] (channel = ((h&1)*2+(w&1))*c + ch; h, w even).
- * dgb (optional, fp32 [2][c], written, not accumulated): d gamma = sum_n sums[n][c][1], d beta = sum_n sums[n][c][0]. */
+ * dgb (optional, fp32 [2][c], written, not accumulated): d gamma = sum_n sums[n][c][1], d beta = sum_n sums[n][c][0].
+ * out_pad > 0 (plain NHWC output only): draw is [n][h+2*out_pad][w+2*out_pad][c] with the gradient at (out_pad, out_pad) and a
+ * ZERO halo written by this call (operand of a pixel-stream data-gradient GEMM, FNST_DESC_LINEAR). */
 int fnst_inorm_bwd_apply(const void* gy, const void* raw, const float* stats, const float* sums, const float* gamma,
                          void* draw, float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, float eps,
-                         int out_s2d, int device, void* stream);
+                         int out_s2d, int out_pad, int device, void* stream);
 
 /*
  * InstanceNorm2d backward in ONE pass (same semantics as fnst_inorm_bwd_reduce followed by fnst_inorm_bwd_apply; autograd of

@@ -19,9 +19,21 @@ def _reflect(i: torch.Tensor, n: int) -> torch.Tensor:
     return torch.where(i >= n, 2 * (n - 1) - i, i)
 
 
-def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc, stats_zeroed=False):
+def conv_gather(spec, a, a_dims, a_strides, out, out_hw, stats, use_tc, stats_zeroed=False, linear=False):
     n, ah, aw, ac = a_dims
     sn, sh, sw = a_strides
+    if linear:
+        # pixel-stream form (fnst.h FNST_DESC_LINEAR): one row of aw pixels, tap (dh, dw) = linear shift dh * pitch + dw
+        assert n == 1 and ah == 1 and out_hw[0] == 1 and spec.epilogue == EPI_NHWC and stats is None
+        pitch = sh // sw
+        view = a.as_strided((aw, ac), (sw, 1), a.storage_offset()).double()
+        acc = torch.zeros((out_hw[1], spec.n_gemm), dtype=torch.float64)
+        for t, (dh, dw, c0) in enumerate(spec.taps):
+            q = torch.arange(out_hw[1]) + dh * pitch + dw
+            ok = ((q >= 0) & (q < aw)).double().view(-1, 1)
+            acc += (view[q.clamp(0, aw - 1)][:, c0:c0 + spec.kc] * ok) @ spec.weight.double()[:, t * spec.kc:(t + 1) * spec.kc].t()
+        out.view(-1, spec.c_out).copy_(acc[:, :spec.c_out].to(out.dtype))
+        return
     view = a.as_strided((n, ah, aw, ac), (sn, sh, sw, 1), a.storage_offset()).double()
     oh, ow = out_hw
     wgt = spec.weight.double()
@@ -300,17 +312,17 @@ def affine_grads(sums_flat, entries, n, out):
 
 
 def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, pad=0, pad_mode=PAD_NONE, s2d=False, eps=1e-5,
-                     arena=None, sums=None):
+                     arena=None, sums=None, gsrc_slack=0):
     n, h, w, c = raw.shape
     g = torch.zeros((n, h, w, c), dtype=torch.float64)
     if gsrc is not None:
         hp, wp = h + 2 * pad, w + 2 * pad
         gs = gsrc.double()
         if s2d:                                      # undo the space-to-depth layout written by inorm_apply
-            hs, ws = (hp + 1) // 2, (wp + 1) // 2
+            hs, ws = (hp + 1) // 2 + gsrc_slack, (wp + 1) // 2 + gsrc_slack
             gs = gs.view(n, hs, ws, 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * hs, 2 * ws, c)[:, :hp, :wp]
         else:
-            gs = gs.view(n, hp, wp, c)
+            gs = gs.view(n, hp + gsrc_slack, wp + gsrc_slack, c)[:, :hp, :wp]
         if pad and pad_mode == PAD_REFLECT:          # ReflectionPad2d backward: every halo position adds into its source
             hi = _reflect(torch.arange(-pad, h + pad), h)
             wi = _reflect(torch.arange(-pad, w + pad), w)
@@ -334,7 +346,7 @@ def inorm_bwd_reduce(gsrc, extra, raw, stats, gamma, beta, drop, gdtype, relu, p
     return gy, sums
 
 
-def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps=1e-5, want_dgb=True):
+def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps=1e-5, want_dgb=True, out_pad=0):
     n, h, w, c = raw.shape
     cnt = h * w
     _, rstd, xhat = _norm_consts(raw, stats, eps)
@@ -343,6 +355,8 @@ def inorm_bwd_apply(gy, raw, stats, sums, gamma, out_s2d=False, eps=1e-5, want_d
     d = gamma.double() * rstd.view(n, 1, 1, c) * (gy.double() - m1 - xhat * m2)
     if out_s2d:
         d = d.view(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(n, h // 2, w // 2, 4 * c)
+    if out_pad:
+        d = F.pad(d, (0, 0, out_pad, out_pad, out_pad, out_pad))
     dgb = torch.stack([sums[:, :, 1].sum(0), sums[:, :, 0].sum(0)]).float()
     return d.to(gy.dtype), dgb
 

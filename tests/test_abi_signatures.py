@@ -67,6 +67,6 @@ def test_enum_constants_match_the_header():
     mirror = {"FNST_F32": _lib.F32, "FNST_F16": _lib.F16, "FNST_BF16": _lib.BF16, "FNST_EPI_NHWC": _lib.EPI_NHWC,
               "FNST_EPI_D2S": _lib.EPI_D2S, "FNST_EPI_NCHW_F32": _lib.EPI_NCHW_F32, "FNST_EPI_ROWSUM9": _lib.EPI_ROWSUM9,
               "FNST_PAD_NONE": _lib.PAD_NONE, "FNST_PAD_REFLECT": _lib.PAD_REFLECT, "FNST_PAD_ZERO": _lib.PAD_ZERO,
-              "FNST_DESC_PREZEROED": _lib.DESC_PREZEROED, "FNST_MAX_TAPS": _lib.MAX_TAPS}
+              "FNST_DESC_PREZEROED": _lib.DESC_PREZEROED, "FNST_DESC_LINEAR": _lib.DESC_LINEAR, "FNST_MAX_TAPS": _lib.MAX_TAPS}
     for name, value in mirror.items():
         assert vals[name] == value, (name, vals.get(name), value)

@@ -247,3 +247,49 @@ def test_gram_tc(shape, dtype):
     got = ops.gram(f.to(DEV), use_tc=True)
     assert rel_l2(got, ref) < 1e-5
     assert rel_l2(ops.gram(f.to(DEV), use_tc=False), ref) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 64), (2, 10, 12), (3, 37, 45)])
+def test_pixel_stream_dgrad_matches_box_form(shape):
+    """Pixel-stream data gradient of the trunk convolutions (fnst.h FNST_DESC_LINEAR; backward.LINEAR_DGRAD) against the box form:
+    inorm_bwd_apply(out_pad=2) == dense d_raw inside a ZERO halo; the 3x3 data-gradient GEMM over the linear pixel stream of
+    that buffer == the box form on the (H+2) x (W+2) domain, bit for bit (same accumulation order), in the [:H+2, :W+2] corner of
+    an (H+4) x (W+4) buffer; inorm_bwd_reduce(gsrc_slack=2) on that buffer == the dense call."""
+    B, H, W = shape
+    C = 256
+    g = torch.Generator().manual_seed(29)
+    gdt, adt = torch.bfloat16, torch.float16
+    raw = (torch.randn((B, H, W, C), generator=g) * 1.5 + 0.3).to(adt).to(DEV)
+    gy = torch.randn((B, H, W, C), generator=g).to(gdt).to(DEV)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(C, generator=g) * 0.3).to(DEV)
+    st = torch.stack([raw.double().sum((1, 2)), (raw.double() ** 2).sum((1, 2))], dim=-1).float()
+    sums = torch.stack([gy.double().sum((1, 2)), torch.zeros((B, C), dtype=torch.float64, device=DEV)], dim=-1).float().contiguous()
+    # poison the allocator's free blocks so that an unwritten halo cannot be zero by luck
+    junk = torch.full((B * (H + 4) * (W + 4) * C * 2,), float("nan"), dtype=gdt, device=DEV)
+    del junk
+    d_pad, _ = ops.inorm_bwd_apply(gy, raw, st, sums, gamma, want_dgb=False, out_pad=2)
+    d_dense, _ = ops.inorm_bwd_apply(gy, raw, st, sums, gamma, want_dgb=False)
+    assert d_pad.shape == (B, H + 4, W + 4, C)
+    assert torch.equal(d_pad[:, 2:-2, 2:-2], d_dense)
+    halo = d_pad.clone()
+    halo[:, 2:-2, 2:-2] = 0
+    assert torch.equal(halo, torch.zeros_like(halo))
+
+    wt = (torch.randn((C, C, 3, 3), generator=g) / 48)
+    wd = backward.pack_dgrad(engine.pack_conv(wt, torch.float64), 9, C, gdt).to(DEV)
+    taps9 = engine.taps_kxk(3)
+    box = torch.empty((B, H + 2, W + 2, C), dtype=gdt, device=DEV)
+    ops.conv_gather(ConvSpec(backward._neg(taps9), C, wd, C, C), d_dense, (B, H, W, C), engine._nhwc_strides(d_dense), box,
+                    (H + 2, W + 2), None, True)
+    m = B * (H + 4) * (W + 4)
+    lin = torch.empty((B, H + 4, W + 4, C), dtype=gdt, device=DEV)
+    ops.conv_gather(ConvSpec([(2 - dh, 2 - dw, 0) for dh, dw, _ in taps9], C, wd, C, C), d_pad, (1, 1, m, C),
+                    (m * C, (W + 4) * C, C), lin, (1, m), None, True, linear=True)
+    assert torch.equal(lin[:, :H + 2, :W + 2], box)
+
+    drop = ((torch.rand((B, C), generator=g) < 0.9).float() / 0.9).to(DEV)
+    common = (raw, st, gamma, beta, drop, gdt, True, 1, _lib.PAD_REFLECT, False)
+    gy_a, sums_a = ops.inorm_bwd_reduce(box, None, *common)
+    gy_b, sums_b = ops.inorm_bwd_reduce(lin, None, *common, gsrc_slack=2)
+    assert torch.equal(gy_a, gy_b) and rel_l2(sums_b, sums_a) < 1e-5
