@@ -508,6 +508,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 int validate_conv_desc(const fnst_conv_desc* d);
+bool rowconv_eligible(const fnst_conv_desc* d);                        // rowconv_tc.cu
+int rowconv_tc(const fnst_conv_desc* d, int device, cudaStream_t st);
 
 template <int BLOCK_N, bool PAIR>
 static int launch_conv_tc(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const ConvTcParams& p, int num_sms,
@@ -571,6 +573,8 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   }
   FNST_DEVICE(device);
   cudaStream_t st = (cudaStream_t)stream;
+  // 3x3 over 64 input channels with few outputs: the row-streaming kernel (resident weights, each input row staged once)
+  if (rowconv_eligible(d)) return rowconv_tc(d, device, st);
 
   ConvTcParams p;
   memset(&p, 0, sizeof(p));

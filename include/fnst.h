@@ -98,7 +98,8 @@ int fnst_version(void);
 const char* fnst_last_error(void);
 /* Tuning knobs of the tensor-core kernels (measurement tooling; defaults are the measured best):
  * "conv_block_n" (0 = heuristic), "conv_pair" (0/1: cta_group::2 CTA pairs), "conv_stage_out" (0/1: shared-memory tile + TMA
- * store epilogue for one-tile-per-CTA launches), "wgrad_waves_x2", "wgrad_bn" (0 = widest), "pdl" (0/1),
+ * store epilogue for one-tile-per-CTA launches), "conv_rowstream" (0/1: row-streaming kernel with resident weights for 3x3
+ * convolutions over 64 input channels with 64 / 128 outputs and no statistics), "wgrad_waves_x2", "wgrad_bn" (0 = widest), "pdl" (0/1),
  * "inorm_bwd_blocks" (1/2 resident blocks per SM of the InstanceNorm backward reduce kernel), "resize_staged" (0/1).
  * Returns 0, or -1 for an unknown name. */
 int fnst_set_tuning(const char* name, int value);

@@ -22,7 +22,7 @@ def knob(name, value):
 @pytest.fixture
 def restore_knobs():
     yield
-    for k, v in (("conv_block_n", 0), ("conv_pair", 1), ("pdl", 1), ("dbg_mode", 0)):
+    for k, v in (("conv_block_n", 0), ("conv_pair", 1), ("pdl", 1), ("dbg_mode", 0), ("conv_rowstream", 1)):
         knob(k, v)
 
 
@@ -122,3 +122,47 @@ def test_zero_arena_semantics():
     assert t1.data_ptr() % 16 == 0 and t2.data_ptr() % 16 == 0
     with pytest.raises(RuntimeError):
         a.take(64)
+
+
+@pytest.mark.parametrize("form", ["forward", "dgrad"])
+@pytest.mark.parametrize("cout", [64, 128])
+@pytest.mark.parametrize("shape", [(2, 37, 45), (1, 128, 130), (3, 20, 300), (4, 256, 256)])
+def test_row_streaming_conv_matches_gather_gemm(shape, cout, form, restore_knobs):
+    """Row-streaming 3x3 kernel (rowconv_tc.cu: resident weights, each input row staged once, taps = address shifts) against
+    the generic gather-GEMM on the same descriptor -- VGG conv1_2 / conv2_1 forward (bias + ReLU, zero padding by TMA) and the
+    conv1_2 data-gradient form (reversed taps, addend, ReLU mask, bf16) -- and against float64 on the small shape.  Both kernels
+    accumulate the same 576 products in fp32 (in a different order) and round once to 16 bits."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(31)
+    dt = torch.float16 if form == "forward" else torch.bfloat16
+    a = torch.randn((B, H, W, 64), generator=g).to(dt).to(DEV)
+    wt = (torch.randn((cout, 9 * 64), generator=g) / 24).to(dt).to(DEV)
+    taps = engine.taps_kxk(3, origin=-1)
+    if form == "forward":
+        spec = ConvSpec(taps, 64, wt, cout, cout, bias=torch.randn(cout, generator=g).to(DEV), relu=True)
+    else:
+        addend = torch.randn((B, H, W, cout), generator=g).to(dt).to(DEV)
+        mask = torch.randn((B, H, W, cout), generator=g).to(torch.float16).to(DEV)
+        spec = ConvSpec(backward._neg(taps), 64, wt, cout, cout, addend=addend, mask=mask)
+    outs = []
+    for rowstream in (1, 0):
+        knob("conv_rowstream", rowstream)
+        out = torch.full((B, H, W, cout), float("nan"), dtype=dt, device=DEV)
+        ops.conv_gather(spec, a, (B, H, W, 64), engine._nhwc_strides(a), out, (H, W), None, True)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.isfinite(outs[0]).all()
+    err = (outs[0].double() - outs[1].double()).abs().max().item()
+    scale = outs[1].double().abs().max().item()
+    assert err <= (2.0 ** -9 if dt == torch.float16 else 2.0 ** -6) * scale, (err, scale)        # at most ~2 units in the last place of the largest value
+    assert float((outs[0].double() - outs[1].double()).norm() / outs[1].double().norm()) < (2e-4 if dt == torch.float16 else 2e-3)
+    if H * W <= 2000:
+        x = a.double().cpu().permute(0, 3, 1, 2)
+        w4 = wt.double().cpu().view(cout, 3, 3, 64).permute(0, 3, 1, 2)
+        if form == "forward":
+            ref = F.relu(F.conv2d(x, w4, spec.bias.double().cpu(), padding=1))
+        else:
+            ref = F.conv2d(x, w4.flip(2, 3), padding=1)
+            ref = (ref + addend.double().cpu().permute(0, 3, 1, 2)) * (mask.cpu().permute(0, 3, 1, 2) > 0)
+        ref = ref.permute(0, 2, 3, 1)
+        assert float((outs[0].double().cpu() - ref).norm() / ref.norm()) < (1e-3 if dt == torch.float16 else 6e-3)
