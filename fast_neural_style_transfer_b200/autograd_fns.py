@@ -55,6 +55,26 @@ def gram(feat: torch.Tensor) -> torch.Tensor:
     return ops.gram(f, use_tc=_gram_tc_ok(f))
 
 
+# ---- zero-copy gradient hand-off to a graphed VGG backward -------------------------------------------------------
+#
+# The captured VGG backward reads the feature-map gradients from its own static input buffers.  A loss node whose input IS a
+# feature map of such a graph (recognised by the address of the graph's static output) claims the matching input buffer when
+# it runs forward and writes its gradient straight into it in backward: autograd then hands the graph a tensor that already
+# lives at the static address, and the 63 MB of device copies per step (4 x 256 x 256) disappear.  A buffer can be claimed
+# once per forward of the graph -- a second consumer of the same feature map gets None and allocates as before, so autograd's
+# gradient accumulation never sees two aliases of one buffer.
+
+GRAD_SLOTS: dict = {}        # data_ptr of a graphed feature map -> (weakref to its VGGGraph, feature index)
+
+
+def _claim_grad_slot(f_nhwc: torch.Tensor):
+    ent = GRAD_SLOTS.get(f_nhwc.data_ptr())
+    if ent is None:
+        return None
+    state = ent[0]()
+    return None if state is None else state.claim_grad_slot(ent[1], f_nhwc)
+
+
 # ---- sum of squared differences ----------------------------------------------------------------------
 
 def _sse_forward(a: torch.Tensor, b: torch.Tensor, scale: float) -> torch.Tensor:
@@ -78,13 +98,14 @@ class _SSE(torch.autograd.Function):
         an, bn = _match_layout(a.detach(), b.detach())
         ctx.save_for_backward(an, bn)
         ctx.is_feat, ctx.scale = a.dim() == 4, scale
+        ctx.slot = _claim_grad_slot(an) if a.dim() == 4 else None
         return _sse_forward(an, bn, scale)
 
     @staticmethod
     def backward(ctx, g):
         from . import backward
         an, bn = ctx.saved_tensors
-        da = backward.sse_backward(an, bn, g, ctx.scale)
+        da = backward.sse_backward(an, bn, g, ctx.scale, out=ctx.slot)
         return (da.permute(0, 3, 1, 2) if ctx.is_feat else da), None, None
 
 
@@ -121,6 +142,7 @@ class _StyleLoss(torch.autograd.Function):
         coefs = [w / (c * c) for w, c in zip(weights, cs)]
         grams, out = _style_forward(fs, targets, coefs)
         ctx.fs, ctx.grams, ctx.targets, ctx.coefs = fs, grams, targets, coefs
+        ctx.slots = [_claim_grad_slot(f) for f in fs]
         return out
 
     @staticmethod
@@ -128,9 +150,9 @@ class _StyleLoss(torch.autograd.Function):
         from . import backward
         scale = g.reshape(1).float()
         outs = []
-        for f, gram_, t, coef in zip(ctx.fs, ctx.grams, ctx.targets, ctx.coefs):
+        for f, gram_, t, coef, slot in zip(ctx.fs, ctx.grams, ctx.targets, ctx.coefs, ctx.slots):
             s = ops.gram_diff_sym(gram_, t, scale, 2.0 * coef, backward.grad_dtype_of(f.dtype))     # d/dG of coef*sum(G-T)^2 is 2*coef*(G-T); dF = F (dG + dG^T)
-            outs.append(backward.gram_apply(f, s).permute(0, 3, 1, 2))
+            outs.append(backward.gram_apply(f, s, out=slot).permute(0, 3, 1, 2))
         ctx.fs = ctx.grams = None
         return (None, None, None) + tuple(outs)
 
@@ -321,8 +343,18 @@ def stylenet_graphed_apply(state: StyleNetTrainGraph, x, drops, params):
     return _StyleNetGraphed.apply(state, x, drops, *params)
 
 
+def _storage_refs(t: torch.Tensor) -> int:
+    """Number of tensors (views included) that share t's storage, plus one for the temporary handle of this call."""
+    return torch._C._storage_Use_Count(t.untyped_storage()._cdata)
+
+
 class VGGGraph:
-    """Graphed VGG feature stack for one input shape: forward (with or without tape) and data-gradient backward."""
+    """Graphed VGG feature stack for one input shape: forward (with or without tape) and data-gradient backward.
+
+    forward(x, alias=True) returns VIEWS of the graph's static output buffer (no 67 MB device copy per call at 4 x 256 x 256);
+    the module only does so while `outputs_free()` -- no tensor handed out by an earlier call is still alive -- and otherwise
+    replays another instance of the graph (the reference loop keeps last step's features in its local variables until the
+    new ones are assigned, so two instances alternate) or, with all instances taken, falls back to a copy."""
 
     def __init__(self, plan, x: torch.Tensor, with_tape: bool):
         from . import graphs
@@ -330,6 +362,8 @@ class VGGGraph:
         self.tape: dict = {}
         self.with_tape = with_tape
         self.in_flight = _InFlight()
+        self.grad_slots: dict = {}          # feature index -> static input of the most recently captured backward graph
+        self.claimed: set = set()
 
         def fwd(x_):
             # the five feature maps live in ONE flat static buffer, so handing them to the caller is one device copy, not five
@@ -349,9 +383,31 @@ class VGGGraph:
 
         self.fwd = graphs.GraphedPlan(fwd, [x.float().contiguous()])
         self.bwd = {}
+        plan._out_buffers = None            # the plan must not keep views of this graph's output alive (see outputs_free)
+        self._refs0 = _storage_refs(self.fwd.outputs)
+        offs = 0
+        for i, n in enumerate(self.numels):
+            GRAD_SLOTS[self.fwd.outputs.data_ptr() + offs * self.fwd.outputs.element_size()] = (weakref.ref(self), i)
+            offs += n
 
-    def forward(self, x):
-        flat = self.fwd(x).clone()
+    def outputs_free(self) -> bool:
+        """True when nothing outside this object references the static output buffer any more."""
+        return _storage_refs(self.fwd.outputs) <= self._refs0
+
+    def claim_grad_slot(self, i: int, f_nhwc: torch.Tensor):
+        """Static gradient-input buffer of feature i of the captured backward, once per forward (None: no capture yet,
+        already claimed, or a different geometry)."""
+        slot = self.grad_slots.get(i)
+        if slot is None or i in self.claimed or tuple(slot.shape) != tuple(f_nhwc.shape):
+            return None
+        self.claimed.add(i)
+        return slot
+
+    def forward(self, x, alias: bool = False):
+        self.claimed.clear()
+        flat = self.fwd(x)
+        if not alias:
+            flat = flat.clone()
         return tuple(v.view(s) for v, s in zip(torch.split(flat, self.numels), self.shapes))
 
     def backward(self, dfeats):
@@ -364,21 +420,23 @@ class VGGGraph:
                 full = [next(it) if used else None for used in pattern]
                 return backward.vgg_backward(self.plan, self.tape, full)
             self.bwd[pattern] = graphs.GraphedPlan(bwd, live)
+            it = iter(self.bwd[pattern].static_inputs)
+            self.grad_slots = {i: next(it) for i, used in enumerate(pattern) if used}
         return self.bwd[pattern](*live).clone()
 
 
 class _VGGGraphed(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, state, x):
+    def forward(ctx, state, x, alias):
         ctx.state = state
         state.in_flight.begin(ctx)
-        return state.forward(x.detach())
+        return state.forward(x.detach(), alias)
 
     @staticmethod
     def backward(ctx, *dfeats):
         ctx.state.in_flight.check(ctx, "VGG19 backward")
-        return None, ctx.state.backward(dfeats)
+        return None, ctx.state.backward(dfeats), None
 
 
-def vgg_graphed_apply(state: VGGGraph, x) -> List[torch.Tensor]:
-    return list(_VGGGraphed.apply(state, x))
+def vgg_graphed_apply(state: VGGGraph, x, alias: bool = False) -> List[torch.Tensor]:
+    return list(_VGGGraphed.apply(state, x, alias))

@@ -529,21 +529,24 @@ def gram_backward(f: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
     return gram_apply(f, (dg + dg.transpose(1, 2)).to(grad_dtype_of(f.dtype)).contiguous())
 
 
-def gram_apply(f: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+def gram_apply(f: torch.Tensor, s: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dF[n] = F[n] S[n] for per-image symmetric factors S (B,C,C) in the gradient dtype of the features (fp16
-    features are multiplied as bf16: kind::f16 MMAs take one 16-bit format, and the products exceed fp16's range)."""
+    features are multiplied as bf16: kind::f16 MMAs take one 16-bit format, and the products exceed fp16's range).
+    out: write the result here (same shape, dtype of s)."""
     B, H, W, C = f.shape
     if f.dtype != s.dtype:
         f = ops.cast(f, s.dtype)
-    out = torch.empty_like(f)
+    if out is None:
+        out = torch.empty_like(f)
+    assert out.shape == f.shape and out.dtype == f.dtype and out.is_contiguous()
     use_tc = f.dtype != torch.float32 and C % 64 == 0
     spec = ConvSpec([(0, 0, 0)], C, s, C, C, per_image_weights=True)      # one launch, image n multiplies by s[n]
     ops.conv_gather(spec, f, (B, H, W, C), _nhwc_strides(f), out, (H, W), None, use_tc)
     return out
 
 
-def sse_backward(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor, coef: float = 1.0) -> torch.Tensor:
-    return ops.sse_bwd(a, b, g.reshape(1).float(), grad_dtype_of(a.dtype), coef=coef)
+def sse_backward(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor, coef: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return ops.sse_bwd(a, b, g.reshape(1).float(), grad_dtype_of(a.dtype), coef=coef, out=out)
 
 
 def tv_backward(x: torch.Tensor, g: torch.Tensor, coef: float = 1.0) -> torch.Tensor:

@@ -92,6 +92,8 @@ class VGG19(nn.Module):
             self.__dict__["_plan_cache"] = cache
         return cache[1]
 
+    MAX_GRAPH_INSTANCES = 3          # captured copies of one (shape, tape) graph that may hand out views of their outputs
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("VGG19 (B200 drop-in) needs CUDA tensors: there is no CPU fallback")
@@ -101,17 +103,28 @@ class VGG19(nn.Module):
         if graphs.enabled() and small and not torch.cuda.is_current_stream_capturing():
             cache = self.__dict__.setdefault("_graphs", {})
             key = (id(plan), tuple(x.shape), x.device.index, need_grad)
-            state = cache.get(key)
-            if state is None:
+            states = cache.get(key)
+            if states is None:
                 for k in [k for k in cache if k[0] != id(plan)] if len(cache) < 8 else list(cache):
                     del cache[k]
-                state = cache[key] = autograd_fns.VGGGraph(plan, x, with_tape=need_grad)
-            if not need_grad:
-                feats = state.forward(x.detach())
-            elif not state.in_flight.busy():
-                feats = autograd_fns.vgg_graphed_apply(state, x)
+                states = cache[key] = []
+            # An instance whose earlier outputs are all dead (and whose tape is not awaiting a backward) hands out views of its
+            # static output buffer: no copy.  The reference loop still holds last step's features while it calls vgg() again,
+            # so a second instance is captured and the two alternate; beyond MAX_GRAPH_INSTANCES the output is copied out.
+            state = next((s for s in states if not s.in_flight.busy() and s.outputs_free()), None)
+            alias = True
+            if state is None and len(states) < self.MAX_GRAPH_INSTANCES:
+                state = autograd_fns.VGGGraph(plan, x, with_tape=need_grad)
+                states.append(state)
+            if state is None:
+                alias = False
+                state = next((s for s in states if not s.in_flight.busy()), None)
+            if state is None:
+                feats = autograd_fns.vgg_apply(plan, x)      # every instance awaits its backward (vgg(a), vgg(b), ...): per-call tape
+            elif not need_grad:
+                feats = state.forward(x.detach(), alias)
             else:
-                feats = autograd_fns.vgg_apply(plan, x)      # vgg(a) and vgg(b) both awaiting backward: per-call tape
+                feats = autograd_fns.vgg_graphed_apply(state, x, alias)
         elif need_grad:
             feats = autograd_fns.vgg_apply(plan, x)
         else:

@@ -426,10 +426,11 @@ def maxpool2_bwd(inp, gout, extra):
     return gin
 
 
-def sse_bwd(a, b, scale, gdtype, relu_mask=False, coef: float = 1.0):
-    """2*coef*scale*(a-b) (b broadcast); scale is a 1-element fp32 CUDA tensor, coef a host constant."""
+def sse_bwd(a, b, scale, gdtype, relu_mask=False, coef: float = 1.0, out: Optional[torch.Tensor] = None):
+    """2*coef*scale*(a-b) (b broadcast); scale is a 1-element fp32 CUDA tensor, coef a host constant.  out: write here."""
     assert a.is_contiguous() and b.is_contiguous() and scale.dtype == torch.float32
-    da = torch.empty(a.shape, dtype=gdtype, device=a.device)
+    da = torch.empty(a.shape, dtype=gdtype, device=a.device) if out is None else out
+    assert da.dtype == gdtype and da.is_contiguous() and da.shape == a.shape
     dev, st = _ctx(a)
     check(lib.fnst_sse_bwd(_ptr(a), _ptr(b), a.numel(), b.numel(), dt(a.dtype), dt(b.dtype), _ptr(scale), float(coef), _ptr(da),
                            dt(gdtype), int(relu_mask), dev, st), "sse_bwd")

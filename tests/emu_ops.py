@@ -376,11 +376,14 @@ def relu_mask(g, extra, act):
     return (v * (act.double() > 0)).to(g.dtype)
 
 
-def sse_bwd(a, b, scale, gdtype, relu_mask=False, coef=1.0):
+def sse_bwd(a, b, scale, gdtype, relu_mask=False, coef=1.0, out=None):
     d = 2.0 * coef * scale.double()[0] * (a.double().reshape(-1, b.numel()) - b.double().reshape(1, -1))
     d = d.view(a.shape)
     if relu_mask:
         d = d * (a.double() > 0)
+    if out is not None:
+        out.copy_(d.to(gdtype))
+        return out
     return d.to(gdtype)
 
 

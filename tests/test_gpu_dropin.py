@@ -163,3 +163,49 @@ def test_pinned_host_batch_is_pipelined_and_equal_to_the_device_path(dropin):
     assert rel_l2(got, ref) < 1e-2 and rel_l2(want, ref) < 1e-2
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net(x)                                                             # pageable host memory is still refused
+
+
+def test_vgg_graph_hands_out_views_and_takes_gradients_in_place(dropin):
+    """Zero-copy hand-offs around the captured VGG graphs (autograd_fns.VGGGraph): the features are views of the graph's static
+    output (two instances alternate while the caller still holds last step's features, as the reference loop does,
+    train.py:178-185); from the second backward on the loss nodes write their gradients straight into the captured backward's
+    input buffers.  Values: features of earlier steps stay intact while held, and every step's input gradient matches the
+    oracle's autograd."""
+    from fast_neural_style_transfer_b200 import autograd_fns
+    _, mv, ll = dropin
+    vp = O.make_vgg_params(seed=1)
+    vgg = mv.VGG19().to(DEV)
+    vgg.load_state_dict(vp)
+    vgg.precision = "fp32"
+    vgg.eval()
+    sty = O.make_image(1, 32, 32, seed=78, normalized=True)
+    with torch.no_grad():
+        targets = [ll.gram_matrix(f).squeeze(0) for f in vgg(sty.to(DEV))]
+    rt = O.style_targets(vp, sty)
+    ptrs, kept = [], []
+    feats = None
+    for step in range(4):
+        content = O.make_image(2, 32, 32, seed=100 + step, normalized=True)
+        x = O.make_image(2, 32, 32, seed=200 + step, normalized=True)
+        xd = x.to(DEV).requires_grad_(True)
+        with torch.no_grad():
+            cf = vgg(content.to(DEV))
+        feats = vgg(xd)                                  # (the previous step's `feats` is alive during this call)
+        ptrs.append(feats[0].data_ptr())
+        loss = 1000.0 * ll.content_loss(feats, cf) + ll.style_loss(feats, targets)
+        state = next(s for lst in vgg._graphs.values() for s in lst if s.with_tape and s.fwd.outputs.data_ptr() == feats[0].data_ptr())
+        if step >= 2:                                    # this instance has captured its backward: all four gradient slots are claimed
+            assert state.claimed == {0, 1, 2, 4}
+        loss.backward()
+        xr = x.clone().requires_grad_(True)
+        rf = O.vgg_forward(vp, xr)
+        (1000.0 * O.content_loss(rf, O.vgg_forward(vp, content)) + O.style_loss(rf, rt)).backward()
+        assert rel_l2(xd.grad, xr.grad) < 2e-3, step                 # (a stale or doubly-written gradient buffer would be an O(1) error)
+        for i in (0, 2, 4):
+            assert rel_l2(feats[i], rf[i]) < 1e-4
+        kept.append((feats[2], rf[2].detach()))
+        if len(kept) > 1:                                # the features of the previous step, still referenced: untouched by this replay
+            assert rel_l2(kept[-2][0], kept[-2][1]) < 1e-4
+            kept.pop(0)
+    taped = [s for lst in vgg._graphs.values() for s in lst if s.with_tape]
+    assert len(taped) == 2 and ptrs[0] == ptrs[2] and ptrs[1] == ptrs[3] and ptrs[0] != ptrs[1]
