@@ -131,23 +131,92 @@ def _style_forward(fs, targets, coefs):
     return grams, out
 
 
+class _StyleLossGraph:
+    """Forward and backward of the fused style loss as two CUDA graphs for ONE set of operand addresses (feature maps, targets,
+    gradient slots).  The style backward runs right after the host-synchronising NaN check of the training loop
+    (train.py:193-200) with the GPU idle: launched kernel by kernel it costs ~0.2 ms of host time (three Gram-difference
+    kernels, three gather-GEMMs with their descriptors and tensor maps); as a captured graph it is one 4-byte copy of the
+    incoming gradient scalar plus one replay.  The cache key holds every address the captured kernels read, so a replay always
+    reads the tensors of the current call."""
+
+    def __init__(self, fs, targets, coefs):
+        from . import graphs
+        # (no reference to the feature maps is kept: they are views of a VGG graph's output buffer, whose "nobody holds my
+        #  outputs" test must not see this cache; the key re-establishes on every call that the same addresses are current)
+        self.targets, self.coefs = list(targets), list(coefs)
+        self.device = fs[0].device
+        self.g_static = torch.zeros(1, dtype=torch.float32, device=self.device)
+        fs = list(fs)
+        self.fwd = graphs.GraphedPlan(lambda: _style_forward(fs, self.targets, self.coefs), [], device=self.device)
+        self.grams, self.out = self.fwd.outputs
+        self.bwd, self.bwd_slots = None, None
+        del fs
+
+    def forward(self) -> torch.Tensor:
+        self.fwd()
+        return self.out.clone()
+
+    def backward(self, g: torch.Tensor, slots, fs) -> list:
+        from . import backward, graphs
+        key = tuple(None if t is None else t.data_ptr() for t in slots)
+        if self.bwd is None or self.bwd_slots != key:
+            def bwd():
+                outs = []
+                for f, gram_, t, coef, slot in zip(fs, self.grams, self.targets, self.coefs, slots):
+                    s = ops.gram_diff_sym(gram_, t, self.g_static, 2.0 * coef, backward.grad_dtype_of(f.dtype))
+                    outs.append(backward.gram_apply(f, s, out=slot))
+                return outs
+            self.g_static.copy_(g.reshape(1))
+            self.bwd, self.bwd_slots = graphs.GraphedPlan(bwd, [], device=self.device), key
+        self.g_static.copy_(g.reshape(1))
+        return self.bwd()
+
+
+_STYLE_GRAPHS: dict = {}
+
+
+def _style_graph(fs, targets, coefs):
+    """Cached _StyleLossGraph for exactly these operand addresses, or None when graphs are off / a capture is in progress."""
+    from . import graphs
+    if not graphs.enabled() or torch.cuda.is_current_stream_capturing():
+        return None
+    key = (tuple((f.data_ptr(), tuple(f.shape), f.dtype) for f in fs), tuple((t.data_ptr(), tuple(t.shape)) for t in targets),
+           tuple(coefs), fs[0].device.index)
+    state = _STYLE_GRAPHS.get(key)
+    if state is None:
+        if len(_STYLE_GRAPHS) >= 8:
+            _STYLE_GRAPHS.clear()
+        # (the graph keeps the tensors it was captured on alive, so their addresses cannot be re-used by other tensors)
+        state = _STYLE_GRAPHS[key] = _StyleLossGraph(fs, targets, coefs)
+    return state
+
+
 class _StyleLoss(torch.autograd.Function):
     """sum_l w_l * SSE(gram(F_l), T_l) / c_l^2 over the given layers as ONE autograd node (losses/losses.py:15-44).
     Backward per layer: one kernel builds S = g*w/c^2 * 2*((G-T) + (G-T)^T)/... in the gradient dtype, one batched 1x1
-    gather-GEMM computes dF = F S -- instead of ~10 autograd nodes per layer on the critical path after the NaN check."""
+    gather-GEMM computes dF = F S -- instead of ~10 autograd nodes per layer on the critical path after the NaN check.
+    Feature maps at stable addresses (views of a captured VGG graph's output) run both passes as CUDA graphs."""
 
     @staticmethod
     def forward(ctx, weights, targets, cs, *feats):
         fs = [_as_nhwc(f.detach()) for f in feats]
         coefs = [w / (c * c) for w, c in zip(weights, cs)]
-        grams, out = _style_forward(fs, targets, coefs)
-        ctx.fs, ctx.grams, ctx.targets, ctx.coefs = fs, grams, targets, coefs
         ctx.slots = [_claim_grad_slot(f) for f in fs]
+        ctx.graph = _style_graph(fs, targets, coefs) if all(f.data_ptr() in GRAD_SLOTS for f in fs) else None
+        ctx.fs = fs
+        if ctx.graph is not None:
+            return ctx.graph.forward()
+        grams, out = _style_forward(fs, targets, coefs)
+        ctx.grams, ctx.targets, ctx.coefs = grams, targets, coefs
         return out
 
     @staticmethod
     def backward(ctx, g):
         from . import backward
+        if ctx.graph is not None:
+            outs = ctx.graph.backward(g, ctx.slots, ctx.fs)
+            ctx.fs = None
+            return (None, None, None) + tuple(o.permute(0, 3, 1, 2) for o in outs)
         scale = g.reshape(1).float()
         outs = []
         for f, gram_, t, coef, slot in zip(ctx.fs, ctx.grams, ctx.targets, ctx.coefs, ctx.slots):

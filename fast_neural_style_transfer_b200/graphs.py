@@ -22,8 +22,9 @@ def enabled() -> bool:
 class GraphedPlan:
     """fn(*static_inputs) -> (tensor | tuple of tensors | dict...) captured as one CUDA graph."""
 
-    def __init__(self, fn: Callable, example_inputs: Sequence[torch.Tensor], warmup: int = 2, pool=None):
-        dev = example_inputs[0].device
+    def __init__(self, fn: Callable, example_inputs: Sequence[torch.Tensor], warmup: int = 2, pool=None, device=None):
+        """example_inputs may be empty (a plan that reads and writes fixed addresses only); `device` is then required."""
+        dev = example_inputs[0].device if example_inputs else torch.device(device)
         self.static_inputs: List[torch.Tensor] = [t.detach().clone() for t in example_inputs]
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
