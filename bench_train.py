@@ -38,7 +38,7 @@ def run(args, wl, net, rank, world, dev, peaks):
                          else (torch.optim.Adam, torch.nn.utils.clip_grad_norm_))
     opt = adam_cls(net.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=80000, eta_min=1e-7)
-    dp = parallel.GradientAllReduce(net, world) if world > 1 else None
+    dp = parallel.GradientAllReduce(net, world, overlap=os.environ.get("FNST_DP_OVERLAP", "0") != "0") if world > 1 else None
     torch.manual_seed(1000 + rank)                                                      # per-rank dropout streams
     g = torch.Generator().manual_seed(1234 + rank)
     n_host = 4

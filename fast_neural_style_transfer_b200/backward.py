@@ -173,14 +173,34 @@ def _assembly(names: Sequence[str], shapes: Sequence[torch.Size], tc: bool, devi
     return ent
 
 
-def assemble_gradients(core: dict, names: Sequence[str], params: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """Flat fp32 gradient of all parameters (in `names` order) from the staging / sums buffers of `stylenet_backward_core`."""
+def assemble_gradients(core: dict, names: Sequence[str], params: Dict[str, torch.Tensor], flat: Optional[torch.Tensor] = None,
+                       first: Optional[str] = None, last: Optional[str] = None) -> torch.Tensor:
+    """Flat fp32 gradient of all parameters (in `names` order) from the staging / sums buffers of `stylenet_backward_core`.
+    first / last: assemble only the contiguous run of parameters from `first` up to (not including) `last` into the given
+    `flat` (bucket-wise assembly while later stages of the backward still run; `bucket_bounds` names the cuts)."""
     asm = _assembly(names, [params[n].shape for n in names], core["tc"], core["staging"].device)
-    flat = torch.empty(asm["total"], dtype=torch.float32, device=core["staging"].device)
-    ops.gather_index(core["staging"], asm["idx"], flat)
-    entries = [(src, c, asm["offsets"][ln + ".weight"], asm["offsets"][ln + ".bias"]) for ln, (src, c) in core["norm_sums"].items()]
-    ops.affine_grads(core["sums"], entries, core["batch"], flat)
+    if flat is None:
+        flat = torch.empty(asm["total"], dtype=torch.float32, device=core["staging"].device)
+    lo = 0 if first is None else asm["offsets"][first]
+    hi = asm["total"] if last is None else asm["offsets"][last]
+    ops.gather_index(core["staging"], asm["idx"][lo:hi], flat[lo:hi])
+    entries = [(src, c, asm["offsets"][ln + ".weight"], asm["offsets"][ln + ".bias"]) for ln, (src, c) in core["norm_sums"].items()
+               if lo <= asm["offsets"][ln + ".weight"] < hi]
+    if entries:
+        ops.affine_grads(core["sums"], entries, core["batch"], flat)
     return flat
+
+
+# Stage cuts of the backward for bucket-wise gradient exchange (parallel.GradientAllReduce): after residual block 2 every
+# gradient from `res_blocks.2` to the end of the parameter list is final (60 % of the bytes), after block 0 those of blocks 0
+# and 1; conv1 / conv2 and their norms (2.6 %) come with the last stage.  Parameter order = module order (models/model.py:27-47).
+STAGE_CUTS = (2, 0)
+
+
+def bucket_bounds(stage: int):
+    """(first, last) parameter names delimiting the gradients completed by stage 0, 1, 2 of the staged backward."""
+    return [("res_blocks.2.conv1.conv.weight", None), ("res_blocks.0.conv1.conv.weight", "res_blocks.2.conv1.conv.weight"),
+            (None, "res_blocks.0.conv1.conv.weight")][stage]
 
 
 def _final_dgrad_layout(wt):                                              # (3, 32, 9, 9) -> (64, 9*64)
@@ -232,6 +252,18 @@ def stylenet_backward(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor)
 def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor) -> dict:
     """Everything of the backward pass except the final assembly: returns the staging buffer (packed weight gradients), the
     InstanceNorm sums buffer and where each norm layer's sums live -- static tensors when captured in a CUDA graph."""
+    gen = stylenet_backward_stages(plan, tape, dy, cuts=())
+    try:
+        while True:
+            next(gen)
+    except StopIteration as done:
+        return done.value
+
+
+def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Tensor, cuts: Sequence[int] = STAGE_CUTS):
+    """Generator form of the backward: yields the (partially filled) result dict after the residual blocks listed in `cuts`
+    (weight-gradient side stream joined at every yield, so each stage can be captured as its own CUDA graph), returns it at
+    the end.  Between two stages the caller may assemble and exchange the gradients that are already final."""
     p = plan.params
     gdt = grad_dtype(plan.precision)
     tc = plan.use_tc
@@ -414,6 +446,10 @@ def stylenet_backward_core(plan: "engine.StyleNetPlan", tape: dict, dy: torch.Te
             wgrad(ConvSpec(taps9, 256, None, 256, 256, tag=f"wgrad_res{i}a"), cur, trunk_w[i], pdims, d_raw_a, (H2, W2), res_db[2 * i], g_pad=Z)
         gsrc = res_dgrad(d_raw_a, 2 * i)
         extra = g_out
+        if i in cuts:
+            if side_stream is not None:
+                main_stream.wait_stream(side_stream)         # the stage's weight gradients are complete when the stage ends
+            yield dict(staging=staging, sums=arena.buf, norm_sums=dict(norm_sums), batch=B, tc=tc)
 
     # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
     d_raw2, _ = inorm_backward("norm2", gsrc, extra, tape["raw2"], tape["st2"], None, True, 1, PAD_REFLECT, gsrc_slack=Z)

@@ -213,7 +213,7 @@ class StyleTransferNet(nn.Module):
     # plan cache (packed weights) is derived state: never pickled, rebuilt when parameters change
     def __getstate__(self):
         state = self.__dict__.copy()
-        for k in ("_plan_cache", "_graphs", "_train_graphs", "_named_cache", "_host_streams"):
+        for k in ("_plan_cache", "_graphs", "_train_graphs", "_named_cache", "_host_streams", "_fnst_bucket_hook"):
             state.pop(k, None)
         return state
 
@@ -409,6 +409,7 @@ class StyleTransferNet(nn.Module):
                         cache.clear()
                     state = cache[key] = autograd_fns.StyleNetTrainGraph(dict(named), precision, x, drops)
                 if not busy:
+                    state.bucket_hook = self.__dict__.get("_fnst_bucket_hook")       # set by parallel.GradientAllReduce
                     return autograd_fns.stylenet_graphed_apply(state, x, drops, params)
                 # an earlier forward of this graph still waits for its backward (gradient accumulation, two losses on two
                 # inputs): the captured tape holds ONE forward, so this call takes the eager per-call-tape path below

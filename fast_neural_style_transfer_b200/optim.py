@@ -48,10 +48,16 @@ class _PtrList:
         self.numels = None
         self.n = 0
 
-    def update(self, tensors: List[torch.Tensor], what: str):
-        ptrs = tuple(t.data_ptr() for t in tensors)
-        key = (ptrs, tuple(t.numel() for t in tensors), tuple(t.dtype for t in tensors), all(t.is_contiguous() for t in tensors),
-               tensors[0].device)
+    def update(self, tensors: List[torch.Tensor], what: str, stable: bool = False):
+        """stable: the tensors are long-lived objects whose geometry cannot change behind their identity (parameters, Adam
+        moments): the key is the tuple of object ids plus addresses (`.data = ...` swaps storage under a stable object) --
+        two cheap calls per tensor instead of four.  Gradients are re-created every step, so they are keyed in full."""
+        ptrs = tuple([t.data_ptr() for t in tensors])
+        if stable:
+            key = (ptrs, tuple([id(t) for t in tensors]))
+        else:
+            key = (ptrs, tuple([t.numel() for t in tensors]), tuple([t.dtype for t in tensors]),
+                   all([t.is_contiguous() for t in tensors]), tensors[0].device)
         if key != self.key:
             ops._ctx(tensors[0])                     # raises for CPU tensors: there is no CPU fallback
             for t in tensors:
@@ -199,10 +205,10 @@ class Adam(torch.optim.Optimizer):
             lists = self._lists.get(gi)
             if lists is None:
                 lists = self._lists[gi] = (_PtrList(), _PtrList(), _PtrList(), _PtrList())
-            pl = lists[0].update(params, "Adam(params)")
+            pl = lists[0].update(params, "Adam(params)", stable=True)
             gl = lists[1].update([p.grad for p in params], "Adam(grads)")
-            ml = lists[2].update([self.state[p]["exp_avg"] for p in params], "Adam(exp_avg)")
-            vl = lists[3].update([self.state[p]["exp_avg_sq"] for p in params], "Adam(exp_avg_sq)")
+            ml = lists[2].update([self.state[p]["exp_avg"] for p in params], "Adam(exp_avg)", stable=True)
+            vl = lists[3].update([self.state[p]["exp_avg_sq"] for p in params], "Adam(exp_avg_sq)", stable=True)
             if any(a != b for a, b in zip(pl.numels, gl.numels)):
                 raise RuntimeError("Adam (B200 path): gradient shapes do not match their parameters")
             if grad_scale is not None and (grad_scale.device != params[0].device or grad_scale.dtype != torch.float32

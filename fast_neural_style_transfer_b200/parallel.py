@@ -47,11 +47,33 @@ def all_finite(value: torch.Tensor, world: int) -> bool:
 class GradientAllReduce:
     """Flat-bucket SUM all-reduce of `module`'s gradients (parameters without a gradient contribute zeros)."""
 
-    def __init__(self, module: torch.nn.Module, world: int):
+    def __init__(self, module: torch.nn.Module, world: int, overlap: bool = False):
+        """overlap: on the drop-in StyleTransferNet (CUDA-graph training path) the exchange is issued bucket by bucket from
+        inside the backward -- the gradients of residual blocks 2-4 and the decoder (60 % of the bytes) as soon as the backward
+        has passed block 2, those of blocks 0-1 after block 0, the encoder's last -- as asynchronous all-reduces on the
+        communicator's stream, so they run under the rest of the backward; `all_reduce()` after `backward()` then only finds
+        the buffer already reduced.  Collectives are issued in the same order on every rank (three per step).
+        Default off: measured on 2 B200s the three stage graphs (weight-gradient branch joined at every cut) cost 0.09 ms per
+        step, more than the ~0.05 ms all-reduce they hide there (profiles/r02_scale.md has the 8-GPU comparison)."""
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         self.world = world
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
+        self._pending: list = []
+        self._reduced = None          # the flat buffer exchanged during the last backward (kept alive so its address stays unique)
+        if hasattr(module, "_resolved_precision"):
+            module.__dict__.pop("_fnst_bucket_hook", None)
+            if overlap and world > 1:
+                module.__dict__["_fnst_bucket_hook"] = self._bucket_ready
+
+    def _bucket_ready(self, flat: torch.Tensor, lo: int, hi: int, last: bool) -> None:
+        """Called by the staged backward when flat[lo:hi] holds final local gradients."""
+        self._pending.append(dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        if last:
+            for work in self._pending:
+                work.wait()                       # the current stream waits for the communicator's stream; the host does not block
+            self._pending = []
+            self._reduced = flat
 
     def _flat_view(self):
         """If every gradient is a view into one contiguous fp32 buffer in parameter order (the CUDA-graph backward
@@ -70,6 +92,10 @@ class GradientAllReduce:
     def all_reduce(self) -> torch.Tensor:
         flat = self._flat_view()
         if flat is not None:
+            if self._reduced is not None and flat.data_ptr() == self._reduced.data_ptr():
+                self._reduced = None               # exchanged bucket by bucket during the backward
+                return flat
+            self._reduced = None
             if self.world > 1:
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM)
             return flat

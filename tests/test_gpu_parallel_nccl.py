@@ -24,7 +24,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, precision, vgg_precision, per_rank, size):
+def _worker(rank, world, port, out_dir, precision, vgg_precision, per_rank, size, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), FNST_VGG19_RANDOM_INIT="1")
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -45,7 +45,7 @@ def _worker(rank, world, port, out_dir, precision, vgg_precision, per_rank, size
         with torch.no_grad():
             targets = [ll.gram_matrix(f).squeeze(0) for f in vgg(sty.to(dev))]
         x = parallel.shard_batch(content, rank, world).to(dev)
-        dp = parallel.GradientAllReduce(net, world)
+        dp = parallel.GradientAllReduce(net, world, overlap=overlap)
         for it in range(2):                                           # second iteration: the CUDA-graph replay path
             y = torch.clamp(net(x), -3, 3)
             with torch.no_grad():
@@ -68,10 +68,12 @@ def _worker(rank, world, port, out_dir, precision, vgg_precision, per_rank, size
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("overlap", [False, True], ids=["one_allreduce", "bucketed_under_backward"])
 @pytest.mark.parametrize("precision,vgg_precision,tol", [("fp32", "fp32", 5e-3), ("fp16", "bf16", 1.5e-1)])
-def test_two_rank_nccl_step_equals_the_global_batch_gradient(tmp_path, precision, vgg_precision, tol):
+def test_two_rank_nccl_step_equals_the_global_batch_gradient(tmp_path, precision, vgg_precision, tol, overlap):
+    """overlap: the exchange issued bucket by bucket from inside the staged backward (three asynchronous all-reduces)."""
     world, per_rank, size = 2, 2, 64
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), precision, vgg_precision, per_rank, size), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), precision, vgg_precision, per_rank, size, overlap), nprocs=world, join=True)
     dp = torch.load(os.path.join(tmp_path, "dp.pt"))
     p = O.make_net_params(seed=0, random_affine=True)
     vp = O.make_vgg_params(seed=1)

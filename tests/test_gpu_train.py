@@ -257,3 +257,48 @@ def test_first_optimizer_steps_follow_the_oracle(dropin, opt_impl):
         # directions (cosine), not element-wise relative error
         cos = float(torch.dot(upd, ref_upd) / (upd.norm() * ref_upd.norm()))
         assert cos > 0.98, (k, cos)
+
+
+def test_staged_backward_buckets_cover_all_gradients(dropin):
+    """Data-parallel form of the captured backward (autograd_fns.StyleNetTrainGraph._backward_staged): three graphs cut after
+    residual blocks 2 and 0, each followed by the assembly of the gradients it completed and a bucket callback.  The buckets
+    tile the flat gradient buffer back to front without gaps, every bucket is final when its callback runs, and the
+    gradients equal those of the single-graph backward."""
+    mm, mv, ll = dropin
+    torch.manual_seed(0)
+    params = O.make_net_params(seed=3, random_affine=True)
+    x = O.make_image(2, 64, 64, seed=11, normalized=True).to(DEV)
+
+    def run(hook):
+        net = mm.StyleTransferNet().to(DEV)
+        net.load_state_dict(params)
+        net.precision = "fp32"
+        net.eval()                                  # no dropout: both runs see the same function
+        for p in net.parameters():
+            p.requires_grad_(True)
+        if hook is not None:
+            net.__dict__["_fnst_bucket_hook"] = hook
+        grads = []
+        for _ in range(2):                          # capture step + replay step
+            net.zero_grad()
+            y = net(x)
+            (y * y).sum().backward()
+            grads.append(torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone())
+        return grads
+
+    seen = []
+
+    def hook(flat, lo, hi, last):
+        seen.append((lo, hi, last, flat[lo:hi].clone()))
+
+    staged = run(hook)
+    plain = run(None)
+    total = staged[0].numel()
+    for step in range(2):
+        b = seen[3 * step:3 * step + 3]
+        assert [t[2] for t in b] == [False, False, True]
+        assert b[0][1] == total and b[0][0] == b[1][1] and b[1][0] == b[2][1] and b[2][0] == 0          # back to front, no gaps
+        assert b[0][1] - b[0][0] > 0.55 * total and b[2][1] - b[2][0] < 0.05 * total
+        for lo, hi, _, snap in b:
+            assert torch.equal(snap, staged[step][lo:hi])                                             # final when handed over
+        assert rel_l2(staged[step], plain[step]) < 1e-5

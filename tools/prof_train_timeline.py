@@ -56,14 +56,18 @@ for e in ks:
     per[name][0] += 1; per[name][1] += e["dur"]
     streams[e["args"].get("stream", 0)] += e["dur"]
 # union busy time
-iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in ks)
-busy, cur_s, cur_e, gaps = 0.0, iv[0][0], iv[0][1], []
-for s, e_ in iv[1:]:
+iv = sorted((e["ts"], e["ts"] + e["dur"], e["name"].split("(")[0][:48]) for e in ks)
+busy, cur_s, cur_e, gaps, last_name, gap_sites = 0.0, iv[0][0], iv[0][1], [], iv[0][2], []
+for s, e_, nm in iv[1:]:
     if s > cur_e:
         busy += cur_e - cur_s
         gaps.append((s - cur_e, cur_e - t0))
-        cur_s, cur_e = s, e_
+        if s - cur_e > 15:
+            gap_sites.append((round(s - cur_e, 1), last_name, nm))
+        cur_s, cur_e, last_name = s, e_, nm
     else:
+        if e_ >= cur_e:
+            last_name = nm
         cur_e = max(cur_e, e_)
 busy += cur_e - cur_s
 span = t1 - t0
@@ -72,5 +76,6 @@ out = {"steps": steps, "span_us_per_step": span / steps, "union_busy_us_per_step
        "streams_busy_us_per_step": {str(k): v / steps for k, v in streams.items()},
        "gaps_over_5us_per_step": sum(1 for g, _ in gaps if g > 5) / steps, "gap_time_over_5us_per_step": sum(g for g, _ in gaps if g > 5) / steps,
        "largest_gaps_us": sorted((round(g, 1) for g, _ in gaps), reverse=True)[:12],
+       "gaps_over_15us_of_the_last_step": [g for g in gap_sites[-(len(gap_sites) // steps):]],
        "top_kernels_us_per_step": [(k, v[0] / steps, round(v[1] / steps, 1)) for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])[:45]]}
 print(json.dumps(out, indent=1))
