@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- style-transfer hot path on B200 (see DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer256|infer1080|train] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer256|infer1080|train|preprocess] [--impl reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic
 images that are already resident in HBM; `e2e` repeats the measurement through the drop-in module
@@ -35,6 +35,9 @@ WORKLOADS = {
                         desc="BASELINE.json configs[0]: single 1x3x256x256 image (latency case)"),
     "train": dict(batch=4, h=256, w=256, metric="train steps/sec (batch 4 per GPU, 256x256)", unit="steps/s", scaling="weak",
                   desc="BASELINE.json configs[1]/[4]: perceptual-loss training step, batch 4 per GPU"),
+    # SURVEY 8f N3 (a "next" row, not part of BASELINE's metric): bench_preprocess.py
+    "preprocess": dict(batch=32, h=1080, w=1920, metric="input-transform images/sec", unit="images/s", scaling="weak",
+                       desc="SURVEY 8f N3: Resize + ToTensor + Normalize of decoded 1080x1920 frames, one launch per batch"),
 }
 NET_GFLOP_256 = 52.867          # algorithmic forward GFLOP per 256x256 image
 TRAIN_GFLOP_IMG = 286.82        # algorithmic GFLOP per image of one training step
@@ -190,6 +193,15 @@ def run_reference(args, wl):
             O.clip_and_adam(params, grads, state, step=i + 1)
         units = 1.0
         sample = f"one full training step, batch {sample_b} at {wl['h']}x{wl['w']} (the whole workload unit)"
+    elif args.workload == "preprocess":
+        import numpy as np
+        from oracle import pil_resize as R
+        cores = 1
+        img = np.random.default_rng(5).integers(0, 256, (wl["h"], wl["w"], 3), dtype=np.uint8)
+        def step(i):
+            R.to_tensor(R.resize_bilinear_u8(img, 256, 256), (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+        units = 1.0
+        sample = "one 1080x1920 image per step (oracle/pil_resize.c: Pillow's two-pass bilinear resize + ToTensor + Normalize, one thread)"
     else:
         sample_b = 8 if wl["h"] <= 256 else 1
         x = O.make_image(sample_b, wl["h"], wl["w"], seed=1234)
@@ -210,7 +222,7 @@ def run_reference(args, wl):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": (train_config(int(os.environ.get("WORLD_SIZE", 1)), 4, wl["h"], wl["w"]) if args.workload == "train"
                        else {"workload": args.workload, "desc": wl["desc"]}),
-            "device": "host CPU (oracle port of the reference modules, all host threads)",
+            "device": "host CPU (oracle port of the reference modules, %s)" % ("one thread" if cores == 1 else "all host threads"),
             "cpu_baseline": {"value": value, "unit": wl["unit"], "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -570,6 +582,12 @@ def main():
         net.precision = precision
         return net
 
+    if args.workload == "preprocess":
+        import bench_preprocess
+        line = bench_preprocess.run(args, rank, world, dev, peaks, not args.no_cpu_baseline)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
     if not everything:
         args.precision = args.precision or "fp16"
         net = make_net(args.precision)
@@ -595,9 +613,16 @@ def main():
         torch.cuda.empty_cache()
         if sub is not None:
             subs[name] = sub
+    import bench_preprocess
+    try:
+        pre = bench_preprocess.run(args, rank, world, dev, peaks, False)
+    except Exception as exc:                                       # a "next"-row leg never costs the measured headline
+        pre = {"error": repr(exc)[:300]}
+    torch.cuda.empty_cache()
     if rank != 0:
         return
     line["inference"] = subs          # BASELINE configs[3], [2], [0]; `config` above stays that of the headline training workload
+    line["preprocess"] = pre          # SURVEY 8f N3 (a "next" row)
     if not args.no_eager_reference and not os.environ.get("FNST_BENCH_NO_ROOFLINE"):
         try:
             line["gpu_eager_reference"] = gpu_eager_reference(dev, ("train", "infer256", "infer1080"))

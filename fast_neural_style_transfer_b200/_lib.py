@@ -103,6 +103,8 @@ EXPORTS = {
     "fnst_grad_scale": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "fnst_resize_to_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_void_p]),
+    "fnst_resize_batch_to_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_void_p]),
     "fnst_resize_window_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
     "fnst_adam_step": (C.c_int, [C.POINTER(C.c_void_p)] * 4 + [C.POINTER(C.c_int64), C.c_int] + [C.c_double] * 5
                        + [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),

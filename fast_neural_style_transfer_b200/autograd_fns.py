@@ -501,6 +501,8 @@ class VGGGraph:
         self.bwd = {}
         plan._out_buffers = None            # the plan must not keep views of this graph's output alive (see outputs_free)
         self._refs0 = _storage_refs(self.fwd.outputs)
+        for k in [k for k, (ref, _) in GRAD_SLOTS.items() if ref() is None]:
+            del GRAD_SLOTS[k]                # graphs that no longer exist
         offs = 0
         for i, n in enumerate(self.numels):
             GRAD_SLOTS[self.fwd.outputs.data_ptr() + offs * self.fwd.outputs.element_size()] = (weakref.ref(self), i)

@@ -97,6 +97,8 @@ struct ResizeParams {
   int strip_rows;          // capacity of the shared-memory strip (rows)
   int stage_pitch;         // STAGED: bytes per staged input row (multiple of 4) and rows per staging chunk
   int stage_rows;
+  const fnst_image_desc* batch;   // non-null: blockIdx.z selects the image (in / in_h / in_w / in_pitch come from the table,
+                                  // the outputs are offset by z images)
 };
 
 // STAGED: the input span of the tile is first copied to shared memory with coalesced 32-bit loads (chunks of stage_rows rows),
@@ -107,9 +109,19 @@ struct ResizeParams {
 // once per device) -- so they bound the kernel times from above rather than rank the two forms; until both are re-measured
 // from a CUDA graph the verified un-staged form stays the default (tuning knob resize_staged = 1 selects this one).
 template <bool STAGED>
-__global__ void __launch_bounds__(RS_TILE * RS_TILE) resize_to_tensor_kernel(const ResizeParams p) {
+__global__ void __launch_bounds__(RS_TILE * RS_TILE) resize_to_tensor_kernel(const ResizeParams p_in) {
   pdl_trigger();
   pdl_wait();
+  ResizeParams p = p_in;
+  if (p.batch) {
+    // many images per launch (fnst_resize_batch_to_tensor): the grid's z index walks a device table of image descriptors
+    const fnst_image_desc d = p.batch[blockIdx.z];
+    p.in = reinterpret_cast<const uint8_t*>(d.data);
+    p.in_h = d.h; p.in_w = d.w; p.in_pitch = d.pitch_bytes;
+    const int64_t px = (int64_t)p.out_h * p.out_w * 3;
+    if (p.out_f) p.out_f += (int64_t)blockIdx.z * px;
+    if (p.out_u8) p.out_u8 += (int64_t)blockIdx.z * px;
+  }
   __shared__ int kh[RS_TILE][RS_KMAX], kv[RS_TILE][RS_KMAX];
   __shared__ int bh[RS_TILE][2], bv[RS_TILE][2];
   extern __shared__ uint8_t strip[];                 // [rows][RS_TILE][3] horizontal-pass results of this tile's columns
@@ -277,6 +289,7 @@ extern "C" int fnst_resize_to_tensor(const void* img_hwc, int in_h, int in_w, in
   const bool staged = tuning().resize_staged != 0 && in_w != out_w;
   size_t smem = (size_t)p.strip_rows * RS_TILE * 3;
   p.stage_pitch = p.stage_rows = 0;
+  p.batch = nullptr;
   if (staged) {
     const int span_px = strip_rows_bound(in_w, out_w);               // same bound along the width: input columns one tile touches
     p.stage_pitch = 4 * ((3 * span_px + 6) / 4);
@@ -300,6 +313,56 @@ extern "C" int fnst_resize_to_tensor(const void* img_hwc, int in_h, int in_w, in
   dim3 grid((out_w + RS_TILE - 1) / RS_TILE, (out_h + RS_TILE - 1) / RS_TILE);
   launch_pdl(kern, grid, dim3(RS_TILE * RS_TILE), smem, (cudaStream_t)stream, p);
   return launch_status("resize_to_tensor");
+}
+
+// Many images in ONE launch (grid z = image): the per-image launches of fnst_resize_to_tensor are 256 blocks of 256 threads
+// each -- less than one wave of a 148-SM GPU, so a single image is latency-bound (13.7 us for a 6.2 MB 1080p frame = 0.45 TB/s);
+// a batch keeps every SM busy with ~16 resident tiles whose coefficient set-up and byte loads overlap.
+extern "C" int fnst_resize_batch_to_tensor(const fnst_image_desc* images_dev, int n, int max_in_h, int max_in_w, int out_h,
+                                           int out_w, float* out_nchw, void* out_u8_nhwc, const float* mean3, const float* std3,
+                                           int device, void* stream) {
+  FNST_CHECK_ARG(images_dev && (out_nchw || out_u8_nhwc) && n > 0 && n <= 65535, "resize_batch_to_tensor: bad arguments");
+  FNST_CHECK_ARG(max_in_h > 0 && max_in_w > 0 && out_h > 0 && out_w > 0, "resize_batch_to_tensor: bad sizes");
+  FNST_CHECK_ARG((mean3 == nullptr) == (std3 == nullptr), "resize_batch_to_tensor: pass both mean and std, or neither");
+  const AxisScale ah = axis_scale(max_in_w, out_w), av = axis_scale(max_in_h, out_h);
+  FNST_CHECK_ARG(ah.ksize <= RS_KMAX && av.ksize <= RS_KMAX,
+                 "resize_batch_to_tensor: down-scaling factor above %d is not supported (%dx%d -> %dx%d)", (RS_KMAX - 1) / 2, max_in_h,
+                 max_in_w, out_h, out_w);
+  ResizeParams p;
+  memset(&p, 0, sizeof(p));
+  p.batch = images_dev;
+  p.out_h = out_h; p.out_w = out_w;
+  p.out_f = out_nchw; p.out_u8 = reinterpret_cast<uint8_t*>(out_u8_nhwc);
+  p.normalize = mean3 != nullptr;
+  for (int c = 0; c < 3; ++c) { p.mean[c] = mean3 ? mean3[c] : 0.f; p.std[c] = std3 ? std3[c] : 1.f; }
+  // strip capacity for the tallest image (the bound grows with the input height; shorter images need less)
+  p.strip_rows = strip_rows_bound(max_in_h, out_h);
+  if (p.strip_rows < RS_TILE) p.strip_rows = RS_TILE;
+  size_t smem = (size_t)p.strip_rows * RS_TILE * 3;
+  // staged form (tuning knob resize_staged): the tile's input span goes to shared memory with coalesced 32-bit loads first
+  const bool staged = tuning().resize_staged != 0 && max_in_w != out_w;
+  if (staged) {
+    const int span_px = strip_rows_bound(max_in_w, out_w);
+    p.stage_pitch = 4 * ((3 * span_px + 6) / 4);
+    p.stage_rows = (32 * 1024) / p.stage_pitch;
+    if (p.stage_rows > p.strip_rows) p.stage_rows = p.strip_rows;
+    if (p.stage_rows < 1) p.stage_rows = 1;
+    smem = ((smem + 15) & ~size_t(15)) + (size_t)p.stage_rows * p.stage_pitch;
+  }
+  FNST_CHECK_ARG(smem <= 160 * 1024, "resize_batch_to_tensor: strip of %d rows does not fit shared memory", p.strip_rows);
+  FNST_DEVICE(device);
+  auto kern = staged ? resize_to_tensor_kernel<true> : resize_to_tensor_kernel<false>;
+  if (smem > 32 * 1024) {
+    static std::atomic<unsigned long long> opted[2] = {{0ull}, {0ull}};
+    const unsigned long long bit = 1ull << (device & 63);
+    if (!(opted[staged ? 1 : 0].load(std::memory_order_acquire) & bit)) {
+      FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      opted[staged ? 1 : 0].fetch_or(bit, std::memory_order_release);
+    }
+  }
+  dim3 grid((out_w + RS_TILE - 1) / RS_TILE, (out_h + RS_TILE - 1) / RS_TILE, n);
+  launch_pdl(kern, grid, dim3(RS_TILE * RS_TILE), smem, (cudaStream_t)stream, p);
+  return launch_status("resize_batch_to_tensor");
 }
 
 // Host twin of the device arithmetic (same functions compiled for the host): used by the tests to pin the coefficient

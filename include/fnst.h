@@ -358,6 +358,18 @@ int fnst_adam_step(void* const* params, void* const* grads, void* const* exp_avg
 int fnst_resize_to_tensor(const void* img_hwc, int in_h, int in_w, int64_t in_pitch_bytes, int out_h, int out_w,
                           float* out_chw, void* out_u8_hwc, const float* mean3, const float* std3, int device, void* stream);
 
+/* Many images per launch: `images_dev` is a DEVICE array of n descriptors (decoded uint8 RGB images, sizes may differ;
+ * max_in_h / max_in_w bound them: they size the kernel's shared-memory strip and the down-scaling check).  Image i is written to
+ * out_nchw[i] ([n][3][out_h][out_w] float) and / or out_u8_nhwc[i] ([n][out_h][out_w][3]); same arithmetic as
+ * fnst_resize_to_tensor, bit for bit.  Replaces the per-sample transform calls behind DataLoader's collate (train.py:98-107). */
+typedef struct fnst_image_desc {
+  const void* data;        /* uint8 [h][w][3] (device), rows pitch_bytes apart */
+  int32_t h, w;
+  int64_t pitch_bytes;
+} fnst_image_desc;
+int fnst_resize_batch_to_tensor(const fnst_image_desc* images_dev, int n, int max_in_h, int max_in_w, int out_h, int out_w,
+                                float* out_nchw, void* out_u8_nhwc, const float* mean3, const float* std3, int device,
+                                void* stream);
 /* Test hook (no device work): the resampling window of output index `index` along one axis, computed on the HOST by the
  * same functions the kernel runs on the device.  Returns the window capacity ksize (> 0), or < 0 on bad arguments. */
 int fnst_resize_window_host(int in_size, int out_size, int index, int* first, int* len, int* kk, int kk_capacity);

@@ -60,7 +60,9 @@ def test_cta_pair_matches_single_cta(cfg, restore_knobs):
     o1, s1 = _conv(pair=2, **cfg)
     assert torch.equal(o0, o1)
     assert float(((s0[..., 1] - s1[..., 1]).abs() / (s0[..., 1].abs() + 1)).max()) < (3e-3 if cfg.get("dt") == torch.bfloat16 else 2e-4)
-    assert float((s0[..., 0] - s1[..., 0]).abs().max()) < 2e-3 * float(s0[..., 1].max()) ** 0.5
+    # sum x over a plane of the stored (rounded) values vs of the fp32 accumulators: the rounding errors add up like a random
+    # walk, std = 2^-9 (bf16) or 2^-12 (fp16) / sqrt(3) * sqrt(sum x^2); the bound is ~7 sigma of the worst of ~1000 planes
+    assert float((s0[..., 0] - s1[..., 0]).abs().max()) < (8e-3 if cfg.get("dt") == torch.bfloat16 else 2e-3) * float(s0[..., 1].max()) ** 0.5
 
 
 @pytest.mark.parametrize("shape", [(1, 256, 256), (3, 100, 131), (5, 17, 9), (1, 270, 480)])

@@ -46,6 +46,22 @@ def test_batch_of_mixed_sizes_strided_rows_and_other_output_sizes():
     assert np.array_equal(up.cpu().numpy(), np.asarray(Image.fromarray(imgs[2]).resize((500, 300), Image.BILINEAR)))
 
 
+def test_batch_launch_equals_per_image_launches(monkeypatch):
+    """One launch for the whole batch (fnst_resize_batch_to_tensor: grid z = image, descriptor table on the device) against one
+    launch per image -- mixed sizes, a row-strided crop, up- and down-scaling in one batch: bit-identical."""
+    imgs = [torch.from_numpy(_img(h, w, s)).to(DEV) for s, (h, w) in enumerate([(1080, 1920), (300, 401), (64, 48), (256, 256), (900, 333)])]
+    imgs.append(imgs[0][100:700, 200:1500])                               # pitch != 3 * width
+    for mean, std in ((MEAN, STD), (None, None)):
+        batched = P.resize_to_tensor(imgs, (256, 256), mean, std)
+        monkeypatch.setattr(P, "BATCH_LAUNCH_MIN", 10 ** 9)
+        single = P.resize_to_tensor(imgs, (256, 256), mean, std)
+        monkeypatch.undo()
+        assert torch.equal(batched, single)
+    other = P.resize_to_tensor(imgs[:3], (120, 200))
+    for got, img in zip(other, imgs[:3]):
+        assert torch.equal(got, P.resize_to_tensor(img, (120, 200))[0])
+
+
 def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         P.resize_to_tensor(torch.zeros((64, 64, 3), dtype=torch.uint8))                          # CPU tensor: no fallback

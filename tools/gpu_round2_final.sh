@@ -19,17 +19,19 @@ x = json.load(open('gpurun_out/r02_bench_train_fp16x3.json')); print('train fp16
 PY
 timeout 300 python tools/prof_train_timeline.py 4 > gpurun_out/r02_timeline.json 2> gpurun_out/r02_timeline.err; rm -f gpurun_out/train_trace.json; echo "timeline rc=$?"
 timeout 300 python tools/bench_kernels.py --out gpurun_out/r02_bench_kernels.json > gpurun_out/r02_bench_kernels.log 2>&1; echo "kernels rc=$?"
+timeout 120 python tools/bench_rowconv.py > gpurun_out/r02_bench_rowconv.json 2> gpurun_out/r02_bench_rowconv.err; echo "rowconv rc=$?"
+timeout 120 python tools/exp_rowconv_timeline.py > gpurun_out/r02_rowconv_timeline.log 2>&1; echo "rowconv timeline rc=$?"
 timeout 200 python tools/exp_conv_timeline.py > gpurun_out/r02_conv_timeline.log 2>&1; echo "conv timeline rc=$?"
 export FNST_BENCH_NO_ROOFLINE=1
 CMD="python bench.py --workload train --steps 3 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/r02_plain_train.log 2>&1 && {
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 800 --csv --log-file gpurun_out/r02_launches_train.csv $CMD > gpurun_out/r02_ncu_list.log 2>&1; echo "ncu list rc=$?"
-for K in conv_tc_kernel wgrad_tc_kernel "inorm_apply_kernel|inorm_bwd_reduce_kernel|inorm_bwd_apply_kernel"; do
-  N=$(echo $K | cut -d'|' -f1)
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K" -s 24 -c 5 -f -o gpurun_out/r02_prof_$N $CMD > gpurun_out/r02_ncu_full_$N.log 2>&1; echo "ncu full $N rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 800 --csv --log-file gpurun_out/r02_launches_train.csv $CMD > gpurun_out/r02_ncu_list.log 2>&1; echo "ncu list rc=$?"
+for K in "^conv_tc_kernel" "rowconv_tc_kernel" "wgrad_tc_kernel" "inorm_apply_kernel|inorm_bwd_reduce_kernel|inorm_bwd_apply_kernel"; do
+  N=$(echo $K | cut -d'|' -f1 | tr -d '^')
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K" -s 12 -c 6 -f -o gpurun_out/r02_prof_$N $CMD > gpurun_out/r02_ncu_full_$N.log 2>&1; echo "ncu full $N rc=$?"
 done
 }
-python tools/summarize_launches.py gpurun_out/r02_launches_train.csv "Round 2: launches 1800..2600 of FNST_BENCH_NO_ROOFLINE=1 bench.py --workload train --steps 3 --warmup 3" > gpurun_out/r02_train_launches.md 2>/dev/null
+python tools/summarize_launches.py gpurun_out/r02_launches_train.csv "Round 2: launches 1700..2500 of FNST_BENCH_NO_ROOFLINE=1 bench.py --workload train --steps 3 --warmup 3" > gpurun_out/r02_train_launches.md 2>/dev/null
 python tools/ncu_summary.py gpurun_out/r02_prof_*.ncu-rep > gpurun_out/r02_ncu_train_kernels.json 2> gpurun_out/r02_ncu_summary.err
-find gpurun_out -name '*.ncu-rep' -size +20M -delete
+find gpurun_out -name '*.ncu-rep' -size +12M -delete
 du -sh gpurun_out | tail -1
