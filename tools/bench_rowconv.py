@@ -46,5 +46,5 @@ for name, (B, H, W, cout, form) in {"conv1_2_fwd": (4, 256, 256, 64, "f"), "conv
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 100
         gf = 2.0 * B * H * W * cout * 576 / 1e9
-        res[f"{name}_{ {1: 'rowstream', 0: 'gather', 8: 'rowstream_without_epilogue_stores'}[rs] }"] = dict(us=round(us, 2), tflops=round(gf / us, 1))
+        res[f"{name}_{ {1: 'rowstream', 0: 'gather', 8: 'rowstream_without_epilogue_stores'}[rs] }"] = dict(us=round(us, 2), tflops=round(1e3 * gf / us, 1))
 print(json.dumps(res, indent=1))

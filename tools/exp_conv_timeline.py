@@ -10,6 +10,7 @@ from fast_neural_style_transfer_b200.ops import ConvSpec
 DEV = torch.device("cuda", 0)
 def knob(k, v): _lib.check(_lib.lib.fnst_set_tuning(k.encode(), int(v)), "set_tuning")
 
+knob("conv_rowstream", 0)          # this tool times the generic gather-GEMM (the 64-channel case would otherwise take rowconv_tc)
 dbg = torch.zeros(12 * 148, dtype=torch.int64, device=DEV)
 for B, cin, cout, hw, stats in ((4, 256, 256, 64, True), (4, 256, 256, 64, False), (1, 256, 256, 64, True), (4, 512, 512, 32, False), (4, 64, 64, 256, False)):
     a = torch.randn((B, hw + 2, hw + 2, cin), device=DEV).half()
