@@ -21,6 +21,7 @@ Tuning& tuning() {
     if (const char* e = getenv("FNST_CONV_PAIR")) v.conv_pair = atoi(e);
     if (const char* e = getenv("FNST_CONV_STAGE_OUT")) v.conv_stage_out = atoi(e);
     if (const char* e = getenv("FNST_CONV_ROWSTREAM")) v.conv_rowstream = atoi(e);
+    if (const char* e = getenv("FNST_INORM_BWD_TMA")) v.inorm_bwd_tma = atoi(e);
     if (const char* e = getenv("FNST_INORM_BWD_BLOCKS")) v.inorm_bwd_blocks = atoi(e);
     if (const char* e = getenv("FNST_RESIZE_STAGED")) v.resize_staged = atoi(e);
     return v;
@@ -46,6 +47,7 @@ extern "C" int fnst_set_tuning(const char* name, int value) {
   else if (!strcmp(name, "conv_pair")) t.conv_pair = value;
   else if (!strcmp(name, "conv_stage_out")) t.conv_stage_out = value;
   else if (!strcmp(name, "conv_rowstream")) t.conv_rowstream = value;
+  else if (!strcmp(name, "inorm_bwd_tma")) t.inorm_bwd_tma = value;
   else if (!strcmp(name, "inorm_bwd_blocks")) t.inorm_bwd_blocks = value;
   else if (!strcmp(name, "resize_staged")) t.resize_staged = value;
   else if (!strcmp(name, "dbg_mode")) t.dbg_mode = value;

@@ -295,6 +295,119 @@ __global__ void __launch_bounds__(256, MIN_BLOCKS) inorm_bwd_reduce_kernel(const
   }
 }
 
+// Pass 1, TMA-staged form (2-byte tensors, plain halo layout, a whole padded row <= 256 pixels).  The register form above keeps
+// two pixels x three tensors in flight per thread (four need ~180 registers): at batch 4 it is latency-bound at 2.1-2.7 TB/s on
+// L2-resident data.  Here a CTA owns ONE image row: one thread issues the row's three tiles (raw, the padded gradient row, the
+// residual-branch gradient; up to 97 KB) as TMA box loads the moment the dependency wait returns, so every byte of the CTA is
+// in flight at once and two CTAs per SM keep ~200 KB in flight; the arithmetic then reads shared memory (512 contiguous bytes
+// per warp: conflict-free).  Same operations in the same order as the register form: gy is bit-identical.
+// Measured on B200 at 4 x 64 x 64 x 256 (profiles/r02_bench_inorm_tma.json): 11.5 us against 13.5 us alone (L2-hot), but the training
+// step is 0.05 ms SLOWER with it -- a kernel this small is bound by its launch / prologue / tail latencies, and its 100 KB CTAs
+// cannot share SMs with the concurrent weight-gradient GEMMs as the register form's small CTAs do.  Tested option, default off.
+template <typename TA, typename TG>
+__global__ void __launch_bounds__(256, 2)
+inorm_bwd_reduce_tma_kernel(const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_g,
+                            const __grid_constant__ CUtensorMap map_e, const TG* __restrict__ gsrc, const float* __restrict__ stats,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ drop,
+                            TG* __restrict__ gy, float* __restrict__ sums, float* __restrict__ dgb, HaloLayout L, int relu, float eps,
+                            int has_e) {
+  pdl_trigger();
+  extern __shared__ uint8_t sm_raw[];
+  __shared__ uint64_t bar;
+  const int n = blockIdx.y, h = blockIdx.x;
+  const int C = L.C, CG = C >> 3, PL = 256 / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG, c0 = cg * 8;
+  const int Wp = L.W + 2 * L.pad;
+  float* par = reinterpret_cast<float*>(sm_raw);                                   // [5][C]
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw + 20 * C) + 127) & ~uintptr_t(127));
+  const TA* t_raw = reinterpret_cast<const TA*>(tiles);                           // [W][C]
+  const TG* t_g = reinterpret_cast<const TG*>(tiles + (size_t)L.W * C * sizeof(TA));   // [Wp][C] (when gsrc)
+  const TG* t_e = t_g + (gsrc ? (size_t)Wp * C : 0);                              // [W][C]  (when extra)
+  float* part = reinterpret_cast<float*>(tiles);                                  // [PL][2C], re-uses the tiles after the loop
+  {
+    const float inv_cnt = 1.f / (float)(L.H * L.W);
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const float* st = stats + ((size_t)n * C + c) * 2;
+      const float mean = st[0] * inv_cnt;
+      const float rstd = rsqrtf(fmaxf(st[1] * inv_cnt - mean * mean, 0.f) + eps);
+      const float ai = gamma[c] * rstd;
+      par[c] = ai; par[C + c] = beta[c] - mean * ai; par[2 * C + c] = mean; par[3 * C + c] = rstd;
+      par[4 * C + c] = drop ? drop[(size_t)n * C + c] : 1.f;
+    }
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  pdl_wait();                         // (the table above reads forward-pass tensors only)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)((size_t)L.W * C * sizeof(TA) + (gsrc ? (size_t)Wp * C * sizeof(TG) : 0) +
+                                      (has_e ? (size_t)L.W * C * sizeof(TG) : 0));
+    mbar_arrive_expect_tx(&bar, bytes);
+    tma_load_2d(const_cast<TA*>(t_raw), &map_raw, &bar, 0, (n * L.H + h) * L.W);
+    if (gsrc) tma_load_4d(const_cast<TG*>(t_g), &map_g, &bar, 0, 0, h + L.pad, n);
+    if (has_e) tma_load_2d(const_cast<TG*>(t_e), &map_e, &bar, 0, (n * L.H + h) * L.W);
+  }
+  float a[8], b[8], mean[8], rstd[8], ds[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = par[c0 + i]; b[i] = par[C + c0 + i]; mean[i] = par[2 * C + c0 + i]; rstd[i] = par[3 * C + c0 + i]; ds[i] = par[4 * C + c0 + i];
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  int hs[3]; const int nh = L.sources(h, L.H, hs);
+  mbar_wait(&bar, 0);
+  for (int w = pl; w < L.W; w += PL) {
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    if (gsrc) {
+      float t[8];
+      load8<TG>(t_g + (size_t)(w + L.pad) * C + c0, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = t[i];
+      int wsrc[3]; const int nw = L.sources(w, L.W, wsrc);
+      if (nh > 1 || nw > 1) {          // ReflectionPad2d fold: this row's halo columns from the tile, other halo rows from memory
+        for (int ih = 0; ih < nh; ++ih)
+          for (int iw = (ih == 0 ? 1 : 0); iw < nw; ++iw) {
+            if (ih == 0) load8<TG>(t_g + (size_t)wsrc[iw] * C + c0, t);
+            else load8<TG>(gsrc + L.index(n, hs[ih], wsrc[iw], c0), t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] += t[i];
+          }
+      }
+    }
+    if (has_e) {
+      float t[8];
+      load8<TG>(t_e + (size_t)w * C + c0, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] += t[i];
+    }
+    float x[8];
+    load8<TA>(t_raw + (size_t)w * C + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(x[i], a[i], b[i]);
+      float gv = g[i] * ds[i];
+      if (relu && !(y > 0.f)) gv = 0.f;
+      g[i] = gv;
+      s1[i] += gv;
+      s2[i] = fmaf(gv, (x[i] - mean[i]) * rstd[i], s2[i]);
+    }
+    store8<TG>(gy + (((size_t)n * L.H + h) * L.W + w) * C + c0, g);
+  }
+  __syncthreads();                    // every thread is done with the tiles: their memory becomes the reduction scratch
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { part[pl * 2 * C + c0 + i] = s1[i]; part[pl * 2 * C + C + c0 + i] = s2[i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float t = 0.f;
+    for (int q = 0; q < PL; ++q) t += part[q * 2 * C + i];
+    const int c = i < C ? i : i - C, which = i < C ? 0 : 1;
+    atomicAdd(&sums[((size_t)n * C + c) * 2 + which], t);
+    if (dgb) atomicAdd(&dgb[which ? c : C + c], t);
+  }
+}
+
 template <typename TA, typename TG>
 __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const TG* __restrict__ gy, const TA* __restrict__ raw,
                                                               const float* __restrict__ stats, const float* __restrict__ sums,
@@ -899,6 +1012,9 @@ extern "C" int fnst_conv_first_wgrad(const float* x, int n, int h, int w, const 
   return launch_status("conv_first_wgrad");
 }
 
+static int encode_tensor_map_plain(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                   const uint32_t* box);
+
 extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const void* raw, const float* stats,
                                      const float* gamma, const float* beta, const float* drop, void* gy, float* sums,
                                      float* dgb, int n, int h, int w, int c, int act_dtype, int g_dtype, int relu, float eps,
@@ -913,6 +1029,44 @@ extern "C" int fnst_inorm_bwd_reduce(const void* gsrc, const void* extra, const 
     if (dgb) FNST_CUDA(cudaMemsetAsync(dgb, 0, sizeof(float) * 2 * (size_t)c, st));
   }
   HaloLayout L{h, w, c, pad, pad_mode == FNST_PAD_REFLECT ? 1 : 0, s2d, gsrc_slack};
+  if (!gsrc) L.pad = 0;
+  {
+    // TMA-staged form: 2-byte tensors, plain halo layout, the padded row fits one box, two CTAs' tiles fit one SM
+    const int wp = w + 2 * L.pad;
+    const size_t tile_bytes = 2 * ((size_t)w * c + (gsrc ? (size_t)wp * c : 0) + (extra ? (size_t)w * c : 0));
+    const size_t scratch = sizeof(float) * (size_t)(256 / (c / 8)) * 2 * c;
+    const size_t smem_tma = 20 * (size_t)c + 128 + (tile_bytes > scratch ? tile_bytes : scratch);
+    if (tuning().inorm_bwd_tma && act_dtype != FNST_F32 && g_dtype != FNST_F32 && !s2d && c <= 256 && wp <= 256 && h <= 65535 &&
+        smem_tma <= 110 * 1024 && (int64_t)n * h * w < ((int64_t)1 << 31)) {
+      CUtensorMap m_raw, m_g, m_e;
+      memset(&m_g, 0, sizeof(m_g)); memset(&m_e, 0, sizeof(m_e));
+      {
+        const uint64_t dims[2] = {(uint64_t)c, (uint64_t)n * h * w};
+        const uint64_t str[1] = {(uint64_t)c * 2};
+        const uint32_t box[2] = {(uint32_t)c, (uint32_t)w};
+        if (int r = encode_tensor_map_plain(&m_raw, raw, 2, dims, str, box)) return r;
+        if (extra) { if (int r = encode_tensor_map_plain(&m_e, extra, 2, dims, str, box)) return r; }
+      }
+      if (gsrc) {
+        const uint64_t wa = wp + gsrc_slack, ha = h + 2 * L.pad + gsrc_slack;
+        const uint64_t dims[4] = {(uint64_t)c, wa, ha, (uint64_t)n};
+        const uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)c * 2 * wa, (uint64_t)c * 2 * wa * ha};
+        const uint32_t box[4] = {(uint32_t)c, (uint32_t)wp, 1, 1};
+        if (int r = encode_tensor_map_plain(&m_g, gsrc, 4, dims, str, box)) return r;
+      }
+      FNST_DISPATCH_DTYPE(act_dtype, TA, {
+        FNST_DISPATCH_DTYPE(g_dtype, TG, {
+          if (sizeof(TA) == 2 && sizeof(TG) == 2) {
+            auto kern = inorm_bwd_reduce_tma_kernel<TA, TG>;
+            FNST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            launch_pdl(kern, dim3(h, n), dim3(256), smem_tma, st, m_raw, m_g, m_e, reinterpret_cast<const TG*>(gsrc), stats, gamma, beta,
+                       drop, reinterpret_cast<TG*>(gy), sums, dgb, L, relu, eps, extra ? 1 : 0);
+          }
+        });
+      });
+      return launch_status("inorm_bwd_reduce (TMA)");
+    }
+  }
   const int rpb = rows_per_block(h, n);
   dim3 grid((h + rpb - 1) / rpb, n);
   const size_t smem = sizeof(float) * (5 * (size_t)c + (size_t)(256 / (c / 8)) * 2 * c);

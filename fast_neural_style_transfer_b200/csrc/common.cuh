@@ -79,6 +79,9 @@ struct Tuning {
   int conv_stage_out = 1;      // conv_tc epilogue: 1 = shared-memory tile + TMA store + per-column statistics where applicable, 0 = never
   int conv_pair = 1;           // 1: CTA pairs (cta_group::2) where measured faster; 0: never; 2: whenever the column tile is >= 128
   int conv_rowstream = 1;      // 1: 3x3 convolutions over 64 input channels (VGG conv1_2 / conv2_1 and conv1_2's data gradient) use the row-streaming kernel
+  int inorm_bwd_tma = 0;       // 1: InstanceNorm backward pass 1 stages each image row with TMA box loads where the geometry allows
+                               // (alone 11.5 vs 13.5 us at batch 4; inside the training step +0.05 ms: its ~100 KB CTAs cannot share
+                               // SMs with the weight-gradient GEMMs of the side stream the way the register form does -> default off)
   int inorm_bwd_blocks = 2;    // resident blocks per SM the InstanceNorm-backward reduce kernel is compiled for (16-bit types): 1 or 2
   int resize_staged = 0;       // fnst_resize_to_tensor: 1 = stage the tile's input span in shared memory with 32-bit loads
   int dbg_mode = 0;            // measurement only: bit 0 skips the per-chunk column sums, bit 1 the global statistics atomics

@@ -100,7 +100,8 @@ const char* fnst_last_error(void);
  * "conv_block_n" (0 = heuristic), "conv_pair" (0/1: cta_group::2 CTA pairs), "conv_stage_out" (0/1: shared-memory tile + TMA
  * store epilogue for one-tile-per-CTA launches), "conv_rowstream" (0/1: row-streaming kernel with resident weights for 3x3
  * convolutions over 64 input channels with 64 / 128 outputs and no statistics), "wgrad_waves_x2", "wgrad_bn" (0 = widest), "pdl" (0/1),
- * "inorm_bwd_blocks" (1/2 resident blocks per SM of the InstanceNorm backward reduce kernel), "resize_staged" (0/1).
+ * "inorm_bwd_tma" (0/1, default 0: InstanceNorm backward pass 1 stages image rows with TMA box loads), "inorm_bwd_blocks" (1/2 resident
+ * blocks per SM of the register form of that kernel), "resize_staged" (0/1).
  * Returns 0, or -1 for an unknown name. */
 int fnst_set_tuning(const char* name, int value);
 /* Measurement only: while set (non-NULL), every fnst_conv_tc launch makes the MMA-issuing thread of CTA i write

@@ -293,3 +293,34 @@ def test_pixel_stream_dgrad_matches_box_form(shape):
     gy_a, sums_a = ops.inorm_bwd_reduce(box, None, *common)
     gy_b, sums_b = ops.inorm_bwd_reduce(lin, None, *common, gsrc_slack=2)
     assert torch.equal(gy_a, gy_b) and rel_l2(sums_b, sums_a) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [dict(shape=(4, 64, 64, 256), pad=1, extra=False, relu=True, drop=True),
+                                 dict(shape=(4, 64, 64, 256), pad=1, extra=True, relu=False, drop=False),
+                                 dict(shape=(2, 10, 12, 256), pad=0, extra=True, relu=False, drop=False, gsrc=False),
+                                 dict(shape=(1, 37, 45, 64), pad=0, extra=False, relu=True, drop=False),
+                                 dict(shape=(2, 20, 24, 32), pad=4, extra=False, relu=True, drop=False),
+                                 dict(shape=(3, 5, 7, 128), pad=1, extra=True, relu=True, drop=True)])
+def test_inorm_bwd_reduce_tma_form_equals_register_form(cfg):
+    """Pass 1 of the InstanceNorm backward with each image row staged by TMA box loads
+    (tuning knob inorm_bwd_tma) against the register-pipelined form: the same operations in the same order -- gy bit for bit, the per-plane sums up to the
+    order of their fp32 atomics."""
+    B, H, W, C = cfg["shape"]
+    pad = cfg["pad"]
+    g = torch.Generator().manual_seed(41)
+    gdt, adt = torch.bfloat16, torch.float16
+    raw = (torch.randn((B, H, W, C), generator=g) * 1.5 + 0.3).to(adt).to(DEV)
+    st = torch.stack([raw.double().sum((1, 2)), (raw.double() ** 2).sum((1, 2))], dim=-1).float()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.randn(C, generator=g) * 0.3).to(DEV)
+    drop = ((torch.rand((B, C), generator=g) < 0.9).float() / 0.9).to(DEV) if cfg["drop"] else None
+    gsrc = torch.randn((B, H + 2 * pad, W + 2 * pad, C), generator=g).to(gdt).to(DEV) if cfg.get("gsrc", True) else None
+    extra = torch.randn((B, H, W, C), generator=g).to(gdt).to(DEV) if cfg["extra"] else None
+    res = []
+    for tma in (1, 0):
+        _lib.check(_lib.lib.fnst_set_tuning(b"inorm_bwd_tma", tma), "knob")
+        res.append(ops.inorm_bwd_reduce(gsrc, extra, raw, st, gamma, beta, drop, gdt, cfg["relu"], pad,
+                                        _lib.PAD_REFLECT if pad else _lib.PAD_NONE, False))
+    _lib.check(_lib.lib.fnst_set_tuning(b"inorm_bwd_tma", 0), "knob")          # the default
+    assert torch.isfinite(res[0][0].float()).all()
+    assert torch.equal(res[0][0], res[1][0])
+    assert rel_l2(res[0][1], res[1][1]) < 1e-5

@@ -206,7 +206,8 @@ def main():
     for pdl in (0, 1):
         rec("inorm_apply_256", lambda s: case_inorm_apply(B, s), pdl=pdl)
     for blocks in (1, 2):
-        rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=1, inorm_bwd_blocks=blocks)
+        rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=1, inorm_bwd_tma=0, inorm_bwd_blocks=blocks)
+    rec("inorm_bwd_reduce_256", lambda s: case_inorm_bwd(B, s, "reduce"), pdl=1, inorm_bwd_tma=1)
     rec("inorm_bwd_apply_256", lambda s: case_inorm_bwd(B, s, "apply"), pdl=1)
     rec("inorm_bwd_fused_256", lambda s: case_inorm_bwd_fused(B, s), pdl=1)
     rec("inorm_bwd_fused_256_extra_gy", lambda s: case_inorm_bwd_fused(B, s, want_gy=True, extra_on=True), pdl=1)
