@@ -124,3 +124,43 @@ def test_dgrad_operand_layouts():
             d += torch.einsum("ohw,pqco->hwpqc", patch, wd[:, :, :, dh, dw, :])
     full = d.permute(4, 0, 2, 1, 3).reshape(2, 2 * hs, 2 * ws)[:, :9, :9]
     assert torch.allclose(full, x.grad[0], atol=1e-12)
+
+
+def test_staged_backward_and_bucket_wise_assembly(monkeypatch):
+    """The generator form of the backward (backward.stylenet_backward_stages: cut points after residual blocks 2 and 0, the
+    data-parallel path captures one CUDA graph per stage) with the gradients assembled bucket by bucket
+    (assemble_gradients(first, last) over backward.bucket_bounds): every bucket is final when its stage ends, the three
+    buckets tile the flat buffer back to front, and the result equals the single-shot backward."""
+    emu_ops.install_backward(monkeypatch, ops)
+    monkeypatch.setattr(backward, "grad_dtype", lambda precision: torch.float32)
+    p = O.make_net_params(seed=3, random_affine=True)
+    x = O.make_image(2, 24, 24, seed=11)
+    drop = O.make_dropout_scales(2, seed=9)
+    plan = engine.StyleNetPlan("fp16")
+    plan.dtype = torch.float32
+    plan.pack(p)
+    tape = {}
+    y = plan.forward(x, drop, tape)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
+    names = list(plan.params)
+    whole = backward.assemble_gradients(backward.stylenet_backward_core(plan, tape, dy), names, plan.params)
+
+    gen = backward.stylenet_backward_stages(plan, tape, dy)
+    asm = backward._assembly(names, [plan.params[n].shape for n in names], True, dy.device)
+    flat, stage, ranges = None, 0, []
+    while True:
+        try:
+            core, done = next(gen), False
+        except StopIteration as end:
+            core, done = end.value, True
+        first, last = backward.bucket_bounds(stage)
+        flat = backward.assemble_gradients(core, names, plan.params, flat, first, last)
+        lo = 0 if first is None else asm["offsets"][first]
+        hi = asm["total"] if last is None else asm["offsets"][last]
+        ranges.append((lo, hi))
+        assert torch.equal(flat[lo:hi], whole[lo:hi]), stage                    # final as soon as its stage has run
+        stage += 1
+        if done:
+            break
+    assert stage == 3 and ranges[0][1] == asm["total"] and ranges[0][0] == ranges[1][1] and ranges[1][0] == ranges[2][1] and ranges[2][0] == 0
+    assert torch.equal(flat, whole)

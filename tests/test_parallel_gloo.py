@@ -48,6 +48,22 @@ def _worker(rank, world, port, out_dir):
         ar.all_reduce()
         for k in p:
             assert torch.allclose(holder2[k.replace(".", "/")].grad, holder[k.replace(".", "/")].grad, rtol=1e-6, atol=0)
+        # bucket-wise exchange (the staged backward calls the hook as each slice of the flat buffer becomes final, back to front;
+        # asynchronous all-reduces, waited for at the last bucket): same result, and the all_reduce() after backward() is a no-op
+        holder3 = torch.nn.ParameterDict({k.replace(".", "/"): torch.nn.Parameter(v.clone()) for k, v in p.items()})
+        flat3 = torch.cat([grads[k].reshape(-1) for k in order])
+        for k, piece in zip(order, torch.split(flat3, [p[k].numel() for k in order])):
+            holder3[k.replace(".", "/")].grad = piece.view_as(p[k])
+        ar3 = parallel.GradientAllReduce(holder3, world)
+        cuts = [flat3.numel(), flat3.numel() * 2 // 5, 1000, 0]
+        for i in range(3):
+            ar3._bucket_ready(flat3, cuts[i + 1], cuts[i], i == 2)
+        assert ar3._reduced is flat3 and not ar3._pending
+        before = flat3.clone()
+        assert ar3.all_reduce().data_ptr() == flat3.data_ptr() and torch.equal(flat3, before)      # already reduced: untouched
+        assert torch.allclose(flat3, flat, rtol=1e-6, atol=0)
+        ar3.all_reduce()                                                                            # a second call reduces again
+        assert torch.allclose(flat3, world * before, rtol=1e-6, atol=0)
         assert parallel.all_finite(torch.tensor(1.0), world)
         assert not parallel.all_finite(torch.tensor(float("nan") if rank == 1 else 1.0), world)
         if rank == 0:
