@@ -61,13 +61,15 @@ def resize_to_tensor(images: Union[torch.Tensor, Sequence[torch.Tensor]], size: 
         packed.append(img)
     if len(packed) >= BATCH_LAUNCH_MIN:
         # one launch for the whole batch: the grid's z index walks a device table of (pointer, height, width, pitch)
-        table = torch.tensor([[img.data_ptr(), img.shape[0] | (img.shape[1] << 32), img.stride(0)] for img in packed],
-                             dtype=torch.int64).pin_memory().to(dev_t.device, non_blocking=True)
+        table = torch.tensor([[img.data_ptr(), img.shape[0] | (img.shape[1] << 32), img.stride(0)] for img in packed], dtype=torch.int64)
+        if dev_t.is_cuda:
+            table = table.pin_memory().to(dev_t.device, non_blocking=True)
         check(lib.fnst_resize_batch_to_tensor(C.c_void_p(table.data_ptr()), len(packed), max(i.shape[0] for i in packed),
                                               max(i.shape[1] for i in packed), oh, ow, C.c_void_p(out.data_ptr()), None, m3, s3,
                                               dev, stream), "resize_batch_to_tensor")
         ops._count()
-        table.record_stream(torch.cuda.current_stream(dev_t.device))
+        if dev_t.is_cuda:
+            table.record_stream(torch.cuda.current_stream(dev_t.device))
         return out
     for i, img in enumerate(packed):
         check(lib.fnst_resize_to_tensor(C.c_void_p(img.data_ptr()), img.shape[0], img.shape[1], img.stride(0), oh, ow,

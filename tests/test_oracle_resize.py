@@ -96,8 +96,19 @@ def test_preprocess_python_layer_with_emulated_abi(monkeypatch):
             np.ctypeslib.as_array((C.c_float * (3 * oh * ow)).from_address(out_f.value))[:] = R.to_tensor(small, m, s).reshape(-1)
         return 0
 
+    def emu_batch(table, n, max_h, max_w, oh, ow, out_f, out_u8, mean, std, dev, stream):
+        # fnst_image_desc[n] = {void* data; int32 h, w; int64 pitch_bytes}: the batch entry point walks the descriptor table
+        desc = np.ctypeslib.as_array((C.c_int64 * (3 * n)).from_address(table.value)).reshape(n, 3)
+        for i in range(n):
+            ih, iw = int(desc[i, 1] & 0xFFFFFFFF), int(desc[i, 1] >> 32)
+            assert ih <= max_h and iw <= max_w
+            slot = lambda base, nbytes: None if base is None or not getattr(base, "value", None) else C.c_void_p(base.value + i * nbytes)
+            emu(C.c_void_p(int(desc[i, 0])), ih, iw, int(desc[i, 2]), oh, ow, slot(out_f, 3 * oh * ow * 4), slot(out_u8, 3 * oh * ow), mean, std, dev, stream)
+        return 0
+
     class Lib:
         fnst_resize_to_tensor = staticmethod(emu)
+        fnst_resize_batch_to_tensor = staticmethod(emu_batch)
         fnst_last_error = staticmethod(lambda: b"emulated")
 
     monkeypatch.setattr(P, "lib", Lib)
