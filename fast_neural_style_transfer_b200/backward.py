@@ -350,7 +350,6 @@ def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.
         return out
 
     # ---- final_conv (9x9, 32 -> 3) -------------------------------------------------------------------
-    ops.channel_sum(dy, out=slot("final_bias"))
     act4 = tape["act4"]
     Hq, Wq = act4.shape[1], act4.shape[2]
     taps81 = taps_kxk(9)
@@ -364,7 +363,8 @@ def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.
         g_str = (rows_g * pitch_g * 8, pitch_g * 8, 8)
         flat_act = tape["act4_flat"]
         taps9 = [(kh - 8, 0, 0) for kh in range(9)]
-        with on_side(g8, flat_act):
+        with on_side(g8, flat_act, dy):
+            ops.channel_sum(dy, out=slot("final_bias"))          # d bias of final_conv: nothing downstream needs it
             a_g = flat_act
             if a_g.dtype != gdt:
                 a_g = wtw.get("act4_flat") if wtw.get("act4_flat") is not None else ops.cast(flat_act, gdt)
@@ -379,6 +379,7 @@ def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.
                         (B, rows_g, pitch_g // 2, 64), (rows_g * pitch_g * 4, pitch_g * 4, 8), d_act4.view(B, Hq, Wq // 2, 64),
                         (Hq, Wq // 2), None, True)
     else:
+        ops.channel_sum(dy, out=slot("final_bias"))
         g16 = ops.nchw_to_nhwc(dy, gdt, c_pad=16)
         wgrad(ConvSpec(taps81, 32, None, 16, 3), act4, None, (B, Hq, Wq, 32), g16, (H4, W4), slot("final"))
         d_act4 = dgrad(g16, (B, H4, W4, 16), wd_all["final"], taps81, 32, (B, Hq, Wq, 32), (Hq, Wq))

@@ -76,7 +76,8 @@ struct Tuning {
   int wgrad_waves_x2 = 2;      // wgrad_tc split-K target: tasks <= waves_x2/2 * SM count (one wave measured best: fewer L2 atomics)
   int wgrad_bn = 0;            // 0 = widest column block that divides kc; else force 64/128/256
   int pdl = 1;
-  int conv_stage_out = 1;      // conv_tc epilogue: 1 = shared-memory tile + TMA store + per-column statistics where applicable, 0 = never
+  int conv_stage_out = 1;      // conv_tc epilogue: 1 = shared-memory tile + TMA store + per-column statistics where applicable, 0 = never,
+                               // 2 = one-tile-per-CTA launches only (A/B of the private staging tile of the 64 / 128 column tiles)
   int conv_pair = 1;           // 1: CTA pairs (cta_group::2) where measured faster; 0: never; 2: whenever the column tile is >= 128
   int conv_rowstream = 1;      // 1: 3x3 convolutions over 64 input channels (VGG conv1_2 / conv2_1 and conv1_2's data gradient) use the row-streaming kernel
   int inorm_bwd_tma = 0;       // 1: InstanceNorm backward pass 1 stages each image row with TMA box loads where the geometry allows

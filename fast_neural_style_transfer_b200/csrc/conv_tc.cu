@@ -94,7 +94,10 @@ template <int BLOCK_N, bool PAIR = false> struct TcCfg {
   static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // weight rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * TC_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  // column tiles of 64 / 128: a PRIVATE staging tile for the shared-memory + TMA-store epilogue (multi-tile launches cannot
+  // borrow the operand ring: the next tile is loading into it), paid for with one operand stage
+  static constexpr int STAGING_BYTES = (BLOCK_N == 64 || BLOCK_N == 128) ? TC_BLOCK_M * BLOCK_N * 2 : 0;
+  static constexpr int STAGES_RAW = (200 * 1024 - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int CHUNK = BLOCK_N < 32 ? BLOCK_N : 32;     // epilogue column chunk
@@ -102,7 +105,7 @@ template <int BLOCK_N, bool PAIR = false> struct TcCfg {
   static constexpr int EPI_THREADS = 32 * EPI_WARPS;
   static constexpr int THREADS = 64 + EPI_THREADS;              // + TMA producer warp + MMA warp
   static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <typename TOut>
@@ -130,7 +133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
@@ -295,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // swizzle TMA expects -> (a) InstanceNorm column sums with ONE THREAD PER COLUMN walking the 128 staged rows (no
         // transposition, no shuffles; statistics of exactly the values that are stored), (b) TMA tile stores (full 128-byte
         // lines, ragged edges clipped by the tensor map) instead of 16-byte stores at a 512-byte stride per lane.
-        uint8_t* stage = smem;
+        uint8_t* stage = Cfg::STAGING_BYTES ? smem + STAGES * Cfg::STAGE_BYTES : smem;     // private tile, or the idle operand ring (N = 256)
 #pragma unroll 1
         for (int cb = col_begin; cb < col_end; cb += 32) {
           uint32_t raw[32];
@@ -333,6 +336,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // generic-proxy writes -> visible to the async proxy (TMA), then all epilogue warps meet
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (Cfg::STAGING_BYTES) {
+          // every warp has read its part of the accumulator: hand the TMEM stage back now, so that in a multi-tile launch the
+          // MMAs of the tile after next start while this tile is still being stored
+          tc_fence_before();
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]); }
+        }
         if (et == 0 && tile_live) {
 #pragma unroll 1
           for (int b = 0; b < BLOCK_N / 64; ++b) {
@@ -358,6 +367,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             atomicAdd(&p.stats[((size_t)n * p.c_out + col) * 2 + 0], (s1[0] + s1[1]) + (s1[2] + s1[3]));
             atomicAdd(&p.stats[((size_t)n * p.c_out + col) * 2 + 1], (s2[0] + s2[1]) + (s2[2] + s2[3]));
           }
+        }
+        if (Cfg::STAGING_BYTES) {
+          // the staging tile is written again by the next tile of this CTA: nobody may pass before TMA has read it
+          if (et == 0 && tile_live) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+          continue;
         }
         if (et == 0 && tile_live) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         // accumulator fully read long ago: hand the TMEM stage back (keeps the barrier protocol of the generic path)
@@ -497,6 +512,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
 
+  if (Cfg::STAGING_BYTES && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // TMA stores of the last tiles
   if (threadIdx.x == 64) stamp(4);
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();     // pair: neither CTA may leave while the other still signals / reads it
@@ -649,8 +665,11 @@ extern "C" int fnst_conv_tc(const fnst_conv_desc* d, int device, void* stream) {
   CUtensorMap mo;
   memset(&mo, 0, sizeof(mo));
   p.stage_out = 0;
+  // (column tiles of 64 / 128 own a private staging tile: any tile count, CTA pairs included)
+  const bool private_stage = block_n == 64 || block_n == 128;
   if (tuning().conv_stage_out && d->epilogue == FNST_EPI_NHWC && !p.out_is_f32 && block_n >= 64 && d->c_out == d->n_gemm &&
-      d->n_gemm % 64 == 0 && !p.addend && !p.mask && !pair && p.num_tiles <= num_sms && !p.dbg_mode) {
+      d->n_gemm % 64 == 0 && !p.addend && !p.mask && !p.dbg_mode &&
+      ((private_stage && tuning().conv_stage_out == 1) || (!pair && p.num_tiles <= num_sms))) {
     const uint64_t dims[4] = {(uint64_t)d->c_out, (uint64_t)d->out_w, (uint64_t)d->out_h, (uint64_t)d->out_n};
     const uint64_t str[3] = {(uint64_t)d->c_out * 2, (uint64_t)d->c_out * 2 * d->out_w, (uint64_t)d->c_out * 2 * d->out_w * d->out_h};
     const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};

@@ -8,6 +8,8 @@ Two precisions share the same plan:
 """
 from __future__ import annotations
 
+import contextlib
+
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -242,23 +244,40 @@ class StyleNetPlan:
              "conv2": gp("conv", lambda t: pack_conv(t, f64), p["conv2.conv.weight"], dt)}
         # the ten 3x3 256->256 weights are packed by two kernels (stack, permute+cast) into one (10, 256, 2304) tensor
         names = [f"res_blocks.{i}.{c}.conv.weight" for i in range(5) for c in ("conv1", "conv2")]
-        stacked = torch.stack([p[n] for n in names])                              # (10, O, C, 3, 3)
-        res_all = torch.empty((10, 256, 9 * 256), dtype=dt, device=stacked.device)
-        res_all.view(10, 256, 3, 3, 256).copy_(stacked.permute(0, 1, 3, 4, 2))
-        w["res_all"] = res_all
-        for i in range(5):
-            w[f"res{i}a"], w[f"res{i}b"] = res_all[2 * i], res_all[2 * i + 1]
-        w["up1"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up1.upsample_conv.weight"], dt)
-        w["up2"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up2.upsample_conv.weight"], dt)
-        if self.use_tc and FINAL_STREAM:
-            w["final_stream"] = gp("final_stream", lambda t: pack_final_stream(t, f64), p["final_conv.conv.weight"], dt)
-        w["final"] = (gp("final_rowsum", lambda t: pack_final_rowsum(t, f64), p["final_conv.conv.weight"], dt) if self.use_tc
-                      else gp("final_plain", lambda t: pack_final_plain(t, f64), p["final_conv.conv.weight"], dt))
-        self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
-        self.final_bias[:3] = p["final_conv.conv.bias"].float()
+        dev = p[names[0]].device
+        res_all = torch.empty((10, 256, 9 * 256), dtype=dt, device=dev)
+        # Training re-packs every step (the optimizer just changed the weights): only conv1 / conv2 are needed at once, so the
+        # trunk / decoder weights (~25 us of re-layout kernels) are packed on a side branch that forward() joins in front of
+        # the first residual block -- they run under conv1 / norm1 / conv2 / norm2 instead of in front of them.
+        side = None
+        if for_backward and dev.type == "cuda":
+            main = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            stacked = torch.stack([p[n] for n in names])                          # (10, O, C, 3, 3)
+            res_all.view(10, 256, 3, 3, 256).copy_(stacked.permute(0, 1, 3, 4, 2))
+            w["res_all"] = res_all
+            for i in range(5):
+                w[f"res{i}a"], w[f"res{i}b"] = res_all[2 * i], res_all[2 * i + 1]
+            w["up1"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up1.upsample_conv.weight"], dt)
+            w["up2"] = gp("convT", lambda t: pack_conv_transpose(t, f64), p["up2.upsample_conv.weight"], dt)
+            if self.use_tc and FINAL_STREAM:
+                w["final_stream"] = gp("final_stream", lambda t: pack_final_stream(t, f64), p["final_conv.conv.weight"], dt)
+            w["final"] = (gp("final_rowsum", lambda t: pack_final_rowsum(t, f64), p["final_conv.conv.weight"], dt) if self.use_tc
+                          else gp("final_plain", lambda t: pack_final_plain(t, f64), p["final_conv.conv.weight"], dt))
+            self.final_bias = torch.zeros(16, dtype=torch.float32, device=w["final"].device)
+            self.final_bias[:3] = p["final_conv.conv.bias"].float()
+        self._wpack_stream = side
         self.w = w
         self._pack_for_backward(for_backward)
         return self
+
+    def _join_weight_pack(self, dev) -> None:
+        side = getattr(self, "_wpack_stream", None)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._wpack_stream = None
 
     def _pack_for_backward(self, for_backward: bool) -> None:
         if for_backward and self.w["final"].is_cuda:
@@ -345,6 +364,7 @@ class StyleNetPlan:
             tape["w"] = dict(buf2=buf2_b, trunk=[cur_b], mid=[], act4_flat=flat_b)
 
         # residual trunk
+        self._join_weight_pack(dev)          # trunk / decoder weights packed on the side branch of pack(for_backward=True)
         taps9 = taps_kxk(3)
         for i in range(5):
             raw_a, st_a = new(B, H2, W2, 256), stats(256)
