@@ -271,7 +271,11 @@ def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.
     dy = dy.contiguous().float()
     B, _, H4, W4 = dy.shape
     layout, staging_total = _staging_layout(tc)
-    staging = torch.zeros(staging_total, dtype=torch.float32, device=dev)       # split-K targets of every weight gradient: ONE memset
+    # split-K targets of every weight gradient: ONE memset.  On the tensor-core path every writer of this buffer runs on the
+    # weight-gradient side branch, so the 25 MB fill is issued there too (first side block) instead of in front of the first
+    # data gradient.
+    side_zero = tc and os.environ.get("FNST_WGRAD_STREAM", "1") != "0"
+    staging = (torch.empty if side_zero else torch.zeros)(staging_total, dtype=torch.float32, device=dev)
 
     def slot(name):
         off, shape = layout[name]
@@ -359,12 +363,15 @@ def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.
         #  wgrad (8-channel copy: one pixel = 16 bytes, 8 pixels = one 128-byte row): contraction over halo positions p; M side = 16-pixel dy window (128 = 16 px x 8 ch) at p, N side = act4
         #         pixel-pair window at p + (kh-8, 0): D[(i,j)][kh*64 + jj*32 + c] = dW[j][c][kh][jj+8-i]  (9 taps)
         rows_g, pitch_g = H4 + 16, W4 + 16
-        g8 = ops.image_to_halo(dy, 8, PAD_ZERO, 8, rows_g, pitch_g, gdt)
         g_str = (rows_g * pitch_g * 8, pitch_g * 8, 8)
         flat_act = tape["act4_flat"]
         taps9 = [(kh - 8, 0, 0) for kh in range(9)]
-        with on_side(g8, flat_act, dy):
+        with on_side(flat_act, dy, staging):
+            if side_zero:
+                staging.zero_()
             ops.channel_sum(dy, out=slot("final_bias"))          # d bias of final_conv: nothing downstream needs it
+            g8 = ops.image_to_halo(dy, 8, PAD_ZERO, 8, rows_g, pitch_g, gdt)
+            keep_alive.append(g8)
             a_g = flat_act
             if a_g.dtype != gdt:
                 a_g = wtw.get("act4_flat") if wtw.get("act4_flat") is not None else ops.cast(flat_act, gdt)
@@ -472,8 +479,9 @@ def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.
         rows, pitch = 2 * (H1 + 4), (x.shape[3] + 8 + 1) // 2 * 2
         img = ops.image_to_halo(x, 4, PAD_REFLECT, 4, rows, pitch, gdt)
         taps = [(kh >> 1, 0, (kh & 1) * pitch * 4) for kh in range(9)]
-        ops.wgrad(ConvSpec(taps, 64, None, 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64), (rows * pitch * 4, 2 * pitch * 4, 8),
-                  d_raw1, (H1, W1), use_tc=True, out=slot("conv1"), out_zeroed=True)
+        with on_side(img, d_raw1):           # (on the side branch like every other writer of the staging buffer)
+            ops.wgrad(ConvSpec(taps, 64, None, 64, 64), img, (B, H1 + 4, W1, pitch * 4 + 64), (rows * pitch * 4, 2 * pitch * 4, 8),
+                      d_raw1, (H1, W1), use_tc=True, out=slot("conv1"), out_zeroed=True)
     else:
         ops.conv_first_wgrad(tape["x"], d_raw1, 9, 2, 4, PAD_REFLECT, out=slot("conv1"))             # tap-major (243, 64)
     if side_stream is not None:
