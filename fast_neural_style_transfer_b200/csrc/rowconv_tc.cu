@@ -13,7 +13,9 @@
 //     shared-memory address, so a row-shifted start needs nothing else) -- no im2col, no re-load; the three vertical taps are the three newest ring
 //     entries.  Zero padding = TMA out-of-bounds fill (rows and columns).  (First version: un-swizzled core-matrix rows
 //     filled by TMA boxes with a 16-byte inner extent -- measured ~5 clocks per 16-byte piece, 3 us per input row: TMA-bound.)
-//   * one output row = 36 MMAs M128 (pixels) x N x K16 into one TMEM slot of a ring of 512/N slots; two groups of four
+//   * one output row = 36 MMAs M128 (pixels) x N x K16 into one TMEM slot of a ring of 512/N slots (N = 64: TWO output rows per
+//     128-column slot -- the two middle rows of the four-row input window feed both of them with one N = 128 MMA against the
+//     stacked weight blocks, 48 MMAs per row pair instead of 72); two groups of four
 //     epilogue warps take alternate output rows (tcgen05.ld -> bias / ReLU or the data-gradient form (acc + addend) * (mask > 0)
 //     -> 16-byte NHWC stores), so the latency of the mask / addend loads of one row hides under the next row's MMAs.
 // Work split: the (image, strip, output row) units are cut into equal CONTIGUOUS ranges, one per SM -- 2048 row units on 148
@@ -33,7 +35,12 @@ constexpr int RC_EPI_GROUPS = 2;
 template <int N> struct RcCfg {
   static constexpr int W_BYTES = 9 * N * 128;                     // [tap][j][64 channels], 128-byte swizzled rows
   static constexpr int RING = N == 64 ? 8 : 4;                    // input rows resident in shared memory
-  static constexpr int SLOTS = 512 / N;                           // TMEM accumulator slots (output rows in flight)
+  // N = 64: a TMEM slot holds TWO output rows (columns [0,64) = row y, [64,128) = row y+1): the two middle input rows of the
+  // four-row window feed both of them with ONE N = 128 MMA against the stacked weight blocks [W(kh) ; W(kh-1)] -- 48 MMAs per
+  // row pair instead of 72, and an M128 x K16 MMA costs ~64-76 clocks of A-operand read whatever its N (header comment).
+  static constexpr bool PAIRED = N == 64;
+  static constexpr int SLOT_COLS = PAIRED ? 128 : N;
+  static constexpr int SLOTS = 512 / SLOT_COLS;                   // TMEM accumulator slots (units in flight)
   static constexpr int SMEM = W_BYTES + RING * RC_ROW_STRIDE + 1024 + 512;
 };
 
@@ -42,7 +49,7 @@ struct RowConvParams {
   int32_t strips, units;                 // units = n_img * strips * out_h
   int32_t base_h, base_w;                // input coordinate of tap (kh, kw) = (0, 0) relative to the output pixel
   int32_t relu, out_is_bf16, mask_dtype, dbg_mode;
-  uint32_t idesc;
+  uint32_t idesc, idesc_wide;            // MMA instruction descriptors for N and (paired rows) 2N columns
   int8_t tap_of[9];                      // descriptor tap index of kernel position kh * 3 + kw
   void* out;
   const float* bias;
@@ -77,13 +84,17 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   __shared__ float s_bias[N];                           // broadcast reads in the epilogue instead of N global loads per pixel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Paired rows: who stores what.  Data-gradient form (addend / mask loads: the epilogue is latency-bound on them) -- BOTH warp
+  // groups work on every unit, group g on its row g, so the unit's two rows proceed concurrently (measured 61 vs 66 us);
+  // plain form -- the groups take alternate units (23 vs 25 us).
+  const bool split_rows = Cfg::PAIRED && (p.addend != nullptr || p.mask != nullptr);
 
   pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < RING; ++s) { mbar_init(&loaded[s], 1); mbar_init(&freed[s], 1); }
-    for (int s = 0; s < SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], split_rows ? 8 : 4); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
@@ -115,7 +126,11 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ===================== TMA producer =====================
     if (lane == 0 && u_begin < u_end) {
       mbar_arrive_expect_tx(w_bar, Cfg::W_BYTES);
-      for (int t = 0; t < 9; ++t) tma_load_2d(s_w + t * (N * 128), &map_b, w_bar, t * 64, 0);      // {64 k, N outputs} per tap
+      // {64 k, N outputs} per tap, stored [kw][kh = 2, 1, 0]: the blocks of two vertically adjacent taps are consecutive rows of
+      // one wider B operand (paired rows)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          tma_load_2d(s_w + (kw * 3 + (2 - kh)) * (N * 128), &map_b, w_bar, p.tap_of[kh * 3 + kw] * 64, 0);
       uint32_t g = 0;                                    // running input-row count = ring position
       for (int u = u_begin; u < u_end;) {
         int n, x0, y0, rows;
@@ -139,37 +154,61 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) da_kw[kw] = umma_desc_sw128_rowshift(smem_u32(s_in) + kw * 128);
       const uint64_t db_base = umma_smem_desc(smem_u32(s_w), 16, 1024);
-      uint32_t tap_off[9];                               // (addr >> 4) offset of each kernel position's weight block
-#pragma unroll
-      for (int i = 0; i < 9; ++i) tap_off[i] = (uint32_t)p.tap_of[i] * (N * 128 >> 4);
+      constexpr uint32_t BLK = N * 128 >> 4;             // (addr >> 4) size of one weight block [N outputs][64 channels]
       mbar_wait(w_bar, 0);
       tc_fence_after();
-      uint32_t g0 = 0, waited = 0, o = 0;                // first input row of the segment; input rows already waited for; output row count
+      uint32_t g0 = 0, waited = 0, o = 0;                // first input row of the segment; input rows already waited for; unit count
       for (int u = u_begin; u < u_end;) {
         int n, x0, y0, rows;
         segment(u, n, x0, y0, rows);
-        for (int j = 0; j < rows; ++j, ++o) {
+        for (int j = 0; j < rows; ++o) {
+          const int nr = (Cfg::PAIRED && j + 1 < rows) ? 2 : 1;            // output rows of this unit
           const uint32_t s = o % SLOTS;
           mbar_wait_spin(&acc_empty[s], ((o / SLOTS) & 1) ^ 1);
-          while (waited <= g0 + j + 2) { mbar_wait_spin(&loaded[waited % RING], (waited / RING) & 1); ++waited; }
+          while (waited <= g0 + j + nr + 1) { mbar_wait_spin(&loaded[waited % RING], (waited / RING) & 1); ++waited; }
           tc_fence_after();
           stamp(o < 64 ? 64 + (int)o : 1000);
-          const uint32_t d_tmem = tmem_base + s * N;
+          const uint32_t d_tmem = tmem_base + s * Cfg::SLOT_COLS;
+          auto row_desc = [&](int r, int kw) { return da_kw[kw] + (uint64_t)(((g0 + j + r) % RING) * (RC_ROW_STRIDE >> 4)); };
+          if (nr == 2) {
+            // window rows r = 0..3; r = 1, 2 feed both output rows (N = 2 x 64 against [W(r) ; W(r-1)]), r = 0 only the first
+            // (W0 into columns [0,64)), r = 3 only the second (W2 into columns [64,128)).  The first MMA issued must cover all
+            // 128 columns with accumulate = 0, so the wide rows go first.
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const uint64_t row_off = (uint64_t)(((g0 + j + kh) % RING) * (RC_ROW_STRIDE >> 4));
+            for (int r = 1; r <= 2; ++r)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint64_t da = row_desc(r, kw), db = db_base + (uint64_t)((kw * 3 + (2 - r)) * BLK);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_f16(d_tmem, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), p.idesc_wide, (r != 1 || kw != 0 || ks != 0) ? 1u : 0u);
+              }
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              const uint64_t da = da_kw[kw] + row_off, db = db_base + (uint64_t)tap_off[kh * 3 + kw];
+              const uint64_t da0 = row_desc(0, kw), db0 = db_base + (uint64_t)((kw * 3 + 2) * BLK);      // W0
+              const uint64_t da3 = row_desc(3, kw), db3 = db_base + (uint64_t)((kw * 3 + 0) * BLK);      // W2
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)          // 16 K-elements = 32 bytes further inside the 128-byte row: +2 in the (addr >> 4) field
-                umma_f16(d_tmem, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), p.idesc, (kh | kw | ks) != 0 ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_f16(d_tmem, da0 + (uint64_t)(2 * ks), db0 + (uint64_t)(2 * ks), p.idesc, 1u);
+                umma_f16(d_tmem + N, da3 + (uint64_t)(2 * ks), db3 + (uint64_t)(2 * ks), p.idesc, 1u);
+              }
             }
+          } else {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint64_t da = row_desc(kh, kw), db = db_base + (uint64_t)((kw * 3 + (2 - kh)) * BLK);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)          // 16 K-elements = 32 bytes further inside the 128-byte row: +2 in the (addr >> 4) field
+                  umma_f16(d_tmem, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), p.idesc, (kh | kw | ks) != 0 ? 1u : 0u);
+              }
           }
           umma_commit(&acc_full[s]);
           stamp(o < 64 ? 128 + (int)o : 1000);
-          // (the input rows this output row read for the last time are handed back to the producer by the epilogue, which
-          // observes the same completion through acc_full: one tcgen05.commit per row on this thread instead of two to four)
+          // (the input rows this unit read for the last time are handed back to the producer by the epilogue, which observes
+          // the same completion through acc_full: one tcgen05.commit per unit on this thread)
+          j += nr;
         }
         g0 += rows + 2;
         u += rows;
@@ -190,62 +229,75 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       rows_prev = rows;
       const int x = x0 + q * 32 + lane;
       const bool valid = x < p.out_w;
-      for (int j = 0; j < rows; ++j, ++o) {
-        if ((int)(o % RC_EPI_GROUPS) != grp) continue;
+      for (int j = 0; j < rows; ++o) {
+        const int nr = (Cfg::PAIRED && j + 1 < rows) ? 2 : 1;              // output rows of this unit (same walk as the MMA issuer)
+        const int jj = j;
+        j += nr;
+        if (!split_rows && (int)(o % RC_EPI_GROUPS) != grp) continue;      // alternate units per warp group (see split_rows)
         const uint32_t s = o % SLOTS;
         mbar_wait_spin(&acc_full[s], (o / SLOTS) & 1);
         tc_fence_after();
-        if (q == 0 && lane == 0) {
-          // all MMAs up to this output row have completed: input row j (its kh = 0 row) is dead, and so are the two rows
-          // below it once the segment ends
-          mbar_arrive(&freed[(g0 + j) % RING]);
-          if (j == rows - 1) { mbar_arrive(&freed[(g0 + j + 1) % RING]); mbar_arrive(&freed[(g0 + j + 2) % RING]); }
+        if (split_rows && grp >= nr) {                     // single-row unit: the second group only releases the slot
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[s]);
+          continue;
+        }
+        if (q == 0 && lane == 0 && (!split_rows || grp == 0)) {
+          // all MMAs up to this unit have completed: its first nr input rows are dead, and so are the two rows below them
+          // once the segment ends
+          for (int r = 0; r < nr; ++r) mbar_arrive(&freed[(g0 + jj + r) % RING]);
+          if (jj + nr == rows) { mbar_arrive(&freed[(g0 + rows) % RING]); mbar_arrive(&freed[(g0 + rows + 1) % RING]); }
         }
         if (threadIdx.x == 64 || threadIdx.x == 192) stamp(o < 64 ? 192 + (int)o : 1000);
-        const size_t off = (((size_t)n * p.out_h + (y0 + j)) * p.out_w + x) * N;
 #pragma unroll 1
-        for (int cb = 0; cb < N; cb += 32) {
-          uint32_t raw[32];
-          tmem_ld_x32(t_lane + s * N + cb, raw);
-          tmem_ld_wait();
-          if (cb + 32 >= N) {                              // accumulator fully read: hand the slot back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[s]);
-          }
-          if (!valid || (p.dbg_mode & 8)) continue;
-          float v[32];
+        for (int half = 0; half < nr; ++half) {
+          if (split_rows && half != grp) continue;
+          const size_t off = (((size_t)n * p.out_h + (y0 + jj + half)) * p.out_w + x) * N;
+#pragma unroll 1
+          for (int cb = 0; cb < N; cb += 32) {
+            uint32_t raw[32];
+            tmem_ld_x32(t_lane + s * Cfg::SLOT_COLS + half * N + cb, raw);
+            tmem_ld_wait();
+            if ((split_rows || half == nr - 1) && cb + 32 >= N) {       // this warp has read all it needs: hand the slot back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[s]);
+            }
+            if (!valid || (p.dbg_mode & 8)) continue;
+            float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += s_bias[cb + i];
-          if (p.relu) {
+            for (int i = 0; i < 32; ++i) v[i] += s_bias[cb + i];
+            if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.addend || p.mask) {
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (p.addend || p.mask) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                float t[8];
+                if (p.addend) {
+                  load8_dyn(p.addend, p.out_is_bf16 ? FNST_BF16 : FNST_F16, off + cb + i, t);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[i + k] += t[k];
+                }
+                if (p.mask) {
+                  load8_dyn(p.mask, p.mask_dtype, off + cb + i, t);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[i + k] = t[k] > 0.f ? v[i + k] : 0.f;
+                }
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               float t[8];
-              if (p.addend) {
-                load8_dyn(p.addend, p.out_is_bf16 ? FNST_BF16 : FNST_F16, off + cb + i, t);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[i + k] += t[k];
-              }
-              if (p.mask) {
-                load8_dyn(p.mask, p.mask_dtype, off + cb + i, t);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[i + k] = t[k] > 0.f ? v[i + k] : 0.f;
-              }
+              for (int k = 0; k < 8; ++k) t[k] = v[i + k];
+              if (p.out_is_bf16) store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + cb + i, t);
+              else store8<__half>(reinterpret_cast<__half*>(p.out) + off + cb + i, t);
             }
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float t[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t[k] = v[i + k];
-            if (p.out_is_bf16) store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + cb + i, t);
-            else store8<__half>(reinterpret_cast<__half*>(p.out) + off + cb + i, t);
           }
         }
         if (threadIdx.x == 64 || threadIdx.x == 192) stamp(o < 64 ? 256 + (int)o : 1000);
@@ -310,6 +362,7 @@ int rowconv_tc(const fnst_conv_desc* d, int device, cudaStream_t st) {
   p.dbg = tuning().debug_buf;
   p.relu = d->relu; p.out_is_bf16 = d->out_dtype == FNST_BF16; p.mask_dtype = d->mask_dtype;
   p.idesc = umma_idesc_f16(d->dtype == FNST_BF16 ? 1 : 0, d->n_gemm, 0, 0);
+  p.idesc_wide = umma_idesc_f16(d->dtype == FNST_BF16 ? 1 : 0, 2 * d->n_gemm, 0, 0);
   p.out = d->out; p.bias = d->bias; p.addend = d->addend; p.mask = d->mask;
 
   CUtensorMap ma, mb;
