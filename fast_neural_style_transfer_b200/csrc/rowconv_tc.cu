@@ -235,6 +235,18 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         j += nr;
         if (!split_rows && (int)(o % RC_EPI_GROUPS) != grp) continue;      // alternate units per warp group (see split_rows)
         const uint32_t s = o % SLOTS;
+        // Data-gradient form: this thread's 128-byte addend and mask rows are requested BEFORE the wait for the accumulator, so
+        // their memory latency (the epilogue's bound: 134 MB per launch against 20 us of MMA work) runs under the unit's MMAs
+        uint4 pre_a[N == 64 ? 8 : 1], pre_m[N == 64 ? 8 : 1];
+        const bool prefetch = N == 64 && split_rows && grp < nr && valid && !(p.dbg_mode & 8) && (!p.mask || p.mask_dtype != FNST_F32);
+        if (N == 64 && prefetch) {
+          const size_t off = (((size_t)n * p.out_h + (y0 + jj + grp)) * p.out_w + x) * N;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (p.addend) pre_a[i] = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.addend) + off)[i];
+            if (p.mask) pre_m[i] = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.mask) + off)[i];
+          }
+        }
         mbar_wait_spin(&acc_full[s], (o / SLOTS) & 1);
         tc_fence_after();
         if (split_rows && grp >= nr) {                     // single-row unit: the second group only releases the slot
@@ -250,11 +262,11 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (jj + nr == rows) { mbar_arrive(&freed[(g0 + rows) % RING]); mbar_arrive(&freed[(g0 + rows + 1) % RING]); }
         }
         if (threadIdx.x == 64 || threadIdx.x == 192) stamp(o < 64 ? 192 + (int)o : 1000);
-#pragma unroll 1
-        for (int half = 0; half < nr; ++half) {
-          if (split_rows && half != grp) continue;
+#pragma unroll
+        for (int half = 0; half < (Cfg::PAIRED ? 2 : 1); ++half) {
+          if (half >= nr || (split_rows && half != grp)) continue;
           const size_t off = (((size_t)n * p.out_h + (y0 + jj + half)) * p.out_w + x) * N;
-#pragma unroll 1
+#pragma unroll
           for (int cb = 0; cb < N; cb += 32) {
             uint32_t raw[32];
             tmem_ld_x32(t_lane + s * Cfg::SLOT_COLS + half * N + cb, raw);
@@ -274,7 +286,24 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (p.addend || p.mask) {
+            if (N == 64 && prefetch) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                float t[8];
+                if (p.addend) {
+                  if (p.out_is_bf16) { Raw8<__nv_bfloat16> r; r.u = pre_a[(cb + i) >> 3]; raw8_to_f32<__nv_bfloat16>(r, t); }
+                  else { Raw8<__half> r; r.u = pre_a[(cb + i) >> 3]; raw8_to_f32<__half>(r, t); }
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[i + k] += t[k];
+                }
+                if (p.mask) {
+                  if (p.mask_dtype == FNST_BF16) { Raw8<__nv_bfloat16> r; r.u = pre_m[(cb + i) >> 3]; raw8_to_f32<__nv_bfloat16>(r, t); }
+                  else { Raw8<__half> r; r.u = pre_m[(cb + i) >> 3]; raw8_to_f32<__half>(r, t); }
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[i + k] = t[k] > 0.f ? v[i + k] : 0.f;
+                }
+              }
+            } else if (p.addend || p.mask) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
                 float t[8];
