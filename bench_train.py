@@ -105,6 +105,18 @@ def run(args, wl, net, rank, world, dev, peaks):
     norm = B.time_norm_kernels(dev, peaks)
     if rank != 0:
         return None
+    # DRAM traffic of the dominant kernel per launch: from the ncu --set full capture of THIS command kept under profiles/
+    # (ncu cannot run inside a timed bench run); null when the capture is not there
+    traffic, traffic_note = None, "not measured in this run (needs ncu); profiles/ holds the ncu --set full capture of this kernel"
+    try:
+        for row in json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_conv_tc.json"))):
+            if "conv_tc_kernel<256, 0>" in row["kernel"] and row["grid"].startswith("(128"):
+                traffic = row["dram_read_bytes"] + row["dram_write_bytes"]
+                traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r02_ncu_conv_tc.json (ncu --set full "
+                                "--clock-control none of `bench.py --workload train`, cold cache per replay); algorithmic bytes = 8.9 MB "
+                                "halo activations + 1.2 MB weights read, 8.4 MB output written (stays in L2)")
+    except Exception:
+        pass
     value = world * args.steps / (ms / 1e3)
     line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
@@ -119,8 +131,8 @@ def run(args, wl, net, rank, world, dev, peaks):
             "whole_step_tflops": value * bsz * B.TRAIN_GFLOP_IMG / 1e3 / world,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (3x3 256->256 residual conv; forward launch, batch 4)",
                          "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tf_burst"], "frac_of_sustained_peak": achieved / peaks["tf_sustained"], "traffic": None,
-                         "traffic_note": "not measured in this run (needs ncu); profiles/ holds the ncu --set full capture of this kernel",
+                         "frac": achieved / peaks["tf_burst"], "frac_of_sustained_peak": achieved / peaks["tf_sustained"], "traffic": traffic,
+                         "traffic_note": traffic_note,
                          "peak_source": peaks["src"] + " (burst bf16/fp16: the kernel is timed alone, ~20 ms of back-to-back launches)",
                          "launches_timed": k_launches, "kernel_ms": k_ms,
                          "kernel_share_of_step": (k_ms * 30) / (ms / args.steps),
