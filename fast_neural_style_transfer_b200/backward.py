@@ -460,18 +460,30 @@ def stylenet_backward_stages(plan: "engine.StyleNetPlan", tape: dict, dy: torch.
             yield dict(staging=staging, sums=arena.buf, norm_sums=dict(norm_sums), batch=B, tc=tc)
 
     # ---- norm2 + conv2 (stride 2 on the space-to-depth buffer) ---------------------------------------------
-    d_raw2, _ = inorm_backward("norm2", gsrc, extra, tape["raw2"], tape["st2"], None, True, 1, PAD_REFLECT, gsrc_slack=Z)
+    # conv2's data gradient lives on the (H2+1) x (W2+1) space-to-depth domain (65 x 65 at 256x256: 180 ragged boxes); same
+    # pixel-stream form as the trunk with a 1-pixel zero halo around d_raw2: 4 * 66 * 66 / 128 = 137 full tiles
+    Z2 = 1 if lin else 0
+    d_raw2, _ = inorm_backward("norm2", gsrc, extra, tape["raw2"], tape["st2"], None, True, 1, PAD_REFLECT, gsrc_slack=Z, out_pad=Z2)
     buf2 = tape["buf2"]
     Hs, Ws = buf2.shape[1], buf2.shape[2]
     with on_side(buf2, d_raw2):
-        wgrad(ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, wtw.get("buf2"), (B, Hs, Ws, 256), d_raw2, (H2, W2), slot("conv2"))
-    d_buf2 = torch.empty((B, Hs, Ws, 256), dtype=gdt, device=dev)
-    ops.conv_gather(ConvSpec(_neg(TAPS_2X2), 256, wd_all["conv2"], 256, 256), d_raw2, (B, H2, W2, 256), _nhwc_strides(d_raw2), d_buf2,
-                    (Hs, Ws), None, tc)
+        wgrad(ConvSpec(taps_s2d_3x3(64), 64, None, 256, 256), buf2, wtw.get("buf2"), (B, Hs, Ws, 256), d_raw2, (H2, W2), slot("conv2"), g_pad=Z2)
+    if lin and Hs == H2 + 1 and Ws == W2 + 1:
+        m2 = B * (H2 + 2) * (W2 + 2)
+        d_buf2 = torch.empty((B, H2 + 2, W2 + 2, 256), dtype=gdt, device=dev)          # [:, :Hs, :Ws] holds the gradient
+        ops.conv_gather(ConvSpec([(1 - dh, 1 - dw, 0) for dh, dw, _ in TAPS_2X2], 256, wd_all["conv2"], 256, 256), d_raw2, (1, 1, m2, 256),
+                        (m2 * 256, (W2 + 2) * 256, 256), d_buf2, (1, m2), None, True, linear=True)
+        slack1 = 1
+    else:
+        g2 = d_raw2[:, Z2:Z2 + H2, Z2:Z2 + W2, :].contiguous() if Z2 else d_raw2
+        d_buf2 = torch.empty((B, Hs, Ws, 256), dtype=gdt, device=dev)
+        ops.conv_gather(ConvSpec(_neg(TAPS_2X2), 256, wd_all["conv2"], 256, 256), g2, (B, H2, W2, 256), _nhwc_strides(g2), d_buf2,
+                        (Hs, Ws), None, tc)
+        slack1 = 0
 
     # ---- norm1 + conv1 -----------------------------------------------------------------------------------------
     raw1 = tape["raw1"]
-    d_raw1, _ = inorm_backward("norm1", d_buf2, None, raw1, tape["st1"], None, True, 1, PAD_REFLECT, s2d=True)
+    d_raw1, _ = inorm_backward("norm1", d_buf2, None, raw1, tape["st1"], None, True, 1, PAD_REFLECT, s2d=True, gsrc_slack=slack1)
     if tc:
         # same window view as the forward (engine.StyleNetPlan.forward): taps = kernel rows, 16-pixel x 4-channel windows
         x = tape["x"]
