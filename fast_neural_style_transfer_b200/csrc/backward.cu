@@ -824,16 +824,28 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const TA* __restrict_
     const int wo = r % Wc; r /= Wc;
     const int ho = r % Hc; const int n = r / Hc;
     const bool pooled = ho < Ho && wo < Wo;      // odd trailing row/column is not covered by any window
-    float go[8];
-    if (pooled) load8<TG>(gout + (((size_t)n * Ho + ho) * Wo + wo) * C + cg * 8, go);
-    float v[4][8];
+    // all loads of the window (pooled gradient, four inputs, four residual-branch gradients) are issued before any of them
+    // is used: one round trip to memory instead of two (the residual loads used to wait for the arg-max of the inputs)
+    Raw8<TG> go_r, ex_r[4];
+    Raw8<TA> in_r[4];
     bool ok[4];
+    if (pooled) go_r = load_raw8<TG>(gout + (((size_t)n * Ho + ho) * Wo + wo) * C + cg * 8);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int hh = 2 * ho + (q >> 1), ww = 2 * wo + (q & 1);
       ok[q] = hh < H && ww < W;
-      if (ok[q]) load8<TA>(in + (((size_t)n * H + hh) * W + ww) * C + cg * 8, v[q]);
+      if (ok[q]) {
+        const size_t idx = (((size_t)n * H + hh) * W + ww) * C + cg * 8;
+        in_r[q] = load_raw8<TA>(in + idx);
+        if (extra) ex_r[q] = load_raw8<TG>(extra + idx);
+      }
     }
+    float go[8];
+    if (pooled) raw8_to_f32<TG>(go_r, go);
+    float v[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (ok[q]) raw8_to_f32<TA>(in_r[q], v[q]);
     int best[8];
     if (pooled) {
 #pragma unroll
@@ -850,7 +862,7 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const TA* __restrict_
       const int hh = 2 * ho + (q >> 1), ww = 2 * wo + (q & 1);
       const size_t idx = (((size_t)n * H + hh) * W + ww) * C + cg * 8;
       float o[8];
-      if (extra) load8<TG>(extra + idx, o);
+      if (extra) raw8_to_f32<TG>(ex_r[q], o);
       else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = 0.f;
